@@ -1,0 +1,226 @@
+// extern "C" surface of libtrxlppo (declared in include/trxl_ppo.h).  Thin argument marshalling only.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/trxl_ppo.h"
+#include "attention.cuh"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+#include "model.cuh"
+#include "ppo.cuh"
+
+static thread_local char g_err[512] = "";
+
+void trxl_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+typedef const long long* cll;
+
+static int branch_spec(const int32_t* sizes, int n, BranchSpec& bs, int* sumA) {
+    TRXL_CHECK_ARG(sizes && n >= 1 && n <= TRXL_MAX_BRANCHES, "bad branch spec (n=%d)", n);
+    bs.n = n;
+    int off = 0;
+    for (int k = 0; k < n; ++k) {
+        TRXL_CHECK_ARG(sizes[k] > 0, "branch %d has no actions", k);
+        bs.off[k] = off; bs.size[k] = sizes[k]; off += sizes[k];
+    }
+    *sumA = off;
+    return TRXL_OK;
+}
+
+extern "C" {
+
+const char* trxl_last_error(void) { return g_err; }
+int trxl_abi_version(void) { return TRXL_ABI_VERSION; }
+
+int trxl_layout_num_entries(const trxl_model_config* cfg) {
+    std::vector<trxl_param_entry> e;
+    int rc = model_layout(cfg, e, nullptr, nullptr);
+    return rc == TRXL_OK ? (int)e.size() : rc;
+}
+int64_t trxl_layout_total_floats(const trxl_model_config* cfg) {
+    std::vector<trxl_param_entry> e;
+    long long total = 0;
+    int rc = model_layout(cfg, e, &total, nullptr);
+    return rc == TRXL_OK ? total : rc;
+}
+int trxl_layout_entry(const trxl_model_config* cfg, int index, trxl_param_entry* out) {
+    std::vector<trxl_param_entry> e;
+    TRXL_PROPAGATE(model_layout(cfg, e, nullptr, nullptr));
+    TRXL_CHECK_ARG(out && index >= 0 && index < (int)e.size(), "layout entry %d out of range", index);
+    *out = e[index];
+    return TRXL_OK;
+}
+int trxl_layout_groups(const trxl_model_config* cfg) {
+    std::vector<trxl_param_entry> e;
+    int g = 0;
+    int rc = model_layout(cfg, e, nullptr, &g);
+    return rc == TRXL_OK ? g : rc;
+}
+int64_t trxl_workspace_floats(const trxl_model_config* cfg, int N) { return model_workspace_floats(cfg, N); }
+
+int trxl_model_forward(const trxl_model_config* cfg, const float* params, const float* feat, const float* table, int64_t slots,
+                       const int64_t* ep_index, const int64_t* win_index, const uint8_t* mask, const int64_t* pe_index,
+                       const int64_t* sample_index, const float* pe_table, int N, float* workspace, float* logits, float* value,
+                       float* out_mem, void* stream) {
+    ModelIO io;
+    io.N = N; io.feat = feat; io.table = table; io.slots = slots; io.ep_index = (cll)ep_index; io.win_index = (cll)win_index;
+    io.mask = mask; io.pe_index = (cll)pe_index; io.sample_index = (cll)sample_index; io.pe_table = pe_table;
+    return model_forward(cfg, params, io, workspace, logits, value, out_mem, S(stream));
+}
+
+int trxl_model_backward(const trxl_model_config* cfg, const float* params, float* grads, const float* feat, const float* table,
+                        int64_t slots, const int64_t* ep_index, const int64_t* win_index, const uint8_t* mask,
+                        const int64_t* pe_index, const int64_t* sample_index, const float* pe_table, int N, float* workspace,
+                        const float* out_mem, const float* dlogits, const float* dvalue, float* dfeat, void* stream) {
+    ModelIO io;
+    io.N = N; io.feat = feat; io.table = table; io.slots = slots; io.ep_index = (cll)ep_index; io.win_index = (cll)win_index;
+    io.mask = mask; io.pe_index = (cll)pe_index; io.sample_index = (cll)sample_index; io.pe_table = pe_table;
+    return model_backward(cfg, params, grads, io, workspace, out_mem, dlogits, dvalue, dfeat, S(stream));
+}
+
+static AttnArgs make_attn(const float* table, int64_t slots, int num_blocks, int block, const int64_t* ep_index,
+                          const int64_t* win_index, const uint8_t* mask, const int64_t* pe_index, const int64_t* sample_index,
+                          const float* pe_table, const float* qk, const float* qkb, int ln, int N, int L, int D, int H,
+                          float* probs, float* ctx) {
+    AttnArgs a;
+    a.N = N; a.L = L; a.D = D; a.H = H; a.B = num_blocks; a.blk = block; a.table = table; a.slots = slots;
+    a.ep_index = (cll)ep_index; a.win_index = (cll)win_index; a.mask = mask; a.pe_index = pe_table ? (cll)pe_index : nullptr;
+    a.pe = pe_table; a.sample_index = (cll)sample_index; a.qk = qk; a.qkb = qkb; a.ln = ln;
+    a.scale = (float)sqrt((double)D); a.probs = probs; a.ctx = ctx;
+    return a;
+}
+
+int trxl_window_attention_forward(const float* table, int64_t slots, int num_blocks, int block, const int64_t* ep_index,
+                                  const int64_t* win_index, const uint8_t* mask, const int64_t* pe_index,
+                                  const int64_t* sample_index, const float* pe_table, const float* qk, const float* qkb,
+                                  int layer_norm_rows, int N, int L, int D, int H, float* probs, float* ctx, void* stream) {
+    TRXL_CHECK_ARG(block >= 0 && block < num_blocks, "window_attention: block %d out of range", block);
+    return trxl_window_attn_fwd(make_attn(table, slots, num_blocks, block, ep_index, win_index, mask, pe_index, sample_index,
+                                          pe_table, qk, qkb, layer_norm_rows, N, L, D, H, probs, ctx), S(stream));
+}
+
+int trxl_window_attention_backward(const float* table, int64_t slots, int num_blocks, int block, const int64_t* ep_index,
+                                   const int64_t* win_index, const uint8_t* mask, const int64_t* pe_index,
+                                   const int64_t* sample_index, const float* pe_table, const float* qk, const float* probs,
+                                   const float* ctx, const float* dctx, int layer_norm_rows, int N, int L, int D, int H,
+                                   float* dqk, float* dqkb, float* dpe, void* stream) {
+    TRXL_CHECK_ARG(block >= 0 && block < num_blocks, "window_attention: block %d out of range", block);
+    AttnArgs a = make_attn(table, slots, num_blocks, block, ep_index, win_index, mask, pe_index, sample_index, pe_table, qk,
+                           nullptr, layer_norm_rows, N, L, D, H, const_cast<float*>(probs), const_cast<float*>(ctx));
+    AttnBwdArgs g;
+    g.dctx = dctx; g.dqk = dqk; g.dqkb = dqkb; g.dpe = dpe;
+    return trxl_window_attn_bwd(a, g, S(stream));
+}
+
+int trxl_linear_forward(const float* x, const float* W, const float* bias, float* y, int M, int N, int K, int relu, void* stream) {
+    TRXL_CHECK_ARG(x && W && y, "linear_forward: null pointer");
+    return gemm_nt(S(stream), M, N, K, x, K, W, K, y, N, bias, relu);
+}
+
+int trxl_linear_backward(const float* dy, const float* x, const float* W, float* dx, float* dW, float* db, int M, int N, int K,
+                         float* scratch, void* stream) {
+    TRXL_CHECK_ARG(dy, "linear_backward: null dy");
+    if (dx) { TRXL_CHECK_ARG(W, "linear_backward: dx needs W"); TRXL_PROPAGATE(gemm_nn(S(stream), M, K, N, dy, N, W, K, dx, K)); }
+    if (dW) { TRXL_CHECK_ARG(x, "linear_backward: dW needs x"); TRXL_PROPAGATE(gemm_tn(S(stream), N, K, M, dy, N, x, K, dW, K)); }
+    if (db) { TRXL_CHECK_ARG(scratch, "linear_backward: db needs scratch"); TRXL_PROPAGATE(ew_colsum(S(stream), dy, N, db, M, N, 1.f, 0, scratch)); }
+    return TRXL_OK;
+}
+
+int trxl_layernorm_forward(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd, int rows,
+                           int D, void* stream) {
+    TRXL_CHECK_ARG(x && gamma && beta && y, "layernorm_forward: null pointer");
+    return ew_layernorm_fwd(S(stream), x, D, nullptr, 0, gamma, beta, y, D, nullptr, 0, mean, rstd, rows, D);
+}
+
+int trxl_layernorm_backward(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, float* dx,
+                            float* dgamma, float* dbeta, float* scratch, int rows, int D, void* stream) {
+    TRXL_CHECK_ARG(dy && x && mean && rstd && gamma && dx, "layernorm_backward: null pointer");
+    TRXL_CHECK_ARG(!dgamma || (dbeta && scratch), "layernorm_backward: dgamma needs dbeta and scratch");
+    return ew_layernorm_bwd(S(stream), dy, D, x, D, mean, rstd, gamma, dx, D, 0, dgamma, dbeta, 0, scratch, rows, D);
+}
+
+int trxl_gather_window(const float* in, const int64_t* index, float* out, int64_t N, int L, int64_t slots, int64_t inner, void* stream) {
+    TRXL_CHECK_ARG(in && index && out, "gather_window: null pointer");
+    return ppo_gather_window(S(stream), in, (cll)index, out, N, L, slots, inner);
+}
+int trxl_gather_rows(const float* src, const int64_t* index, float* dst, int64_t rows, int64_t row_floats, void* stream) {
+    TRXL_CHECK_ARG(src && index && dst, "gather_rows: null pointer");
+    return ppo_gather_rows(S(stream), src, (cll)index, dst, rows, row_floats);
+}
+
+int trxl_gae(const float* rewards, const uint8_t* dones, const float* values, const float* last_value, float* advantages, int W,
+             int T, double gamma, double lamda, void* stream) {
+    TRXL_CHECK_ARG(rewards && dones && values && last_value && advantages, "gae: null pointer");
+    return ppo_gae(S(stream), rewards, dones, values, last_value, advantages, W, T, gamma, lamda);
+}
+
+int trxl_rollout_prepare(const int64_t* step, const int64_t* ep, const uint8_t* mask_table, const int64_t* index_table,
+                         uint8_t* mask_out, int64_t mask_stride, int64_t* idx_out, int64_t idx_stride, int64_t* ep_out,
+                         int64_t ep_stride, int W, int L, void* stream) {
+    TRXL_CHECK_ARG(step && mask_table && index_table && mask_out && idx_out, "rollout_prepare: null pointer");
+    return ppo_rollout_prepare(S(stream), (cll)step, (cll)ep, mask_table, (cll)index_table, mask_out, mask_stride,
+                               (long long*)idx_out, idx_stride, (long long*)ep_out, ep_stride, W, L);
+}
+
+int trxl_memory_scatter(float* table, const int64_t* ep, const int64_t* step, const float* new_mem, int W, int64_t slots,
+                        int64_t inner, void* stream) {
+    TRXL_CHECK_ARG(table && ep && step && new_mem, "memory_scatter: null pointer");
+    return ppo_memory_scatter(S(stream), table, (cll)ep, (cll)step, new_mem, W, slots, inner);
+}
+
+int trxl_sample_actions(const float* logits, const float* u, const int64_t* forced_actions, const int32_t* branch_sizes,
+                        int num_branches, int64_t* actions, int64_t act_stride, float* log_probs, int64_t logp_stride,
+                        int64_t* actions_compact, int W, void* stream) {
+    TRXL_CHECK_ARG(logits && (u || forced_actions) && actions && log_probs, "sample_actions: null pointer");
+    BranchSpec bs; int sumA = 0;
+    TRXL_PROPAGATE(branch_spec(branch_sizes, num_branches, bs, &sumA));
+    return ppo_sample_actions(S(stream), logits, sumA, u, (cll)forced_actions, bs, (long long*)actions, act_stride, log_probs, logp_stride,
+                              (long long*)actions_compact, W);
+}
+
+int trxl_adv_stats(const float* advantages, const int64_t* sample_index, int N, double* out3, void* stream) {
+    TRXL_CHECK_ARG(advantages && out3 && N > 0, "adv_stats: bad arguments");
+    return ppo_adv_stats(S(stream), advantages, (cll)sample_index, N, out3);
+}
+
+int trxl_ppo_loss(const float* logits, const float* value, const int64_t* actions, const float* old_log_probs,
+                  const float* old_values, const float* advantages, const int64_t* sample_index, const double* adv_stats3,
+                  const int32_t* branch_sizes, int num_branches, int N, double clip_range, double beta, double vf_coef,
+                  float* dlogits, float* dvalue, float* stats6, float* scratch, void* stream) {
+    TRXL_CHECK_ARG(logits && value && actions && old_log_probs && old_values && advantages && adv_stats3 && stats6 && scratch,
+                   "ppo_loss: null pointer");
+    PpoLossArgs a;
+    TRXL_PROPAGATE(branch_spec(branch_sizes, num_branches, a.bs, &a.sumA));
+    a.N = N; a.logits = logits; a.value = value; a.actions = (cll)actions; a.old_logp = old_log_probs; a.old_values = old_values;
+    a.adv = advantages; a.sidx = (cll)sample_index; a.advstats = adv_stats3;
+    a.clip = (float)clip_range; a.clip_lo = (float)(1.0 - clip_range); a.clip_hi = (float)(1.0 + clip_range);
+    a.beta = (float)beta; a.vf_coef = (float)vf_coef; a.dlogits = dlogits; a.dvalue = dvalue; a.partial = scratch;
+    return ppo_loss(S(stream), a, stats6);
+}
+
+int trxl_clip_adamw_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t total_floats,
+                         const int64_t* chunks, int nchunks, int ngroups, double max_grad_norm, double lr, double beta1,
+                         double beta2, double eps, double weight_decay, int64_t step, float* partial, float* norms, void* stream) {
+    TRXL_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && total_floats > 0 && step >= 1, "clip_adamw: bad arguments");
+    TRXL_CHECK_ARG(nchunks == 0 || (chunks && partial && norms), "clip_adamw: clipping needs chunks/partial/norms");
+    AdamWArgs h;
+    const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+    h.decay = (float)(1.0 - lr * weight_decay);
+    h.one_minus_b1 = (float)(1.0 - beta1);
+    h.b2 = (float)beta2;
+    h.one_minus_b2 = (float)(1.0 - beta2);
+    h.bc2_sqrt = (float)sqrt(bc2);
+    h.eps = (float)eps;
+    h.step_size = (float)(lr / bc1);
+    return ppo_clip_adamw(S(stream), params, grads, exp_avg, exp_avg_sq, total_floats, (cll)chunks, nchunks, ngroups,
+                          (float)max_grad_norm, partial, norms, h);
+}
+
+}  // extern "C"

@@ -1,0 +1,551 @@
+// Fused episodic-memory window attention (query length 1), forward and backward.
+//
+// Reference path (transformer.py:31-86,129-137,237-249 + utils.py:52-75 + buffer.py:90):
+//   gather whole episodes (mb,M,B,D) -> gather window (mb,L,B,D) -> +PE -> [LayerNorm_kv] -> K = x Wk^T,
+//   V = x Wv^T over mb*L rows -> energy = q.K -> masked_fill(-1e20) -> softmax(/sqrt(D)) -> P.V
+//
+// This kernel never materialises any of those tensors.  Because the query length is always 1 the
+// projections fold onto the query side exactly (up to fp32 re-association):
+//   energy[h,l] = sum_{d in head h} Q[d] (Wk[d,:] . x_l)          = qk[h,:] . x_l ,  qk[h,:] = Q_h Wk_h
+//   out[d]      = sum_l p[h(d),l] (Wv[d,:] . x_l) = Wv[d,:] . ctx[h(d),:],  ctx[h,:] = sum_l p[h,l] x_l
+// so the only per-(sample, window-slot) work left is streaming the raw fp32 memory row once:
+// H dot products + H axpys per row.  qk (N,H,D) comes from two small GEMMs before this kernel and
+// ctx (N,H,D) feeds one small GEMM after it.  The pre-LayerNorm case streams the same raw rows and
+// normalises on the fly (row mean/rstd from the same pass; gamma/beta are folded into Wk/Wv by the
+// caller): energy = rstd*(qkg.x - mu*sum(qkg)) + qkb,  ctx_hat = sum_l p*rstd*(x - mu).
+//
+// Rows come straight from the episode table (E, slots, B, D) through three index arrays
+// (episode id per sample, slot per window position, PE row per window position), so the minibatch
+// "memories" and "window" tensors of the reference exist only as addresses.
+//
+// Masking: a masked slot of a partially-masked sample has softmax weight exactly 0 in the reference
+// (exp(-6e18 - max) == 0), so its row is never read.  A fully-masked sample (episode step 0) is the
+// exception: the reference yields a uniform distribution over all L slots, and so does this kernel.
+//
+// Algorithmic bytes per (sample, block): 4*L*D (the fp32 window) -> HBM/L2-bandwidth bound.
+#include "attention.cuh"
+
+namespace {
+
+constexpr int NW = 4;                 // warps per CTA
+constexpr float LN_EPS = 1e-5f;
+
+struct RowMeta {                      // per-CTA shared staging of the sample's index rows
+    long long* win;                   // [L] slot in episode
+    long long* pe;                    // [L] PE row
+    unsigned char* vis;               // [L] 1 = read this row
+};
+
+template <int NV4>
+__device__ __forceinline__ void load_row(const float* __restrict__ src, const float* __restrict__ pe_row, int D,
+                                         int lane, float4 (&x)[NV4]) {
+#pragma unroll
+    for (int c = 0; c < NV4; ++c) {
+        const int col = c * 128 + lane * 4;
+        if (col < D) {
+            x[c] = *reinterpret_cast<const float4*>(src + col);
+            if (pe_row) {
+                const float4 p = *reinterpret_cast<const float4*>(pe_row + col);
+                x[c].x += p.x; x[c].y += p.y; x[c].z += p.z; x[c].w += p.w;
+            }
+        } else {
+            x[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+    return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+
+// stage the sample's mask / window / PE index rows in shared memory; returns all_masked
+__device__ __forceinline__ bool stage_meta(const AttnArgs& a, long long row, RowMeta& sm, int* s_flag) {
+    const int tid = threadIdx.x;
+    if (tid == 0) *s_flag = 0;
+    __syncthreads();
+    int any = 0;
+    for (int l = tid; l < a.L; l += blockDim.x) {
+        const unsigned char m = a.mask ? a.mask[row * a.L + l] : 1;
+        sm.vis[l] = m;
+        any |= m;
+        sm.win[l] = a.win_index ? a.win_index[row * a.L + l] : (long long)l;
+        sm.pe[l] = a.pe_index ? a.pe_index[row * a.L + l] : 0;
+    }
+    if (any) *s_flag = 1;
+    __syncthreads();
+    const bool all_masked = (*s_flag == 0);
+    if (all_masked) {
+        for (int l = tid; l < a.L; l += blockDim.x) sm.vis[l] = 1;     // uniform softmax over every slot
+        __syncthreads();
+    }
+    return all_masked;
+}
+
+template <int NV4, int HPW, bool LN>
+__global__ void __launch_bounds__(NW * 32)
+window_attn_fwd_kernel(const AttnArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: win[L] i64 | pe[L] i64 | energies[HPW][L] f32 | ctx[HPW][D] f32 | stats[NW][HPW][3] | vis[L] u8
+    long long* s_win = reinterpret_cast<long long*>(smem_raw);
+    long long* s_pe = s_win + a.L;
+    const int Lp = (a.L + 3) & ~3;                              // keeps the float4 regions 16-byte aligned
+    float* s_e = reinterpret_cast<float*>(s_pe + a.L);
+    float* s_ctx = s_e + HPW * Lp;
+    float* s_stat = s_ctx + HPW * a.D;
+    unsigned char* s_vis = reinterpret_cast<unsigned char*>(s_stat + NW * HPW * 3);
+    __shared__ int s_flag;
+
+    const int n = blockIdx.x;
+    const int h0 = blockIdx.y * HPW;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long row = a.sample_index ? a.sample_index[n] : n;
+    const long long ep = a.ep_index ? a.ep_index[row] : row;
+    RowMeta sm{s_win, s_pe, s_vis};
+    const bool all_masked = stage_meta(a, row, sm, &s_flag);
+
+    // folded query vectors for this head group
+    float4 qk[HPW][NV4];
+    float sg[HPW], qb[HPW];
+#pragma unroll
+    for (int h = 0; h < HPW; ++h) {
+        const bool hv = (h0 + h) < a.H;
+        const float* qp = a.qk + ((long long)n * a.H + (hv ? h0 + h : 0)) * a.D;
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < NV4; ++c) {
+            const int col = c * 128 + lane * 4;
+            qk[h][c] = (hv && col < a.D) ? *reinterpret_cast<const float4*>(qp + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+            s += qk[h][c].x + qk[h][c].y + qk[h][c].z + qk[h][c].w;
+        }
+        sg[h] = LN ? warp_sum(s) : 0.f;
+        qb[h] = (LN && a.qkb && hv) ? a.qkb[(long long)n * a.H + h0 + h] : 0.f;
+    }
+
+    float m_run[HPW], s_run[HPW], c_run[HPW];
+    float4 acc[HPW][NV4];
+#pragma unroll
+    for (int h = 0; h < HPW; ++h) {
+        m_run[h] = -INFINITY; s_run[h] = 0.f; c_run[h] = 0.f;
+#pragma unroll
+        for (int c = 0; c < NV4; ++c) acc[h][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
+    const float* tab = a.table + ((ep * a.slots) * a.B + a.blk) * (long long)a.D;
+    const long long slot_stride = (long long)a.B * a.D;
+    const float invD = 1.f / (float)a.D;
+
+    // two rows in flight per warp
+    for (int l = w; l < a.L; l += 2 * NW) {
+        const int l1 = l + NW;
+        const bool v0 = s_vis[l] != 0;
+        const bool v1 = (l1 < a.L) && (s_vis[l1] != 0);
+        float4 x0[NV4], x1[NV4];
+        if (v0) load_row<NV4>(tab + s_win[l] * slot_stride, a.pe ? a.pe + s_pe[l] * a.D : nullptr, a.D, lane, x0);
+        if (v1) load_row<NV4>(tab + s_win[l1] * slot_stride, a.pe ? a.pe + s_pe[l1] * a.D : nullptr, a.D, lane, x1);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const bool vis = r ? v1 : v0;
+            const int ll = r ? l1 : l;
+            if (!vis) continue;                       // warp-uniform
+            float4 (&x)[NV4] = r ? x1 : x0;
+            float red[HPW + 2];
+#pragma unroll
+            for (int h = 0; h < HPW; ++h) {
+                float d = 0.f;
+#pragma unroll
+                for (int c = 0; c < NV4; ++c) d += dot4(qk[h][c], x[c]);
+                red[h] = d;
+            }
+            float s1 = 0.f, s2 = 0.f;
+            if (LN) {
+#pragma unroll
+                for (int c = 0; c < NV4; ++c) {
+                    s1 += x[c].x + x[c].y + x[c].z + x[c].w;
+                    s2 += dot4(x[c], x[c]);
+                }
+            }
+            red[HPW] = s1; red[HPW + 1] = s2;
+            if (LN) warp_sum_multi<HPW + 2>(red);
+            else {
+                float (&rh)[HPW] = *reinterpret_cast<float(*)[HPW]>(&red[0]);
+                warp_sum_multi<HPW>(rh);
+            }
+            float mu = 0.f, rstd = 1.f;
+            if (LN) {
+                mu = red[HPW] * invD;
+                const float var = fmaxf(red[HPW + 1] * invD - mu * mu, 0.f);
+                rstd = rsqrtf(var + LN_EPS);
+            }
+#pragma unroll
+            for (int h = 0; h < HPW; ++h) {
+                float e = LN ? fmaf(rstd, red[h] - mu * sg[h], qb[h]) : red[h];
+                e = all_masked ? 0.f : __fdiv_rn(e, a.scale);
+                if (lane == 0) s_e[h * Lp + ll] = e;
+                const float m_new = fmaxf(m_run[h], e);
+                const float corr = __expf(m_run[h] - m_new);          // exp(-inf) = 0 on first row
+                const float pe_ = __expf(e - m_new);
+                s_run[h] = s_run[h] * corr + pe_;
+                const float wgt = pe_ * rstd;
+                if (LN) c_run[h] = c_run[h] * corr + wgt * mu;
+#pragma unroll
+                for (int c = 0; c < NV4; ++c) {
+                    acc[h][c].x = fmaf(wgt, x[c].x, acc[h][c].x * corr);
+                    acc[h][c].y = fmaf(wgt, x[c].y, acc[h][c].y * corr);
+                    acc[h][c].z = fmaf(wgt, x[c].z, acc[h][c].z * corr);
+                    acc[h][c].w = fmaf(wgt, x[c].w, acc[h][c].w * corr);
+                }
+                m_run[h] = m_new;
+            }
+        }
+    }
+
+    // ---- merge the NW per-warp online-softmax states ----
+    if (lane == 0) {
+#pragma unroll
+        for (int h = 0; h < HPW; ++h) {
+            s_stat[(w * HPW + h) * 3 + 0] = m_run[h];
+            s_stat[(w * HPW + h) * 3 + 1] = s_run[h];
+            s_stat[(w * HPW + h) * 3 + 2] = c_run[h];
+        }
+    }
+    for (int i = threadIdx.x; i < HPW * a.D; i += blockDim.x) s_ctx[i] = 0.f;
+    __syncthreads();
+    float m_all[HPW], s_all[HPW], c_all[HPW], my_scale[HPW];
+#pragma unroll
+    for (int h = 0; h < HPW; ++h) {
+        float mm = -INFINITY;
+#pragma unroll
+        for (int ww = 0; ww < NW; ++ww) mm = fmaxf(mm, s_stat[(ww * HPW + h) * 3]);
+        float ss = 0.f, cc = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < NW; ++ww) {
+            const float mw = s_stat[(ww * HPW + h) * 3];
+            const float f = (mw == -INFINITY) ? 0.f : __expf(mw - mm);
+            ss += s_stat[(ww * HPW + h) * 3 + 1] * f;
+            cc += s_stat[(ww * HPW + h) * 3 + 2] * f;
+        }
+        m_all[h] = mm; s_all[h] = ss; c_all[h] = cc;
+        my_scale[h] = (m_run[h] == -INFINITY) ? 0.f : __expf(m_run[h] - mm);
+    }
+    // deterministic merge: warps add their scaled accumulators in warp order
+    for (int ww = 0; ww < NW; ++ww) {
+        if (w == ww) {
+#pragma unroll
+            for (int h = 0; h < HPW; ++h)
+#pragma unroll
+                for (int c = 0; c < NV4; ++c) {
+                    const int col = c * 128 + lane * 4;
+                    if (col < a.D) {
+                        float4* p = reinterpret_cast<float4*>(s_ctx + h * a.D + col);
+                        float4 t = *p;
+                        t.x = fmaf(acc[h][c].x, my_scale[h], t.x); t.y = fmaf(acc[h][c].y, my_scale[h], t.y);
+                        t.z = fmaf(acc[h][c].z, my_scale[h], t.z); t.w = fmaf(acc[h][c].w, my_scale[h], t.w);
+                        *p = t;
+                    }
+                }
+        }
+        __syncthreads();
+    }
+    // ---- write ctx (N,H,D) and probs (N,H,L) ----
+#pragma unroll
+    for (int h = 0; h < HPW; ++h) {
+        if (h0 + h >= a.H) continue;
+        const float inv = 1.f / s_all[h];
+        float* cp = a.ctx + ((long long)n * a.H + h0 + h) * a.D;
+        for (int j = threadIdx.x; j < a.D; j += blockDim.x) cp[j] = (s_ctx[h * a.D + j] - c_all[h]) * inv;
+        float* pp = a.probs + ((long long)n * a.H + h0 + h) * a.L;
+        for (int l = threadIdx.x; l < a.L; l += blockDim.x)
+            pp[l] = s_vis[l] ? __expf(s_e[h * Lp + l] - m_all[h]) * inv : 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward: given d(ctx) (N,H,D) and the saved probs/ctx, produce d(qk) (N,H,D), d(qkb) (N,H) and,
+// for a learned positional table, scatter-add d(PE).  The memory rows themselves carry no gradient
+// (reference transformer.py:248: memories are detached inputs).
+// ---------------------------------------------------------------------------------------------
+template <int NV4, int HPW, bool LN>
+__global__ void __launch_bounds__(NW * 32)
+window_attn_bwd_kernel(const AttnArgs a, const AttnBwdArgs g) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    long long* s_win = reinterpret_cast<long long*>(smem_raw);
+    long long* s_pe = s_win + a.L;
+    const int Lp = (a.L + 3) & ~3;
+    float* s_p = reinterpret_cast<float*>(s_pe + a.L);          // probs [HPW][Lp]
+    float* s_acc = s_p + HPW * Lp;                              // [HPW][D]
+    float* s_stat = s_acc + HPW * a.D;                          // [NW][HPW][2]
+    unsigned char* s_vis = reinterpret_cast<unsigned char*>(s_stat + NW * HPW * 2);
+    __shared__ int s_flag;
+
+    const int n = blockIdx.x;
+    const int h0 = blockIdx.y * HPW;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long row = a.sample_index ? a.sample_index[n] : n;
+    const long long ep = a.ep_index ? a.ep_index[row] : row;
+    RowMeta sm{s_win, s_pe, s_vis};
+    const bool all_masked = stage_meta(a, row, sm, &s_flag);
+    const bool need_dx = g.dpe != nullptr;
+
+    for (int i = threadIdx.x; i < HPW * a.L; i += blockDim.x) {
+        const int h = i / a.L, l = i % a.L;
+        s_p[h * Lp + l] = (h0 + h < a.H) ? a.probs[((long long)n * a.H + h0 + h) * a.L + l] : 0.f;
+    }
+    for (int i = threadIdx.x; i < HPW * a.D; i += blockDim.x) s_acc[i] = 0.f;
+
+    float4 dc[HPW][NV4], qk[HPW][NV4];
+    float dot0[HPW], sdc[HPW];
+#pragma unroll
+    for (int h = 0; h < HPW; ++h) {
+        const bool hv = (h0 + h) < a.H;
+        const long long off = ((long long)n * a.H + (hv ? h0 + h : 0)) * a.D;
+        float d = 0.f, s = 0.f;
+#pragma unroll
+        for (int c = 0; c < NV4; ++c) {
+            const int col = c * 128 + lane * 4;
+            const bool ok = hv && col < a.D;
+            dc[h][c] = ok ? *reinterpret_cast<const float4*>(g.dctx + off + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+            qk[h][c] = (ok && need_dx) ? *reinterpret_cast<const float4*>(a.qk + off + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) {
+                const float4 cx = *reinterpret_cast<const float4*>(a.ctx + off + col);
+                d += dot4(dc[h][c], cx);
+            }
+            s += dc[h][c].x + dc[h][c].y + dc[h][c].z + dc[h][c].w;
+        }
+        dot0[h] = warp_sum(d);
+        sdc[h] = LN ? warp_sum(s) : 0.f;
+    }
+    __syncthreads();
+
+    float4 acc[HPW][NV4];
+    float accmu[HPW], accb[HPW];
+#pragma unroll
+    for (int h = 0; h < HPW; ++h) {
+        accmu[h] = 0.f; accb[h] = 0.f;
+#pragma unroll
+        for (int c = 0; c < NV4; ++c) acc[h][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float* tab = a.table + ((ep * a.slots) * a.B + a.blk) * (long long)a.D;
+    const long long slot_stride = (long long)a.B * a.D;
+    const float invD = 1.f / (float)a.D;
+    const bool skip_all = all_masked && !need_dx;      // constant energies: no gradient reaches qk
+
+    if (!skip_all) {
+        for (int l = w; l < a.L; l += NW) {
+            if (!s_vis[l]) continue;
+            float4 x[NV4];
+            load_row<NV4>(tab + s_win[l] * slot_stride, a.pe ? a.pe + s_pe[l] * a.D : nullptr, a.D, lane, x);
+            float red[HPW + 2];
+#pragma unroll
+            for (int h = 0; h < HPW; ++h) {
+                float d = 0.f;
+#pragma unroll
+                for (int c = 0; c < NV4; ++c) d += dot4(dc[h][c], x[c]);
+                red[h] = d;
+            }
+            float s1 = 0.f, s2 = 0.f;
+            if (LN) {
+#pragma unroll
+                for (int c = 0; c < NV4; ++c) {
+                    s1 += x[c].x + x[c].y + x[c].z + x[c].w;
+                    s2 += dot4(x[c], x[c]);
+                }
+            }
+            red[HPW] = s1; red[HPW + 1] = s2;
+            if (LN) warp_sum_multi<HPW + 2>(red);
+            else {
+                float (&rh)[HPW] = *reinterpret_cast<float(*)[HPW]>(&red[0]);
+                warp_sum_multi<HPW>(rh);
+            }
+            float mu = 0.f, rstd = 1.f;
+            if (LN) {
+                mu = red[HPW] * invD;
+                const float var = fmaxf(red[HPW + 1] * invD - mu * mu, 0.f);
+                rstd = rsqrtf(var + LN_EPS);
+            }
+            float dE[HPW];
+#pragma unroll
+            for (int h = 0; h < HPW; ++h) {
+                const float gdot = LN ? rstd * (red[h] - mu * sdc[h]) : red[h];      // dctx . x_hat
+                dE[h] = all_masked ? 0.f : __fdiv_rn(s_p[h * Lp + l] * (gdot - dot0[h]), a.scale);
+                const float wgt = dE[h] * rstd;
+                accb[h] += dE[h];
+                if (LN) accmu[h] = fmaf(wgt, mu, accmu[h]);
+#pragma unroll
+                for (int c = 0; c < NV4; ++c) {
+                    acc[h][c].x = fmaf(wgt, x[c].x, acc[h][c].x); acc[h][c].y = fmaf(wgt, x[c].y, acc[h][c].y);
+                    acc[h][c].z = fmaf(wgt, x[c].z, acc[h][c].z); acc[h][c].w = fmaf(wgt, x[c].w, acc[h][c].w);
+                }
+            }
+            if (need_dx) {
+                // d(x_hat) = sum_h dE[h] qk[h] + p[h,l] dctx[h]; then LayerNorm backward (no affine) if LN
+                float4 dxh[NV4];
+                float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+                for (int c = 0; c < NV4; ++c) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int h = 0; h < HPW; ++h) {
+                        const float p = s_p[h * Lp + l];
+                        v.x += dE[h] * qk[h][c].x + p * dc[h][c].x; v.y += dE[h] * qk[h][c].y + p * dc[h][c].y;
+                        v.z += dE[h] * qk[h][c].z + p * dc[h][c].z; v.w += dE[h] * qk[h][c].w + p * dc[h][c].w;
+                    }
+                    dxh[c] = v;
+                    if (LN) {
+                        const int col = c * 128 + lane * 4;
+                        if (col < a.D) {
+                            const float4 xh = make_float4((x[c].x - mu) * rstd, (x[c].y - mu) * rstd,
+                                                          (x[c].z - mu) * rstd, (x[c].w - mu) * rstd);
+                            t1 += v.x + v.y + v.z + v.w;
+                            t2 += dot4(v, xh);
+                        }
+                    }
+                }
+                if (LN) {
+                    t1 = warp_sum(t1) * invD;
+                    t2 = warp_sum(t2) * invD;
+                }
+                float* dst = g.dpe + s_pe[l] * a.D;
+#pragma unroll
+                for (int c = 0; c < NV4; ++c) {
+                    const int col = c * 128 + lane * 4;
+                    if (col < a.D) {
+                        float4 v = dxh[c];
+                        if (LN) {
+                            v.x = rstd * (v.x - t1 - (x[c].x - mu) * rstd * t2);
+                            v.y = rstd * (v.y - t1 - (x[c].y - mu) * rstd * t2);
+                            v.z = rstd * (v.z - t1 - (x[c].z - mu) * rstd * t2);
+                            v.w = rstd * (v.w - t1 - (x[c].w - mu) * rstd * t2);
+                        }
+                        atomicAdd(dst + col, v.x); atomicAdd(dst + col + 1, v.y);
+                        atomicAdd(dst + col + 2, v.z); atomicAdd(dst + col + 3, v.w);
+                    }
+                }
+            }
+        }
+    }
+    // ---- merge warps (deterministic order) ----
+    if (lane == 0) {
+#pragma unroll
+        for (int h = 0; h < HPW; ++h) {
+            s_stat[(w * HPW + h) * 2 + 0] = accmu[h];
+            s_stat[(w * HPW + h) * 2 + 1] = accb[h];
+        }
+    }
+    for (int ww = 0; ww < NW; ++ww) {
+        if (w == ww) {
+#pragma unroll
+            for (int h = 0; h < HPW; ++h)
+#pragma unroll
+                for (int c = 0; c < NV4; ++c) {
+                    const int col = c * 128 + lane * 4;
+                    if (col < a.D) {
+                        float4* p = reinterpret_cast<float4*>(s_acc + h * a.D + col);
+                        float4 t = *p;
+                        t.x += acc[h][c].x; t.y += acc[h][c].y; t.z += acc[h][c].z; t.w += acc[h][c].w;
+                        *p = t;
+                    }
+                }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int h = 0; h < HPW; ++h) {
+        if (h0 + h >= a.H) continue;
+        float mu_sum = 0.f, b_sum = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < NW; ++ww) {
+            mu_sum += s_stat[(ww * HPW + h) * 2];
+            b_sum += s_stat[(ww * HPW + h) * 2 + 1];
+        }
+        float* dq = g.dqk + ((long long)n * a.H + h0 + h) * a.D;
+        for (int j = threadIdx.x; j < a.D; j += blockDim.x) dq[j] = s_acc[h * a.D + j] - mu_sum;
+        if (g.dqkb && threadIdx.x == 0) g.dqkb[(long long)n * a.H + h0 + h] = b_sum;
+    }
+}
+
+template <int NV4, int HPW>
+int launch_fwd(const AttnArgs& a, cudaStream_t st) {
+    dim3 grid(a.N, trxl_cdiv(a.H, HPW));
+    const size_t smem = (size_t)a.L * 16 + (size_t)HPW * ((a.L + 3) & ~3) * 4 + (size_t)HPW * a.D * 4 + NW * HPW * 3 * 4 + a.L + 16;
+    if (a.ln) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(window_attn_fwd_kernel<NV4, HPW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        window_attn_fwd_kernel<NV4, HPW, true><<<grid, NW * 32, smem, st>>>(a);
+    } else {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(window_attn_fwd_kernel<NV4, HPW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        window_attn_fwd_kernel<NV4, HPW, false><<<grid, NW * 32, smem, st>>>(a);
+    }
+    TRXL_CHECK_LAUNCH("window_attn_fwd");
+    return TRXL_OK;
+}
+
+template <int NV4, int HPW>
+int launch_bwd(const AttnArgs& a, const AttnBwdArgs& g, cudaStream_t st) {
+    dim3 grid(a.N, trxl_cdiv(a.H, HPW));
+    const size_t smem = (size_t)a.L * 16 + (size_t)HPW * ((a.L + 3) & ~3) * 4 + (size_t)HPW * a.D * 4 + NW * HPW * 2 * 4 + a.L + 16;
+    if (a.ln) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(window_attn_bwd_kernel<NV4, HPW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        window_attn_bwd_kernel<NV4, HPW, true><<<grid, NW * 32, smem, st>>>(a, g);
+    } else {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(window_attn_bwd_kernel<NV4, HPW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        window_attn_bwd_kernel<NV4, HPW, false><<<grid, NW * 32, smem, st>>>(a, g);
+    }
+    TRXL_CHECK_LAUNCH("window_attn_bwd");
+    return TRXL_OK;
+}
+
+// heads per warp pass: keep (qk + acc) register arrays <= ~64 float4-lanes
+int pick_hpw(int nv4, int H) {
+    int hpw = nv4 <= 2 ? 4 : 2;
+    if (nv4 > 4) hpw = 1;
+    while (hpw > 1 && hpw / 2 >= H) hpw /= 2;
+    return hpw;
+}
+
+}  // namespace
+
+static int check_args(const AttnArgs& a) {
+    TRXL_CHECK_ARG(a.N >= 0 && a.L > 0 && a.H > 0 && a.D > 0, "window_attention: bad dims N=%d L=%d D=%d H=%d", a.N, a.L, a.D, a.H);
+    TRXL_CHECK_ARG(a.D % 4 == 0 && a.D <= 1024, "window_attention: embed_dim must be a multiple of 4 and <= 1024 (got %d)", a.D);
+    TRXL_CHECK_ARG(a.D % a.H == 0, "window_attention: embed_dim %d not divisible by heads %d", a.D, a.H);
+    TRXL_CHECK_ARG(a.L <= 4096, "window_attention: memory_length %d > 4096 unsupported", a.L);
+    TRXL_CHECK_ARG(a.table && a.qk && a.probs && a.ctx, "window_attention: null pointer");
+    TRXL_CHECK_ARG(((uintptr_t)a.table % 16 == 0) && ((uintptr_t)a.qk % 16 == 0) && ((uintptr_t)a.ctx % 16 == 0) &&
+                   (!a.pe || (uintptr_t)a.pe % 16 == 0), "window_attention: pointers must be 16-byte aligned");
+    TRXL_CHECK_ARG(!a.pe || a.pe_index, "window_attention: pe table given without pe_index");
+    return TRXL_OK;
+}
+
+#define DISPATCH(NV4, FN, ...)                                                   \
+    do {                                                                        \
+        const int hpw = pick_hpw(NV4, a.H);                                     \
+        if (hpw == 4) return FN<NV4, 4>(__VA_ARGS__);                           \
+        if (hpw == 2) return FN<NV4, 2>(__VA_ARGS__);                           \
+        return FN<NV4, 1>(__VA_ARGS__);                                         \
+    } while (0)
+
+int trxl_window_attn_fwd(const AttnArgs& a, cudaStream_t st) {
+    TRXL_PROPAGATE(check_args(a));
+    if (a.N == 0) return TRXL_OK;
+    const int nv4 = (a.D + 127) / 128;
+    switch (nv4) {
+        case 1: DISPATCH(1, launch_fwd, a, st);
+        case 2: DISPATCH(2, launch_fwd, a, st);
+        case 3: DISPATCH(3, launch_fwd, a, st);
+        case 4: DISPATCH(4, launch_fwd, a, st);
+        default: return launch_fwd<8, 1>(a, st);
+    }
+}
+
+int trxl_window_attn_bwd(const AttnArgs& a, const AttnBwdArgs& g, cudaStream_t st) {
+    TRXL_PROPAGATE(check_args(a));
+    TRXL_CHECK_ARG(g.dctx && g.dqk, "window_attention_bwd: null pointer");
+    if (a.N == 0) return TRXL_OK;
+    const int nv4 = (a.D + 127) / 128;
+    switch (nv4) {
+        case 1: DISPATCH(1, launch_bwd, a, g, st);
+        case 2: DISPATCH(2, launch_bwd, a, g, st);
+        case 3: DISPATCH(3, launch_bwd, a, g, st);
+        case 4: DISPATCH(4, launch_bwd, a, g, st);
+        default: return launch_bwd<8, 1>(a, g, st);
+    }
+}

@@ -1,0 +1,223 @@
+// fp32 SIMT GEMM with strided/batched operands and a fused epilogue.
+//
+//   C[b][m, n] (+)= epi( sum_k A[b](m, k) * B[b](k, n) )        epi: +bias[n], ReLU, +R[m, n]
+//
+// A is either "k-contiguous" (a_kc=1: A[m*lda + k], a row-major (M, K) matrix) or "m-contiguous"
+// (a_kc=0: A[k*lda + m], i.e. the transpose of a row-major (K, M) matrix).  Same for B with n.
+// The three combinations the model needs:
+//   forward  y = x W^T      : A = x (kc),   B = W  (kc: B(k, n) = W[n*ldw + k])
+//   dgrad    dx = dy W      : A = dy (kc),  B = W  (nc: B(k, n) = W[k*ldw + n])
+//   wgrad    dW = dy^T x    : A = dy (mc),  B = x  (nc)
+// fp32 accumulate in a fixed k order (deterministic).  The parity contract of this engine is 1e-4
+// against the reference's fp32 CPU path, so the linears stay in full fp32 on the CUDA cores here.
+#include "gemm.cuh"
+
+namespace {
+
+constexpr int BK = 16;
+
+template <int BM, int BN, int TM, int TN, bool AKC, bool BKC>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+sgemm_kernel(const GemmArgs g) {
+    constexpr int NT = (BM / TM) * (BN / TN);
+    constexpr int PAD = 4;
+    __shared__ __align__(16) float As[2][BK][BM + PAD];
+    __shared__ __align__(16) float Bs[2][BK][BN + PAD];
+
+    const int tid = threadIdx.x;
+    const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int b = blockIdx.z;
+    const float* __restrict__ A = g.A + (long long)b * g.sA;
+    const float* __restrict__ B = g.B + (long long)b * g.sB;
+    float* __restrict__ C = g.C + (long long)b * g.sC;
+    const float* __restrict__ bias = g.bias ? g.bias + (long long)b * g.sBias : nullptr;
+    const float* __restrict__ R = g.R ? g.R + (long long)b * g.sR : nullptr;
+
+    constexpr int A_V4 = BM * BK / 4, B_V4 = BN * BK / 4;
+    constexpr int A_PER = (A_V4 + NT - 1) / NT, B_PER = (B_V4 + NT - 1) / NT;
+    float4 ra[A_PER], rb[B_PER];
+
+    auto load_a = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < A_PER; ++i) {
+            const int v = tid + i * NT;
+            float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (v < A_V4) {
+                if (AKC) {
+                    const int m = m0 + v / (BK / 4), k = k0 + (v % (BK / 4)) * 4;
+                    if (m < g.M) {
+                        const float* p = A + (long long)m * g.lda + k;
+                        if (g.vecA && k + 3 < g.K) val = *reinterpret_cast<const float4*>(p);
+                        else {
+                            if (k < g.K) val.x = p[0];
+                            if (k + 1 < g.K) val.y = p[1];
+                            if (k + 2 < g.K) val.z = p[2];
+                            if (k + 3 < g.K) val.w = p[3];
+                        }
+                    }
+                } else {
+                    const int k = k0 + v / (BM / 4), m = m0 + (v % (BM / 4)) * 4;
+                    if (k < g.K) {
+                        const float* p = A + (long long)k * g.lda + m;
+                        if (g.vecA && m + 3 < g.M) val = *reinterpret_cast<const float4*>(p);
+                        else {
+                            if (m < g.M) val.x = p[0];
+                            if (m + 1 < g.M) val.y = p[1];
+                            if (m + 2 < g.M) val.z = p[2];
+                            if (m + 3 < g.M) val.w = p[3];
+                        }
+                    }
+                }
+            }
+            ra[i] = val;
+        }
+    };
+    auto load_b = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < B_PER; ++i) {
+            const int v = tid + i * NT;
+            float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (v < B_V4) {
+                if (BKC) {
+                    const int n = n0 + v / (BK / 4), k = k0 + (v % (BK / 4)) * 4;
+                    if (n < g.N) {
+                        const float* p = B + (long long)n * g.ldb + k;
+                        if (g.vecB && k + 3 < g.K) val = *reinterpret_cast<const float4*>(p);
+                        else {
+                            if (k < g.K) val.x = p[0];
+                            if (k + 1 < g.K) val.y = p[1];
+                            if (k + 2 < g.K) val.z = p[2];
+                            if (k + 3 < g.K) val.w = p[3];
+                        }
+                    }
+                } else {
+                    const int k = k0 + v / (BN / 4), n = n0 + (v % (BN / 4)) * 4;
+                    if (k < g.K) {
+                        const float* p = B + (long long)k * g.ldb + n;
+                        if (g.vecB && n + 3 < g.N) val = *reinterpret_cast<const float4*>(p);
+                        else {
+                            if (n < g.N) val.x = p[0];
+                            if (n + 1 < g.N) val.y = p[1];
+                            if (n + 2 < g.N) val.z = p[2];
+                            if (n + 3 < g.N) val.w = p[3];
+                        }
+                    }
+                }
+            }
+            rb[i] = val;
+        }
+    };
+    auto store_tiles = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < A_PER; ++i) {
+            const int v = tid + i * NT;
+            if (v < A_V4) {
+                if (AKC) {
+                    const int m = v / (BK / 4), k = (v % (BK / 4)) * 4;
+                    As[buf][k][m] = ra[i].x; As[buf][k + 1][m] = ra[i].y;
+                    As[buf][k + 2][m] = ra[i].z; As[buf][k + 3][m] = ra[i].w;
+                } else {
+                    const int k = v / (BM / 4), m = (v % (BM / 4)) * 4;
+                    *reinterpret_cast<float4*>(&As[buf][k][m]) = ra[i];
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < B_PER; ++i) {
+            const int v = tid + i * NT;
+            if (v < B_V4) {
+                if (BKC) {
+                    const int n = v / (BK / 4), k = (v % (BK / 4)) * 4;
+                    Bs[buf][k][n] = rb[i].x; Bs[buf][k + 1][n] = rb[i].y;
+                    Bs[buf][k + 2][n] = rb[i].z; Bs[buf][k + 3][n] = rb[i].w;
+                } else {
+                    const int k = v / (BN / 4), n = (v % (BN / 4)) * 4;
+                    *reinterpret_cast<float4*>(&Bs[buf][k][n]) = rb[i];
+                }
+            }
+        }
+    };
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    const int nk = (g.K + BK - 1) / BK;
+    load_a(0);
+    load_b(0);
+    store_tiles(0);
+    __syncthreads();
+    for (int kt = 0; kt < nk; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nk) {
+            load_a((kt + 1) * BK);
+            load_b((kt + 1) * BK);
+        }
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float a[TM], bb[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) a[i] = As[buf][k][ty * TM + i];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) bb[j] = Bs[buf][k][tx * TN + j];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        if (kt + 1 < nk) {
+            store_tiles(buf ^ 1);
+            __syncthreads();
+        }
+    }
+
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int m = m0 + ty * TM + i;
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int n = n0 + tx * TN + j;
+            if (n >= g.N) continue;
+            float v = acc[i][j] * g.alpha;
+            if (bias) v += bias[n];
+            if (g.relu) v = fmaxf(v, 0.f);
+            if (R) v += R[(long long)m * g.ldr + n];
+            float* cp = C + (long long)m * g.ldc + n;
+            if (g.accumulate) v += *cp;
+            *cp = v;
+        }
+    }
+}
+
+template <int BM, int BN, int TM, int TN>
+int launch_cfg(const GemmArgs& g, cudaStream_t st) {
+    dim3 grid(trxl_cdiv(g.N, BN), trxl_cdiv(g.M, BM), g.batch);
+    dim3 block((BM / TM) * (BN / TN));
+    if (g.a_kc && g.b_kc) sgemm_kernel<BM, BN, TM, TN, true, true><<<grid, block, 0, st>>>(g);
+    else if (g.a_kc && !g.b_kc) sgemm_kernel<BM, BN, TM, TN, true, false><<<grid, block, 0, st>>>(g);
+    else if (!g.a_kc && !g.b_kc) sgemm_kernel<BM, BN, TM, TN, false, false><<<grid, block, 0, st>>>(g);
+    else sgemm_kernel<BM, BN, TM, TN, false, true><<<grid, block, 0, st>>>(g);
+    TRXL_CHECK_LAUNCH("sgemm");
+    return TRXL_OK;
+}
+
+}  // namespace
+
+int trxl_gemm(GemmArgs g, cudaStream_t st) {
+    TRXL_CHECK_ARG(g.M >= 0 && g.N >= 0 && g.K >= 0 && g.batch >= 1, "gemm: bad dims M=%d N=%d K=%d batch=%d", g.M, g.N, g.K, g.batch);
+    if (g.M == 0 || g.N == 0) return TRXL_OK;
+    auto aligned = [](const void* p, long long ld, long long bs) {
+        return ((uintptr_t)p % 16 == 0) && (ld % 4 == 0) && (bs % 4 == 0);
+    };
+    g.vecA = aligned(g.A, g.lda, g.sA);
+    g.vecB = aligned(g.B, g.ldb, g.sB);
+    if (g.alpha == 0.f) g.alpha = 1.f;
+    // tile choice: small problems get small tiles so more CTAs are in flight
+    const long long tiles64 = (long long)trxl_cdiv(g.M, 64) * trxl_cdiv(g.N, 64) * g.batch;
+    if (g.M <= 32 || g.N <= 32 || tiles64 < 96) return launch_cfg<32, 32, 2, 2>(g, st);
+    return launch_cfg<64, 64, 4, 4>(g, st);
+}

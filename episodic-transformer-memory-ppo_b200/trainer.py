@@ -1,0 +1,452 @@
+"""PPO trainer over an episodic TransformerXL memory -- B200-native drop-in for the reference's
+``trainer.PPOTrainer`` (trainer.py:16-383).  ``PPOTrainer(config, run_id, device)``,
+``run_training()``, ``close()`` and the internal methods BASELINE.json names
+(``_sample_training_data``, ``get_last_value``, ``_train_epochs``, ``_train_mini_batch``) keep their
+signatures and semantics; ``train.py`` drives it unchanged.
+
+How the hot path is mapped onto the GPU (all arithmetic in libtrxlppo, see csrc/):
+  * episodic memory is one device table (E, M, B, D); a worker's live episode is a row of it, so
+    "clone the finished episode, zero the worker memory, append a new episode" (trainer.py:205-213) is
+    just "point the worker at a fresh zero row";
+  * rollout step: obs H2D -> rollout_prepare (mask / window-index rows) -> model trunk (window read
+    in place from the table) -> memory_scatter -> sample_actions -> actions D2H;
+  * PPO step: sample_index (the shuffled rows) -> obs gather (+ cuDNN conv encoder) -> trunk forward
+    -> adv_stats -> fused loss fwd/bwd -> trunk backward -> conv backward -> [all-reduce] ->
+    fused clip + AdamW.  No (mb, M, B, D) / (mb, L, B, D) tensors, no host sync inside an update;
+  * multi-GPU: one process per GPU, each with its own workers/buffer/table; gradients are summed with
+    a single all-reduce of the flat gradient arena per optimiser step (parallel.py).
+"""
+import os
+import pickle
+import time
+from collections import deque
+
+import numpy as np
+import torch
+
+import trxl_native as native
+from buffer import Buffer, MiniBatch
+from model import ActorCriticModel
+from optim_native import FusedClipAdamW
+from parallel import DataParallelContext
+from utils import create_env, polynomial_decay, process_episode_info
+from worker import Worker
+
+
+def build_mask_table(memory_length):
+    """(L, L) strictly-lower-triangular float table (trainer.py:78); row min(step, L-1) is a sample's mask."""
+    return torch.tril(torch.ones((memory_length, memory_length)), diagonal=-1)
+
+
+def build_window_index_table(max_episode_length, memory_length):
+    """(M, L) int64 window slots by episode step (trainer.py:88-90)."""
+    if memory_length > max_episode_length:
+        raise ValueError("memory_length (%d) must not exceed the environment's max_episode_steps (%d)"
+                         % (memory_length, max_episode_length))
+    head = torch.arange(memory_length).repeat(memory_length - 1, 1)
+    tail = torch.arange(max_episode_length - memory_length + 1).unsqueeze(1) + torch.arange(memory_length).unsqueeze(0)
+    return torch.cat((head, tail)).long()
+
+
+class PPOTrainer:
+    def __init__(self, config, run_id="run", device=torch.device("cpu"), workers=None, summary_writer=True):
+        self.config = config
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise native.NativeLibraryError(
+                "PPOTrainer needs a CUDA device: the B200 engine has no CPU path (got device=%s). "
+                "Use the reference implementation for CPU runs." % self.device)
+        native.load()
+        self.run_id = run_id
+        self.num_workers = config["n_workers"]
+        self.lr_schedule = config["learning_rate_schedule"]
+        self.beta_schedule = config["beta_schedule"]
+        self.cr_schedule = config["clip_range_schedule"]
+        t = config["transformer"]
+        self.memory_length, self.num_blocks, self.embed_dim = t["memory_length"], t["num_blocks"], t["embed_dim"]
+        self.dp = DataParallelContext(self.device)
+
+        self.writer = None
+        if summary_writer and self.dp.rank == 0:
+            from torch.utils.tensorboard import SummaryWriter
+            os.makedirs("./summaries", exist_ok=True)
+            self.writer = SummaryWriter("./summaries/" + run_id + time.strftime("/%Y%m%d-%H%M%S/"))
+
+        dummy_env = create_env(self._env_config(-1))
+        observation_space = dummy_env.observation_space
+        self.action_space_shape = (dummy_env.action_space.n,)
+        self.max_episode_length = dummy_env.max_episode_steps
+        dummy_env.close()
+        self.obs_shape = tuple(observation_space.shape)
+
+        self.buffer = Buffer(config, observation_space, self.action_space_shape, self.max_episode_length, self.device)
+        self.model = ActorCriticModel(config, observation_space, self.action_space_shape, self.max_episode_length).to(self.device)
+        self.model.train()
+        self.dp.broadcast_(self.model.flat_parameters())
+        self.optimizer = FusedClipAdamW(self.model, lr=self.lr_schedule["initial"], max_grad_norm=config["max_grad_norm"])
+
+        # env workers: anything with a ``child`` pipe end speaking the reference protocol
+        self.workers = workers if workers is not None else [Worker(self._env_config(w)) for w in range(self.num_workers)]
+        self.worker_ids = range(self.num_workers)
+        self.worker_current_episode_step = torch.zeros((self.num_workers,), dtype=torch.long)
+        for worker in self.workers:
+            worker.child.send(("reset", None))
+        self.obs = np.zeros((self.num_workers,) + self.obs_shape, dtype=np.float32)
+        for w, worker in enumerate(self.workers):
+            self.obs[w] = worker.child.recv()
+
+        # bit-exact integer tables, built on the host and uploaded once
+        self.memory_mask = build_mask_table(self.memory_length)
+        self.memory_indices = build_window_index_table(self.max_episode_length, self.memory_length)
+        dev, W, T, L = self.device, self.num_workers, config["worker_steps"], self.memory_length
+        self._mask_table_dev = (self.memory_mask != 0).to(torch.uint8).to(dev).contiguous()
+        self._index_table_dev = self.memory_indices.to(dev).contiguous()
+
+        # episode table + per-worker cursors
+        self._table = None
+        self._table_cap = 0
+        self._ep_host = torch.arange(W, dtype=torch.long).pin_memory()      # table row of each worker's live episode
+        self._step_host = self.worker_current_episode_step.pin_memory()
+        self.worker_current_episode_step = self._step_host
+        self._ep_dev = torch.arange(W, dtype=torch.long, device=dev)
+        self._step_dev = torch.zeros(W, dtype=torch.long, device=dev)
+        self._alloc_table(self._initial_capacity())
+        self._n_rows = W              # rows of the table in use
+        self._n_episodes = W          # episodes the reference's buffer.memories would hold
+
+        # staging buffers
+        self._obs_pinned = torch.zeros((W,) + self.obs_shape, dtype=torch.float32).pin_memory()
+        self._obs_dev = torch.zeros((W,) + self.obs_shape, dtype=torch.float32, device=dev)
+        self._act_dev = torch.zeros((W, len(self.action_space_shape)), dtype=torch.long, device=dev)
+        self._act_pinned = torch.zeros((W, len(self.action_space_shape)), dtype=torch.long).pin_memory()
+        self._rollout_rows = (torch.arange(W, device=dev).unsqueeze(0) * T + torch.arange(T, device=dev).unsqueeze(1)).contiguous()
+        self._win_last = torch.zeros((W, L), dtype=torch.long, device=dev)
+        self._mask_last = torch.zeros((W, L), dtype=torch.uint8, device=dev)
+        self._train_state = {}
+        self._forced_actions = None     # optional (T, W, n_branches) int64 device tensor: replay these actions (parity tests)
+        self.timers = {"rollout": 0.0, "train": 0.0, "env": 0.0}
+
+    # ------------------------------------------------------------------------------------------ setup helpers
+    def _env_config(self, worker):
+        cfg = dict(self.config["environment"])
+        if cfg.get("type") == "Synthetic":
+            cfg["seed"] = int(cfg.get("seed", 0)) + 1 + worker + 10007 * getattr(getattr(self, "dp", None), "rank", 0)
+        return cfg
+
+    def _initial_capacity(self):
+        W, T = self.num_workers, self.config["worker_steps"]
+        return W + max(8, (W * T) // max(1, self.max_episode_length // 2))
+
+    def _alloc_table(self, capacity):
+        new = torch.zeros((capacity, self.max_episode_length, self.num_blocks, self.embed_dim), dtype=torch.float32,
+                          device=self.device)
+        if self._table is not None:
+            new[:self._table.shape[0]].copy_(self._table)
+        self._table, self._table_cap = new, capacity
+
+    @property
+    def memory(self):
+        """(W, M, B, D) live episodic memory of every worker (the reference's ``self.memory``)."""
+        return self._table[self._ep_dev]
+
+    def _new_row(self):
+        if self._n_rows >= self._table_cap:
+            self._alloc_table(self._table_cap * 2)
+        self._n_rows += 1
+        return self._n_rows - 1
+
+    def _begin_rollout(self):
+        """Reference trainer.py:154-156: the buffer's episode list restarts as the W live memories."""
+        W = self.num_workers
+        live = self._table[self._ep_dev]                 # (W, M, B, D) copy
+        self._table.zero_()
+        self._table[:W].copy_(live)
+        self._ep_host.copy_(torch.arange(W))
+        self._ep_dev.copy_(self._ep_host, non_blocking=True)
+        self._n_rows = W
+        self._n_episodes = W
+
+    # ------------------------------------------------------------------------------------------ training loop
+    def run_training(self):
+        """Sample -> prepare -> optimise for ``config["updates"]`` updates; saves the final model (trainer.py:101-143)."""
+        if self.dp.rank == 0:
+            print("Starting training on %s (%d rank%s)" % (self.device, self.dp.world_size, "" if self.dp.world_size == 1 else "s"))
+        episode_infos = deque(maxlen=100)
+        for update in range(self.config["updates"]):
+            lr = polynomial_decay(self.lr_schedule["initial"], self.lr_schedule["final"], self.lr_schedule["max_decay_steps"],
+                                  self.lr_schedule["power"], update)
+            beta = polynomial_decay(self.beta_schedule["initial"], self.beta_schedule["final"],
+                                    self.beta_schedule["max_decay_steps"], self.beta_schedule["power"], update)
+            clip_range = polynomial_decay(self.cr_schedule["initial"], self.cr_schedule["final"],
+                                          self.cr_schedule["max_decay_steps"], self.cr_schedule["power"], update)
+            sampled = self._sample_training_data()
+            self.buffer.prepare_batch_dict()
+            training_stats, grad_info = self._train_epochs(lr, clip_range, beta)
+            training_stats = np.mean(training_stats, axis=0)
+            episode_infos.extend(sampled)
+            episode_result = process_episode_info(episode_infos)
+            if self.dp.rank == 0:
+                self._report(update, training_stats, episode_result)
+                self._write_gradient_summary(update, grad_info)
+                self._write_training_summary(update, training_stats, episode_result)
+        if self.dp.rank == 0:
+            self._save_model()
+
+    def _report(self, update, s, ep):
+        head = "{:4}".format(update)
+        if ep:
+            head += " reward={:.2f} std={:.2f} length={:.1f} std={:.2f}".format(ep["reward_mean"], ep["reward_std"],
+                                                                               ep["length_mean"], ep["length_std"])
+            if "success_mean" in ep:
+                head += " success={:.2f}".format(ep["success_mean"])
+        print(head + " pi_loss={:3f} v_loss={:3f} entropy={:.3f} loss={:3f} value={:.3f} advantage={:.3f}".format(
+            s[0], s[1], s[3], s[2], torch.mean(self.buffer.values).item(), torch.mean(self.buffer.advantages).item()))
+
+    # ------------------------------------------------------------------------------------------ rollout
+    def _sample_training_data(self):
+        """Run every worker for ``worker_steps`` steps (trainer.py:145-225)."""
+        t0 = time.perf_counter()
+        cfg, buf, model = self.config, self.buffer, self.model
+        W, T, L = self.num_workers, cfg["worker_steps"], self.memory_length
+        nb = len(self.action_space_shape)
+        episode_infos = []
+        self._begin_rollout()
+        flat_mask = buf.memory_mask.view(torch.uint8).view(W * T, L)
+        flat_idx = buf.memory_indices.view(W * T, L)
+        flat_ep = buf.memory_index.view(W * T)
+        inner = self.num_blocks * self.embed_dim
+        uniforms = torch.rand((T, W, nb), device=self.device)
+        ws = model.workspace(W)
+        outs = model._alloc_outputs(W, self.device)
+        stream = torch.cuda.current_stream()
+        env_time = 0.0
+        with torch.no_grad():
+            for t in range(T):
+                # observations: host -> pinned -> device, and into the buffer
+                self._obs_pinned.copy_(torch.from_numpy(self.obs))
+                self._obs_dev.copy_(self._obs_pinned, non_blocking=True)
+                buf.obs[:, t] = self._obs_dev
+                self._step_dev.copy_(self._step_host, non_blocking=True)
+                self._ep_dev.copy_(self._ep_host, non_blocking=True)
+                # mask / window rows of every worker's episode step straight into buffer[:, t]
+                native.rollout_prepare(self._step_dev, self._ep_dev, self._mask_table_dev, self._index_table_dev,
+                                       flat_mask.data_ptr() + t * L, T * L, flat_idx.data_ptr() + t * L * 8, T * L,
+                                       flat_ep.data_ptr() + t * 8, T, W, L)
+                rows = self._rollout_rows[t]
+                feat = model.encode(self._obs_dev)
+                logits, value, new_mem = model.forward_table(feat, self._table, flat_ep, flat_idx, flat_mask, flat_idx,
+                                                             sample_index=rows, n=W, ws=ws, out=outs)
+                native.memory_scatter(self._table, self._ep_dev, self._step_dev, new_mem, self.max_episode_length, inner)
+                forced = None if self._forced_actions is None else self._forced_actions[t]
+                native.sample_actions(logits, uniforms[t], self.action_space_shape, buf.actions.data_ptr() + t * nb * 8, T * nb,
+                                      buf.log_probs.data_ptr() + t * nb * 4, T * nb, self._act_dev, W, forced=forced)
+                buf.values[:, t] = value
+                self._act_pinned.copy_(self._act_dev, non_blocking=True)
+                stream.synchronize()
+                actions = self._act_pinned.numpy()
+                te = time.perf_counter()
+                for w, worker in enumerate(self.workers):
+                    worker.child.send(("step", actions[w].copy()))
+                for w, worker in enumerate(self.workers):
+                    obs, buf.rewards[w, t], buf.dones[w, t], info = worker.child.recv()
+                    if info:                                   # episode finished (trainer.py:195)
+                        self._step_host[w] = 0
+                        episode_infos.append(info)
+                        worker.child.send(("reset", None))
+                        obs = worker.child.recv()
+                        # the finished episode keeps its table row; the worker continues on a fresh zero row
+                        self._ep_host[w] = self._new_row()
+                        if t < T - 1:
+                            self._n_episodes = self._n_rows
+                    else:
+                        self._step_host[w] += 1
+                    self.obs[w] = obs
+                env_time += time.perf_counter() - te
+        last_value = self.get_last_value()
+        buf.calc_advantages(last_value, cfg["gamma"], cfg["lamda"])
+        buf.memories = self._table[:self._n_episodes]
+        self.timers["env"] += env_time
+        self.timers["rollout"] += time.perf_counter() - t0
+        return episode_infos
+
+    def get_last_value(self):
+        """Bootstrap value of the current observation (trainer.py:227-237).  Quirks kept: the window is
+        ``[clip(s-L,0), clip(s,L))`` and the positional indices are those of the last rollout step."""
+        W, L, T = self.num_workers, self.memory_length, self.config["worker_steps"]
+        step = self._step_host.clone()
+        start = torch.clip(step - L, 0)
+        self._win_last.copy_((start.unsqueeze(1) + torch.arange(L).unsqueeze(0)).to(self.device))
+        self._mask_last.copy_(self._mask_table_dev[torch.clip(step, 0, L - 1).to(self.device)])
+        self._step_dev.copy_(self._step_host, non_blocking=True)
+        self._ep_dev.copy_(self._ep_host, non_blocking=True)
+        with torch.no_grad():
+            self._obs_pinned.copy_(torch.from_numpy(self.obs))
+            self._obs_dev.copy_(self._obs_pinned, non_blocking=True)
+            feat = self.model.encode(self._obs_dev)
+            pe_idx = self.buffer.memory_indices[:, -1].contiguous()
+            _, value, _ = self.model.forward_table(feat, self._table, self._ep_dev, self._win_last, self._mask_last, pe_idx, n=W)
+        return value.clone()
+
+    # ------------------------------------------------------------------------------------------ optimisation
+    def _train_epochs(self, learning_rate, clip_range, beta):
+        """epochs x minibatches (trainer.py:239-256).  Returns (list of 6-stat lists, dict of grad-norm lists).
+        Statistics stay on the device until the end of the update: one host sync per update."""
+        t0 = time.perf_counter()
+        n_steps = self.config["epochs"] * (self.buffer.batch_size // self.buffer.mini_batch_size +
+                                           (1 if self.buffer.batch_size % self.buffer.mini_batch_size else 0))
+        g = self.model._n_groups
+        stats = torch.zeros((n_steps, 6), dtype=torch.float32, device=self.device)
+        norms = torch.zeros((n_steps, g + 2), dtype=torch.float32, device=self.device)
+        i = 0
+        for _ in range(self.config["epochs"]):
+            for mini_batch in self.buffer.mini_batch_generator():
+                self._ppo_step(mini_batch, learning_rate, clip_range, beta, stats[i], norms[i])
+                i += 1
+        stats, norms = stats[:i].cpu(), norms[:i].cpu()           # the only sync of the update
+        if self.dp.world_size > 1:
+            pass                                                   # stats were all-reduced on the device
+        train_info = [[np.float32(v) for v in row] for row in stats.tolist()]
+        grad_info = {}
+        for row in norms:
+            for key, value in self.model.grad_norms_from(row).items():
+                grad_info.setdefault(key, []).append(value)
+        self.timers["train"] += time.perf_counter() - t0
+        return train_info, grad_info
+
+    def _train_mini_batch(self, samples, learning_rate, clip_range, beta):
+        """One optimiser step on one minibatch (trainer.py:258-323).  ``samples`` is either a ``MiniBatch``
+        from this package's buffer or a plain dict with the reference's keys (materialised tensors).
+        Returns [policy_loss, vf_loss, loss, entropy, approx_kl, clip_fraction] as numpy scalars."""
+        g = self.model._n_groups
+        stats = torch.zeros(6, dtype=torch.float32, device=self.device)
+        self._last_norms = torch.zeros(g + 2, dtype=torch.float32, device=self.device)
+        self._ppo_step(samples, learning_rate, clip_range, beta, stats, self._last_norms)
+        return [np.asarray(v, dtype=np.float32) for v in stats.cpu().tolist()]
+
+    def _scratch(self, n):
+        st = self._train_state.get(n)
+        if st is None:
+            dev, model = self.device, self.model
+            st = {
+                "ws": torch.empty(model._ws_floats(n), dtype=torch.float32, device=dev),
+                "out": model._alloc_outputs(n, dev),
+                "dlogits": torch.empty((n, model._sum_actions), dtype=torch.float32, device=dev),
+                "dvalue": torch.empty((n,), dtype=torch.float32, device=dev),
+                "advstats": torch.zeros(3, dtype=torch.float64, device=dev),
+                "loss_scratch": torch.empty(n // 128 * 5 + 64, dtype=torch.float32, device=dev),
+                "dfeat": torch.empty((n, model._feat_dim), dtype=torch.float32, device=dev) if model._visual else None,
+                "obs": torch.empty((n,) + self.obs_shape, dtype=torch.float32, device=dev),
+            }
+            self._train_state = {n: st}          # keep one size resident
+        return st
+
+    def _ppo_step(self, samples, learning_rate, clip_range, beta, stats_out, norms_out):
+        model, cfg = self.model, self.config
+        if isinstance(samples, MiniBatch):
+            buf = samples.buffer
+            flat = buf.samples_flat
+            sidx = samples.sample_index
+            n = sidx.shape[0]
+            st = self._scratch(n)
+            native.gather_rows(flat["obs"], sidx, st["obs"])
+            obs = st["obs"]
+            table = buf.memories
+            ep_index, win_index = flat["memory_index"], flat["memory_indices"]
+            mask = flat["memory_mask"].view(torch.uint8)
+            actions, old_logp, old_values, adv = flat["actions"], flat["log_probs"], flat["values"], flat["advantages"]
+        else:   # reference-style dict of materialised tensors (trainer.py:271-274)
+            dev = self.device
+            obs = samples["obs"].to(dev, torch.float32).contiguous()
+            n = obs.shape[0]
+            st = self._scratch(n)
+            sidx = None
+            table = samples["memories"].to(dev, torch.float32).contiguous()          # (n, M, B, D), episode n <-> sample n
+            ep_index = None
+            win_index = samples["memory_indices"].to(dev, torch.int64).contiguous()
+            mask = (samples["memory_mask"].to(dev) != 0).to(torch.uint8).contiguous()
+            actions = samples["actions"].to(dev, torch.int64).contiguous()
+            old_logp = samples["log_probs"].to(dev, torch.float32).contiguous()
+            old_values = samples["values"].to(dev, torch.float32).contiguous()
+            adv = samples["advantages"].to(dev, torch.float32).contiguous()
+        pe_index = win_index
+
+        for group in self.optimizer.param_groups:
+            group["lr"] = learning_rate
+        self.optimizer.zero_grad()
+        # encoder (cuDNN) with autograd so its backward can be driven by d loss / d features
+        if model._visual:
+            with torch.enable_grad():
+                feat_g = model.encode(obs)
+            feat = feat_g.detach().contiguous()
+        else:
+            feat_g, feat = None, obs.reshape(n, -1)
+        logits, value, out_mem = st["out"]
+        native.model_forward(model._cfg, model.flat_parameters(), feat, table, table.shape[1], ep_index, win_index, mask,
+                             pe_index, sidx, model._pe_table(), n, st["ws"], logits, value, out_mem)
+        native.adv_stats(adv, sidx, n, st["advstats"])
+        self.dp.all_reduce_(st["advstats"])
+        native.ppo_loss(logits, value, actions, old_logp, old_values, adv, sidx, st["advstats"], self.action_space_shape, n,
+                        clip_range, beta, cfg["value_loss_coefficient"], st["dlogits"], st["dvalue"], stats_out,
+                        st["loss_scratch"])
+        native.model_backward(model._cfg, model.flat_parameters(), model.flat_grads(), feat, table, table.shape[1], ep_index,
+                              win_index, mask, pe_index, sidx, model._pe_table(), n, st["ws"], out_mem, st["dlogits"],
+                              st["dvalue"], st["dfeat"])
+        if feat_g is not None:
+            feat_g.backward(st["dfeat"])           # accumulates into the conv slices of the gradient arena
+        if self.dp.world_size > 1:
+            self.dp.all_reduce_(model.flat_grads())     # ONE collective per optimiser step: the flat gradient arena
+            self.dp.all_reduce_(stats_out)
+        self.optimizer.step(norms_out=norms_out)
+
+    # ------------------------------------------------------------------------------------------ logging / io
+    def _write_training_summary(self, update, training_stats, episode_result):
+        if self.writer is None:
+            return
+        for key, value in (episode_result or {}).items():
+            if "std" not in key:
+                self.writer.add_scalar("episode/" + key, value, update)
+        names = ("losses/policy_loss", "losses/value_loss", "losses/loss", "losses/entropy")
+        for name, value in zip(names, training_stats[:4]):
+            self.writer.add_scalar(name, value, update)
+        self.writer.add_scalar("training/value_mean", torch.mean(self.buffer.values).item(), update)
+        self.writer.add_scalar("training/advantage_mean", torch.mean(self.buffer.advantages).item(), update)
+        # the reference writes stats[4] (KL) under "clip_fraction" and stats[5] under "kl" (trainer.py:343-344);
+        # the tags are kept so dashboards line up with reference runs
+        self.writer.add_scalar("other/clip_fraction", training_stats[4], update)
+        self.writer.add_scalar("other/kl", training_stats[5], update)
+
+    def _write_gradient_summary(self, update, grad_info):
+        if self.writer is None:
+            return
+        for key, value in grad_info.items():
+            self.writer.add_scalar("gradients/" + key, np.mean(value), update)
+
+    def _save_model(self):
+        """``(state_dict, config)`` pickle at ./models/<run_id>.nn, the reference's checkpoint format (trainer.py:356-362)."""
+        os.makedirs("./models", exist_ok=True)
+        state = {k: v.detach().cpu().clone() for k, v in self.model.state_dict().items()}
+        with open("./models/" + self.run_id + ".nn", "wb") as f:
+            pickle.dump((state, self.config), f)
+        print("Model saved to ./models/" + self.run_id + ".nn")
+
+    def close(self, exit_process=True):
+        """Shut down workers and the summary writer (trainer.py:364-383; the reference also exits the process)."""
+        try:
+            if self.writer is not None:
+                self.writer.close()
+        except Exception:
+            pass
+        for worker in self.workers:
+            try:
+                worker.child.send(("close", None))
+            except Exception:
+                pass
+        time.sleep(0.2)
+        for worker in self.workers:
+            proc = getattr(worker, "process", None)
+            if proc is not None:
+                proc.join(timeout=1.0)
+                if proc.is_alive():
+                    proc.terminate()
+        if exit_process:
+            raise SystemExit(0)

@@ -1,0 +1,262 @@
+"""ctypes binding of libtrxlppo.so (C ABI in include/trxl_ppo.h).
+
+PyTorch is only the owner of device memory and streams here: every wrapper passes raw
+``tensor.data_ptr()`` values plus the current CUDA stream handle.  There is NO CPU fallback: if the
+shared library is missing or a symbol is absent, importing callers fail with an error that says how
+to build it (``python __graft_entry__.py``)."""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtrxlppo.so")
+MAX_BRANCHES = 8
+LN_MODES = {"": 0, None: 0, "pre": 1, "post": 2}
+PE_MODES = {"": 0, None: 0, "relative": 1, "learned": 2}
+
+_lib = None
+
+vp, i32, i64, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_double
+
+
+class ModelConfig(C.Structure):
+    _fields_ = [("embed_dim", C.c_int32), ("num_heads", C.c_int32), ("num_blocks", C.c_int32),
+                ("memory_length", C.c_int32), ("hidden_size", C.c_int32), ("feat_dim", C.c_int32),
+                ("layer_norm", C.c_int32), ("pos_enc", C.c_int32), ("gtrxl", C.c_int32),
+                ("max_episode_steps", C.c_int32), ("num_branches", C.c_int32),
+                ("branch_sizes", C.c_int32 * MAX_BRANCHES), ("conv_in_channels", C.c_int32)]
+
+
+class ParamEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 96), ("offset", C.c_int64), ("ndim", C.c_int32), ("shape", C.c_int64 * 4),
+                ("group", C.c_int32)]
+
+
+CFGP = C.POINTER(ModelConfig)
+
+# name -> (restype, argtypes); this is the full exported surface of include/trxl_ppo.h
+SIGNATURES = {
+    "trxl_last_error": (C.c_char_p, []),
+    "trxl_abi_version": (i32, []),
+    "trxl_layout_num_entries": (i32, [CFGP]),
+    "trxl_layout_total_floats": (i64, [CFGP]),
+    "trxl_layout_entry": (i32, [CFGP, i32, C.POINTER(ParamEntry)]),
+    "trxl_layout_groups": (i32, [CFGP]),
+    "trxl_workspace_floats": (i64, [CFGP, i32]),
+    "trxl_model_forward": (i32, [CFGP, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
+    "trxl_model_backward": (i32, [CFGP, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]),
+    "trxl_window_attention_forward": (i32, [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "trxl_window_attention_backward": (i32, [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32,
+                                             vp, vp, vp, vp]),
+    "trxl_linear_forward": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "trxl_linear_backward": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]),
+    "trxl_layernorm_forward": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, vp]),
+    "trxl_layernorm_backward": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]),
+    "trxl_gather_window": (i32, [vp, vp, vp, i64, i32, i64, i64, vp]),
+    "trxl_gather_rows": (i32, [vp, vp, vp, i64, i64, vp]),
+    "trxl_gae": (i32, [vp, vp, vp, vp, vp, i32, i32, f64, f64, vp]),
+    "trxl_rollout_prepare": (i32, [vp, vp, vp, vp, vp, i64, vp, i64, vp, i64, i32, i32, vp]),
+    "trxl_memory_scatter": (i32, [vp, vp, vp, vp, i32, i64, i64, vp]),
+    "trxl_sample_actions": (i32, [vp, vp, vp, C.POINTER(C.c_int32), i32, vp, i64, vp, i64, vp, i32, vp]),
+    "trxl_adv_stats": (i32, [vp, vp, i32, vp, vp]),
+    "trxl_ppo_loss": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int32), i32, i32, f64, f64, f64, vp, vp, vp, vp, vp]),
+    "trxl_clip_adamw_step": (i32, [vp, vp, vp, vp, i64, vp, i32, i32, f64, f64, f64, f64, f64, f64, i64, vp, vp, vp]),
+}
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libtrxlppo.so and bind every symbol of the ABI.  Raises NativeLibraryError (never
+    falls back to another implementation) when the library or a symbol is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError("%s not found: build it with `python __graft_entry__.py` (nvcc, sm_100a). "
+                                 "This engine has no CPU/PyTorch fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise NativeLibraryError("libtrxlppo.so does not export %s (stale build?)" % name) from e
+        fn.restype, fn.argtypes = res, args
+    if lib.trxl_abi_version() != 1:
+        raise NativeLibraryError("libtrxlppo.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, _lib.trxl_last_error().decode()))
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    """Device pointer of a tensor (None -> NULL).  Tensors must be CUDA and contiguous."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise NativeLibraryError("libtrxlppo operates on CUDA tensors only (got %s); no CPU fallback exists" % t.device)
+    assert t.is_contiguous(), "non-contiguous tensor passed to native op"
+    return t.data_ptr()
+
+
+def branch_array(sizes):
+    arr = (C.c_int32 * len(sizes))(*[int(s) for s in sizes])
+    return arr
+
+
+def make_config(embed_dim, num_heads, num_blocks, memory_length, hidden_size, feat_dim, layer_norm, pos_enc, gtrxl,
+                max_episode_steps, branch_sizes, conv_in_channels=0):
+    cfg = ModelConfig()
+    cfg.embed_dim, cfg.num_heads, cfg.num_blocks, cfg.memory_length = embed_dim, num_heads, num_blocks, memory_length
+    cfg.hidden_size, cfg.feat_dim = hidden_size, feat_dim
+    cfg.layer_norm = LN_MODES[layer_norm] if not isinstance(layer_norm, int) else layer_norm
+    cfg.pos_enc = PE_MODES[pos_enc] if not isinstance(pos_enc, int) else pos_enc
+    cfg.gtrxl = int(bool(gtrxl))
+    cfg.max_episode_steps = int(max_episode_steps)
+    cfg.num_branches = len(branch_sizes)
+    for i, s in enumerate(branch_sizes):
+        cfg.branch_sizes[i] = int(s)
+    cfg.conv_in_channels = int(conv_in_channels)
+    return cfg
+
+
+def layout(cfg):
+    """[(name, offset, shape, group)], total floats, number of grad-norm groups."""
+    lib = load()
+    n = lib.trxl_layout_num_entries(C.byref(cfg))
+    if n < 0:
+        raise ValueError("invalid model config: " + lib.trxl_last_error().decode())
+    out = []
+    e = ParamEntry()
+    for i in range(n):
+        _check(lib.trxl_layout_entry(C.byref(cfg), i, C.byref(e)), "trxl_layout_entry")
+        out.append((e.name.decode(), int(e.offset), tuple(int(e.shape[k]) for k in range(e.ndim)), int(e.group)))
+    return out, int(lib.trxl_layout_total_floats(C.byref(cfg))), int(lib.trxl_layout_groups(C.byref(cfg)))
+
+
+def workspace_floats(cfg, n):
+    v = load().trxl_workspace_floats(C.byref(cfg), int(n))
+    if v < 0:
+        raise ValueError("invalid config: " + _lib.trxl_last_error().decode())
+    return int(v)
+
+
+def model_forward(cfg, params, feat, table, slots, ep_index, win_index, mask, pe_index, sample_index, pe_table, n, ws,
+                  logits, value, out_mem):
+    lib = load()
+    _check(lib.trxl_model_forward(C.byref(cfg), _p(params), _p(feat), _p(table), int(slots), _p(ep_index), _p(win_index),
+                                  _p(mask), _p(pe_index), _p(sample_index), _p(pe_table), int(n), _p(ws), _p(logits),
+                                  _p(value), _p(out_mem), _stream()), "trxl_model_forward")
+
+
+def model_backward(cfg, params, grads, feat, table, slots, ep_index, win_index, mask, pe_index, sample_index, pe_table, n, ws,
+                   out_mem, dlogits, dvalue, dfeat):
+    lib = load()
+    _check(lib.trxl_model_backward(C.byref(cfg), _p(params), _p(grads), _p(feat), _p(table), int(slots), _p(ep_index),
+                                   _p(win_index), _p(mask), _p(pe_index), _p(sample_index), _p(pe_table), int(n), _p(ws),
+                                   _p(out_mem), _p(dlogits), _p(dvalue), _p(dfeat), _stream()), "trxl_model_backward")
+
+
+def window_attention_forward(table, slots, num_blocks, block, ep_index, win_index, mask, pe_index, sample_index, pe_table, qk,
+                             qkb, ln, n, L, D, H, probs, ctx):
+    lib = load()
+    _check(lib.trxl_window_attention_forward(_p(table), int(slots), num_blocks, block, _p(ep_index), _p(win_index), _p(mask),
+                                             _p(pe_index), _p(sample_index), _p(pe_table), _p(qk), _p(qkb), int(ln), n, L, D, H,
+                                             _p(probs), _p(ctx), _stream()), "trxl_window_attention_forward")
+
+
+def window_attention_backward(table, slots, num_blocks, block, ep_index, win_index, mask, pe_index, sample_index, pe_table, qk,
+                              probs, ctx, dctx, ln, n, L, D, H, dqk, dqkb, dpe):
+    lib = load()
+    _check(lib.trxl_window_attention_backward(_p(table), int(slots), num_blocks, block, _p(ep_index), _p(win_index), _p(mask),
+                                              _p(pe_index), _p(sample_index), _p(pe_table), _p(qk), _p(probs), _p(ctx),
+                                              _p(dctx), int(ln), n, L, D, H, _p(dqk), _p(dqkb), _p(dpe), _stream()),
+           "trxl_window_attention_backward")
+
+
+def linear_forward(x, w, bias, y, relu=False):
+    m, k = x.shape
+    n = w.shape[0]
+    _check(load().trxl_linear_forward(_p(x), _p(w), _p(bias), _p(y), m, n, k, int(relu), _stream()), "trxl_linear_forward")
+
+
+def linear_backward(dy, x, w, dx, dw, db, scratch):
+    m, n = dy.shape
+    k = w.shape[1] if w is not None else x.shape[1]
+    _check(load().trxl_linear_backward(_p(dy), _p(x), _p(w), _p(dx), _p(dw), _p(db), m, n, k, _p(scratch), _stream()),
+           "trxl_linear_backward")
+
+
+def layernorm_forward(x, gamma, beta, y, mean, rstd):
+    rows, d = x.shape
+    _check(load().trxl_layernorm_forward(_p(x), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), rows, d, _stream()),
+           "trxl_layernorm_forward")
+
+
+def layernorm_backward(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, scratch):
+    rows, d = x.shape
+    _check(load().trxl_layernorm_backward(_p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dx), _p(dgamma), _p(dbeta),
+                                          _p(scratch), rows, d, _stream()), "trxl_layernorm_backward")
+
+
+def gather_window(src, index, out):
+    n, slots = src.shape[0], src.shape[1]
+    inner = src[0, 0].numel()
+    _check(load().trxl_gather_window(_p(src), _p(index), _p(out), n, index.shape[1], slots, inner, _stream()), "trxl_gather_window")
+
+
+def gather_rows(src, index, dst):
+    rows = index.shape[0]
+    row_floats = src[0].numel()
+    _check(load().trxl_gather_rows(_p(src), _p(index), _p(dst), rows, row_floats, _stream()), "trxl_gather_rows")
+
+
+def gae(rewards, dones, values, last_value, adv, gamma, lamda):
+    w, t = values.shape
+    _check(load().trxl_gae(_p(rewards), _p(dones), _p(values), _p(last_value), _p(adv), w, t, float(gamma), float(lamda),
+                           _stream()), "trxl_gae")
+
+
+def rollout_prepare(step, ep, mask_table, index_table, mask_out_ptr, mask_stride, idx_out_ptr, idx_stride, ep_out_ptr,
+                    ep_stride, w, L):
+    _check(load().trxl_rollout_prepare(_p(step), _p(ep), _p(mask_table), _p(index_table), mask_out_ptr, mask_stride,
+                                       idx_out_ptr, idx_stride, ep_out_ptr, ep_stride, w, L, _stream()), "trxl_rollout_prepare")
+
+
+def memory_scatter(table, ep, step, new_mem, slots, inner):
+    _check(load().trxl_memory_scatter(_p(table), _p(ep), _p(step), _p(new_mem), ep.shape[0], int(slots), int(inner), _stream()),
+           "trxl_memory_scatter")
+
+
+def sample_actions(logits, u, branch_sizes, act_ptr, act_stride, logp_ptr, logp_stride, act_compact, w, forced=None):
+    _check(load().trxl_sample_actions(_p(logits), _p(u), _p(forced), branch_array(branch_sizes), len(branch_sizes), act_ptr, act_stride,
+                                      logp_ptr, logp_stride, _p(act_compact), w, _stream()), "trxl_sample_actions")
+
+
+def adv_stats(adv, sample_index, n, out3):
+    _check(load().trxl_adv_stats(_p(adv), _p(sample_index), n, _p(out3), _stream()), "trxl_adv_stats")
+
+
+def ppo_loss(logits, value, actions, old_logp, old_values, adv, sample_index, adv_stats3, branch_sizes, n, clip, beta, vf_coef,
+             dlogits, dvalue, stats6, scratch):
+    _check(load().trxl_ppo_loss(_p(logits), _p(value), _p(actions), _p(old_logp), _p(old_values), _p(adv), _p(sample_index),
+                                _p(adv_stats3), branch_array(branch_sizes), len(branch_sizes), n, float(clip), float(beta),
+                                float(vf_coef), _p(dlogits), _p(dvalue), _p(stats6), _p(scratch), _stream()), "trxl_ppo_loss")
+
+
+def clip_adamw_step(params, grads, m, v, total, chunks, nchunks, ngroups, max_norm, lr, step, partial, norms,
+                    betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01):
+    _check(load().trxl_clip_adamw_step(_p(params), _p(grads), _p(m), _p(v), int(total), _p(chunks), int(nchunks), int(ngroups),
+                                       float(max_norm), float(lr), float(betas[0]), float(betas[1]), float(eps),
+                                       float(weight_decay), int(step), _p(partial), _p(norms), _stream()), "trxl_clip_adamw_step")

@@ -1,0 +1,165 @@
+/* libtrxlppo -- C ABI of the B200-native PPO + TransformerXL hot path.
+ *
+ * The reference (MarcoMeter/episodic-transformer-memory-ppo) is pure Python/PyTorch and has no FFI;
+ * each entry point below names the reference code it replaces (file:line under /root/reference).
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, <0 = error (TRXL_ERR_*); trxl_last_error() gives a
+ *     thread-local message.  Nothing throws across this boundary.
+ *   - all tensor arguments are raw DEVICE pointers into memory the caller owns (fp32 `float`,
+ *     int64 `long long`, bool `unsigned char`), row-major, 16-byte aligned unless stated otherwise.
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on that stream and
+ *     never synchronises, allocates or frees device memory.
+ *   - no CPU fallback exists: these kernels are built for sm_100a only.
+ */
+#ifndef TRXL_PPO_H
+#define TRXL_PPO_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRXL_ABI_VERSION 1
+#define TRXL_MAX_BRANCHES 8
+
+enum { TRXL_LN_NONE = 0, TRXL_LN_PRE = 1, TRXL_LN_POST = 2 };        /* config["transformer"]["layer_norm"] */
+enum { TRXL_PE_NONE = 0, TRXL_PE_RELATIVE = 1, TRXL_PE_LEARNED = 2 }; /* ...["positional_encoding"]          */
+
+/* Model hyper-parameters (reference configs/ *.yaml + environment spaces, model.py:11-69). */
+typedef struct trxl_model_config {
+    int32_t embed_dim;          /* transformer.embed_dim (multiple of 4)                */
+    int32_t num_heads;          /* transformer.num_heads                                */
+    int32_t num_blocks;         /* transformer.num_blocks                               */
+    int32_t memory_length;      /* transformer.memory_length                            */
+    int32_t hidden_size;        /* hidden_layer_size (multiple of 4)                    */
+    int32_t feat_dim;           /* inputs of lin_hidden: conv features or vector-obs dim */
+    int32_t layer_norm;         /* TRXL_LN_*                                            */
+    int32_t pos_enc;            /* TRXL_PE_*                                            */
+    int32_t gtrxl;              /* 0/1                                                  */
+    int32_t max_episode_steps;  /* rows of the positional table                         */
+    int32_t num_branches;       /* len(action_space_shape)                              */
+    int32_t branch_sizes[TRXL_MAX_BRANCHES];
+    int32_t conv_in_channels;   /* >0: reserve conv1..3 parameters (visual obs) in the arena */
+} trxl_model_config;
+
+/* One parameter of the flat arena, named as in the reference state_dict. */
+typedef struct trxl_param_entry {
+    char name[96];
+    int64_t offset;             /* in floats from the arena base (multiple of 4)        */
+    int32_t ndim;
+    int64_t shape[4];
+    int32_t group;              /* gradient-norm group, see trxl_layout_groups          */
+} trxl_param_entry;
+
+const char* trxl_last_error(void);
+int trxl_abi_version(void);
+
+/* ---- parameter arena layout ------------------------------------------------------------------ */
+/* Number of entries / total floats of the arena for a config (<0 on invalid config). */
+int trxl_layout_num_entries(const trxl_model_config* cfg);
+int64_t trxl_layout_total_floats(const trxl_model_config* cfg);
+int trxl_layout_entry(const trxl_model_config* cfg, int index, trxl_param_entry* out);
+/* Number of gradient-norm groups G (reference model.py:128-151): 0 encoder, 1 linear_layer,
+ * 2..2+B-1 transformer_block_i, then policy_head_k, lin_policy, lin_value, value (head), other. */
+int trxl_layout_groups(const trxl_model_config* cfg);
+
+/* ---- model forward / backward (everything after the CNN) -------------------------------------- */
+/* floats of workspace needed by trxl_model_forward/backward for N samples */
+int64_t trxl_workspace_floats(const trxl_model_config* cfg, int N);
+
+/* Replaces ActorCriticModel.forward from lin_hidden on (model.py:97-110) and Transformer.forward
+ * (transformer.py:222-253) including the window gather (utils.py:52-75, buffer.py:90,
+ * trainer.py:168,233,271) -- the window is read in place from the episode table.
+ *   feat        (N, feat_dim)        encoder features (flattened conv output or the vector obs)
+ *   table       (E, slots, B, D)     episodic memory; sample n reads episode ep_index[row]
+ *   ep_index    (rows,)  or NULL -> row        win_index (rows, L) or NULL -> 0..L-1
+ *   mask        (rows, L) bool       pe_index (rows, L)      sample_index (N,) or NULL -> n
+ *     (row = sample_index[n]; lets a minibatch address the flat rollout buffer without copies)
+ *   pe_table    (max_episode_steps, D) for TRXL_PE_RELATIVE (host-built sinusoid), else NULL
+ * Outputs: logits (N, sum A) raw, value (N,), out_mem (N, B, D) = inputs of every block. */
+int trxl_model_forward(const trxl_model_config* cfg, const float* params, const float* feat, const float* table,
+                       int64_t slots, const int64_t* ep_index, const int64_t* win_index, const uint8_t* mask,
+                       const int64_t* pe_index, const int64_t* sample_index, const float* pe_table, int N,
+                       float* workspace, float* logits, float* value, float* out_mem, void* stream);
+
+/* Backward of the above given d loss/d logits (N, sum A) and d loss/d value (N,): writes every
+ * parameter gradient at its arena offset in `grads` (overwrite, except pos_embedding which is
+ * accumulated with atomics and must be zeroed by the caller) and, if dfeat != NULL, d loss/d feat.
+ * Must follow a trxl_model_forward with the same arguments, workspace and out_mem (autograd of
+ * trainer.py:310 for this part of the graph). */
+int trxl_model_backward(const trxl_model_config* cfg, const float* params, float* grads, const float* feat,
+                        const float* table, int64_t slots, const int64_t* ep_index, const int64_t* win_index,
+                        const uint8_t* mask, const int64_t* pe_index, const int64_t* sample_index,
+                        const float* pe_table, int N, float* workspace, const float* out_mem, const float* dlogits,
+                        const float* dvalue, float* dfeat, void* stream);
+
+/* ---- the hot kernel on its own ---------------------------------------------------------------- */
+/* Fused window gather + PE add + [LayerNorm] + q.K + mask + softmax(/sqrt(D)) + P.V with the K/V
+ * projections folded onto the query side (MultiHeadAttention.forward transformer.py:31-86 for query
+ * length 1).  qk (N,H,D) = per-head Q_h Wk_h; outputs probs (N,H,L) and ctx (N,H,D) = sum_l p x_l. */
+int trxl_window_attention_forward(const float* table, int64_t slots, int num_blocks, int block, const int64_t* ep_index,
+                                  const int64_t* win_index, const uint8_t* mask, const int64_t* pe_index,
+                                  const int64_t* sample_index, const float* pe_table, const float* qk, const float* qkb,
+                                  int layer_norm_rows, int N, int L, int D, int H, float* probs, float* ctx, void* stream);
+int trxl_window_attention_backward(const float* table, int64_t slots, int num_blocks, int block, const int64_t* ep_index,
+                                   const int64_t* win_index, const uint8_t* mask, const int64_t* pe_index,
+                                   const int64_t* sample_index, const float* pe_table, const float* qk, const float* probs,
+                                   const float* ctx, const float* dctx, int layer_norm_rows, int N, int L, int D, int H,
+                                   float* dqk, float* dqkb, float* dpe, void* stream);
+
+/* ---- building blocks (exported for tests and for callers that keep their own graph) ----------- */
+/* y (M,N) = relu?(x (M,K) W(N,K)^T + bias) : nn.Linear forward */
+int trxl_linear_forward(const float* x, const float* W, const float* bias, float* y, int M, int N, int K, int relu, void* stream);
+/* dx = dy W ; dW = dy^T x ; db = colsum(dy)   (any of dx/dW/db may be NULL); scratch >= 64*N+64 floats */
+int trxl_linear_backward(const float* dy, const float* x, const float* W, float* dx, float* dW, float* db, int M, int N, int K,
+                         float* scratch, void* stream);
+/* nn.LayerNorm(D) forward, eps 1e-5; saves mean/rstd (rows,) */
+int trxl_layernorm_forward(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd, int rows,
+                           int D, void* stream);
+int trxl_layernorm_backward(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, float* dx,
+                            float* dgamma, float* dbeta, float* scratch, int rows, int D, void* stream);
+/* batched_index_select(input, 1, index) (utils.py:52-75): out (N,L,inner) = in (N,slots,inner)[n, idx[n,l]] */
+int trxl_gather_window(const float* in, const int64_t* index, float* out, int64_t N, int L, int64_t slots, int64_t inner, void* stream);
+/* dst (rows, row_floats) = src[index[r]]  (minibatch gather of observations, buffer.py:92) */
+int trxl_gather_rows(const float* src, const int64_t* index, float* dst, int64_t rows, int64_t row_floats, void* stream);
+
+/* ---- PPO data path ---------------------------------------------------------------------------- */
+/* Buffer.calc_advantages (buffer.py:95-113): rewards/values/adv (W,T) fp32, dones (W,T) bool.
+ * Bit-identical to the reference's fp32 CPU result. */
+int trxl_gae(const float* rewards, const uint8_t* dones, const float* values, const float* last_value, float* advantages,
+             int W, int T, double gamma, double lamda, void* stream);
+/* trainer.py:165-166: write mask/window-index rows of every worker's current episode step into
+ * the rollout buffer (strided destinations), plus the episode id. */
+int trxl_rollout_prepare(const int64_t* step, const int64_t* ep, const uint8_t* mask_table, const int64_t* index_table,
+                         uint8_t* mask_out, int64_t mask_stride, int64_t* idx_out, int64_t idx_stride, int64_t* ep_out,
+                         int64_t ep_stride, int W, int L, void* stream);
+/* trainer.py:174: table[ep[w], step[w]] = new_mem[w] (inner = B*D floats) */
+int trxl_memory_scatter(float* table, const int64_t* ep, const int64_t* step, const float* new_mem, int W, int64_t slots,
+                        int64_t inner, void* stream);
+/* trainer.py:177-186: sample each branch from softmax(logits) with caller-supplied uniforms u (W, nb)
+ * (inverse CDF); if forced_actions (W, nb) != NULL those actions are taken instead (trajectory replay)
+ * and only their log-probabilities are computed. */
+int trxl_sample_actions(const float* logits, const float* u, const int64_t* forced_actions, const int32_t* branch_sizes,
+                        int num_branches, int64_t* actions, int64_t act_stride, float* log_probs, int64_t logp_stride,
+                        int64_t* actions_compact, int W, void* stream);
+/* {sum a, sum a^2, count} of the minibatch advantages as doubles (all-reduce these across ranks) */
+int trxl_adv_stats(const float* advantages, const int64_t* sample_index, int N, double* out3, void* stream);
+/* trainer.py:277-304,315-316 forward + backward: stats6 = [policy_loss, vf_loss, loss, entropy,
+ * approx_kl, clip_fraction]; dlogits (N, sum A), dvalue (N). scratch >= N/128*5+16 floats */
+int trxl_ppo_loss(const float* logits, const float* value, const int64_t* actions, const float* old_log_probs,
+                  const float* old_values, const float* advantages, const int64_t* sample_index, const double* adv_stats3,
+                  const int32_t* branch_sizes, int num_branches, int N, double clip_range, double beta, double vf_coef,
+                  float* dlogits, float* dvalue, float* stats6, float* scratch, void* stream);
+/* clip_grad_norm_ + AdamW.step (trainer.py:311-312) + get_grad_norm sums (model.py:128-151) over the
+ * flat arena.  chunks (nchunks,3) int64 {start,len,group}; norms (G+2): per-group norms of the
+ * UNCLIPPED grads, total norm, clip coefficient.  Grads are overwritten with the clipped grads. */
+int trxl_clip_adamw_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t total_floats,
+                         const int64_t* chunks, int nchunks, int ngroups, double max_grad_norm, double lr, double beta1,
+                         double beta2, double eps, double weight_decay, int64_t step, float* partial, float* norms, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRXL_PPO_H */

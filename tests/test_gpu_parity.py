@@ -1,0 +1,237 @@
+"""CUDA path vs the reference (golden fixtures) and vs the CPU oracle.  Everything here calls through
+the C ABI of libtrxlppo (ctypes) on a real GPU: `pytest -m gpu`.
+
+Tolerances: integer / bool outputs bit-exact; GAE bit-exact; fp32 activations 1e-4 (BASELINE.json
+north_star); gradients 2e-4 relative to the tensor's max magnitude; parameters after AdamW 2e-5 abs."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden
+from parity_util import HEADS, build_model, run_minibatch_parity
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def dev(x, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(x))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(DEV).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ units
+def test_gae_bit_exact_golden_and_large():
+    import trxl_native as native
+    from oracle import ppo_oracle as O
+    g = load_golden("units")
+    for name in ("gae_a", "gae_b"):
+        adv = torch.zeros_like(dev(g[name + ".values"]))
+        native.gae(dev(g[name + ".rewards"]), dev(g[name + ".dones"].astype(np.uint8)), dev(g[name + ".values"]),
+                   dev(g[name + ".last_value"]), adv, float(g[name + ".gamma"]), float(g[name + ".lamda"]))
+        assert np.array_equal(adv.cpu().numpy(), g[name + ".adv"])
+    # BASELINE sizes (W=32, T=512) and a ragged one, against the oracle, bit for bit
+    for w, t in ((32, 512), (256, 512), (7, 45), (1, 1)):
+        rng = np.random.default_rng(w * 1000 + t)
+        rewards = rng.normal(size=(w, t)).astype(np.float32)
+        dones = rng.random((w, t)) < 0.02
+        values = torch.from_numpy(rng.normal(size=(w, t)).astype(np.float32))
+        lv = torch.from_numpy(rng.normal(size=(w,)).astype(np.float32))
+        want = O.gae(lv, rewards, dones, values, 0.995, 0.95)
+        adv = torch.zeros((w, t), device=DEV)
+        native.gae(dev(rewards), dev(dones.astype(np.uint8)), values.to(DEV), lv.to(DEV), adv, 0.995, 0.95)
+        assert np.array_equal(adv.cpu().numpy(), want.numpy()), (w, t)
+
+
+def test_gather_window_and_rows_bit_exact():
+    import trxl_native as native
+    g = load_golden("units")
+    src, idx = dev(g["bis.src"]), dev(g["bis.idx"])
+    out = torch.empty((4, 5, 2, 3), device=DEV)
+    native.gather_window(src, idx, out)
+    assert np.array_equal(out.cpu().numpy(), g["bis.out"])
+    from utils import batched_index_select
+    assert np.array_equal(batched_index_select(src, 1, idx).cpu().numpy(), g["bis.out"])
+    rows = torch.randn(100, 21168, device=DEV)
+    pick = torch.randint(0, 100, (37,), device=DEV)
+    dst = torch.empty((37, 21168), device=DEV)
+    native.gather_rows(rows, pick, dst)
+    assert torch.equal(dst, rows[pick])
+
+
+@pytest.mark.parametrize("m,n,k", [(5, 7, 3), (32, 256, 256), (2048, 256, 256), (64, 3, 384), (300, 384, 3136), (1, 16, 16)])
+def test_linear_forward_backward(m, n, k):
+    import trxl_native as native
+    torch.manual_seed(m + n + k)
+    x, w, b = torch.randn(m, k, device=DEV), torch.randn(n, k, device=DEV) / k ** 0.5, torch.randn(n, device=DEV)
+    y = torch.empty(m, n, device=DEV)
+    native.linear_forward(x, w, b, y, relu=True)
+    want = torch.relu(x.double() @ w.double().t() + b.double())
+    assert torch.allclose(y.double(), want, atol=1e-4, rtol=1e-4)
+    dy = torch.randn(m, n, device=DEV)
+    dx, dw, db = torch.empty_like(x), torch.empty_like(w), torch.empty_like(b)
+    scratch = torch.empty(64 * n + 64, device=DEV)
+    native.linear_backward(dy, x, w, dx, dw, db, scratch)
+    assert torch.allclose(dx.double(), dy.double() @ w.double(), atol=1e-4, rtol=1e-4)
+    assert torch.allclose(dw.double(), dy.double().t() @ x.double(), atol=2e-4 * max(1, m ** 0.5), rtol=1e-4)
+    assert torch.allclose(db.double(), dy.double().sum(0), atol=1e-4 * max(1, m ** 0.5), rtol=1e-4)
+
+
+@pytest.mark.parametrize("rows,d", [(6, 16), (33, 48), (2048, 256), (5, 384)])
+def test_layernorm_forward_backward(rows, d):
+    import trxl_native as native
+    torch.manual_seed(rows)
+    x = (torch.randn(rows, d, device=DEV) * 2 + 0.5).requires_grad_(True)
+    gamma = (1 + 0.1 * torch.randn(d, device=DEV)).requires_grad_(True)
+    beta = (0.1 * torch.randn(d, device=DEV)).requires_grad_(True)
+    y = torch.empty(rows, d, device=DEV)
+    mean, rstd = torch.empty(rows, device=DEV), torch.empty(rows, device=DEV)
+    native.layernorm_forward(x.detach(), gamma.detach(), beta.detach(), y, mean, rstd)
+    want = torch.nn.functional.layer_norm(x, (d,), gamma, beta, 1e-5)
+    assert torch.allclose(y, want, atol=2e-5, rtol=1e-5)
+    dy = torch.randn(rows, d, device=DEV)
+    want.backward(dy)
+    dx, dg, db = torch.empty(rows, d, device=DEV), torch.empty(d, device=DEV), torch.empty(d, device=DEV)
+    scratch = torch.empty(64 * d + 64, device=DEV)
+    native.layernorm_backward(dy, x.detach(), mean, rstd, gamma.detach(), dx, dg, db, scratch)
+    assert torch.allclose(dx, x.grad, atol=5e-5, rtol=1e-4)
+    assert torch.allclose(dg, gamma.grad, atol=1e-4 * rows ** 0.5, rtol=1e-4)
+    assert torch.allclose(db, beta.grad, atol=1e-4 * rows ** 0.5, rtol=1e-4)
+
+
+def test_mha_module_matches_reference_fixture():
+    """MultiHeadAttention.forward (standalone class API) vs the reference class, incl. a fully masked row."""
+    from transformer import GRUGate, MultiHeadAttention, SinusoidalPosition
+    g = load_golden("units")
+    for name in ("mha_a", "mha_b", "mha_c"):
+        d, h = g[name + ".Wv"].shape[0], int(g[name + ".H"])
+        m = MultiHeadAttention(d, h)
+        m.load_state_dict({"values.weight": torch.from_numpy(g[name + ".Wv"]), "keys.weight": torch.from_numpy(g[name + ".Wk"]),
+                           "queries.weight": torch.from_numpy(g[name + ".Wq"]), "fc_out.weight": torch.from_numpy(g[name + ".Wo"]),
+                           "fc_out.bias": torch.from_numpy(g[name + ".bo"])})
+        m = m.to(DEV)
+        v, q, mask = dev(g[name + ".v"]), dev(g[name + ".q"]), dev(g[name + ".mask"])
+        out, att = m(v, v, q, mask)
+        np.testing.assert_allclose(out.cpu().numpy(), g[name + ".out"], atol=1e-5)
+        np.testing.assert_allclose(att.cpu().numpy(), g[name + ".att"], atol=1e-6)
+    gate = GRUGate(12, 1.5)
+    gate.load_state_dict({k[4:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("gru.") and k[4:] not in ("x", "y", "out")})
+    gate = gate.to(DEV)
+    np.testing.assert_allclose(gate(dev(g["gru.x"]), dev(g["gru.y"])).cpu().numpy(), g["gru.out"], atol=1e-5)
+    for k in g:
+        if k.startswith("sin_D"):
+            d, m_ = int(k.split("_")[1][1:]), int(k.split("_")[2][1:])
+            np.testing.assert_allclose(SinusoidalPosition(d)(m_).numpy(), g[k], atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------ model forward
+@pytest.mark.parametrize("name", golden_names("forward_"))
+def test_model_forward_vs_reference(name):
+    g = load_golden(name)
+    case = name[len("forward_"):]
+    obs_shape = tuple(g["obs"].shape[1:])
+    model, _ = build_model(g, HEADS[case], g["mask"].shape[1], obs_shape, g["action_shape"], g["max_steps"], DEV)
+    with torch.no_grad():
+        pi, value, new_mem = model(dev(g["obs"]), dev(g["memory"]), dev(g["mask"]), dev(g["indices"]))
+    np.testing.assert_allclose(value.cpu().numpy(), g["value"], atol=1e-4)
+    np.testing.assert_allclose(new_mem.cpu().numpy(), g["new_mem"], atol=1e-4)
+    for k, dist in enumerate(pi):
+        np.testing.assert_allclose(dist.logits.cpu().numpy(), g["logits%d" % k], atol=1e-4)
+
+
+def test_model_forward_autograd_bridge():
+    """model.forward in grad mode + a user-built loss + loss.backward() gives the reference's gradients."""
+    g = load_golden("minibatch_pre_rel")
+    inputs = {k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("in.")}
+    model, cfg = build_model(g, 2, inputs["memory_mask"].shape[1], tuple(inputs["obs"].shape[1:]), g["action_shape"],
+                             g["max_steps"], DEV)
+    from oracle import ppo_oracle as O
+    from utils import batched_index_select
+    mb = {k: v.to(DEV) for k, v in inputs.items()}
+    window = batched_index_select(mb["memories"], 1, mb["memory_indices"])
+    model.zero_grad()
+    pi, value, _ = model(mb["obs"], window, mb["memory_mask"], mb["memory_indices"])
+    loss, _ = O.ppo_loss([d.logits for d in pi], value, mb, 0.2, 1e-3, 0.25)
+    loss.backward()
+    total = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in model.parameters()))
+    coef = min(1.0, 0.5 / (float(total) + 1e-6))
+    for pname, p in model.named_parameters():
+        want = g["it0.grad." + pname]
+        scale = max(1e-12, float(np.abs(want).max()))
+        np.testing.assert_allclose(p.grad.cpu().numpy() * coef, want, rtol=2e-4, atol=1e-4 * scale, err_msg=pname)
+
+
+# ------------------------------------------------------------------------------------------------ PPO step
+@pytest.mark.parametrize("name", golden_names("minibatch_"))
+def test_minibatch_step_vs_reference(name):
+    worst = run_minibatch_parity(name, DEV)
+    assert worst < 2e-5, worst
+
+
+# ------------------------------------------------------------------------------------------------ full trainer
+class _Pipe:
+    def __init__(self, env):
+        self.env, self.q = env, []
+
+    def send(self, msg):
+        cmd, data = msg
+        self.q.append(self.env.step(data) if cmd == "step" else (self.env.reset() if cmd == "reset" else None))
+
+    def recv(self):
+        return self.q.pop(0)
+
+
+class _Worker:
+    def __init__(self, env):
+        self.child = _Pipe(env)
+
+
+@pytest.mark.parametrize("name", golden_names("train_"))
+def test_trainer_two_updates_vs_reference(name, tmp_path, monkeypatch):
+    """PPOTrainer end to end (rollout bookkeeping, GAE, epochs x minibatches) replaying the reference's
+    sampled actions so both follow the same trajectory; in-process deterministic envs."""
+    import trainer as trainer_mod
+    from environments.synthetic_env import SyntheticEnv
+    monkeypatch.chdir(tmp_path)
+    g = load_golden(name)
+    nact, max_steps = int(g["n_actions"]), int(g["max_steps"])
+    obs_shape = tuple(int(x) for x in g["obs_shape"])
+    visual = len(obs_shape) > 1
+    W, T = (2, 8) if visual else (3, 12)
+    L = g["u0.memory_mask"].shape[2]
+    heads = 4 if ("visual" in name or name == "train_pre_rel") else 2
+    from parity_util import config_from_golden
+    cfg, sd = config_from_golden(g, heads, L, gamma=0.99, lamda=0.95, epochs=2, n_workers=W, worker_steps=T,
+                                 n_mini_batch=2 if visual else 3, updates=2,
+                                 environment={"type": "Synthetic", "obs_shape": list(obs_shape), "n_actions": nact,
+                                              "max_episode_steps": max_steps, "min_episode_steps": 2, "seed": 0},
+                                 learning_rate_schedule={"initial": 3e-4, "final": 1e-4, "power": 1.0, "max_decay_steps": 10},
+                                 beta_schedule={"initial": 1e-3, "final": 1e-4, "power": 1.0, "max_decay_steps": 10},
+                                 clip_range_schedule={"initial": 0.2, "final": 0.1, "power": 1.0, "max_decay_steps": 10})
+    cfg["transformer"]["gtrxl_bias"] = 1.0
+    workers = [_Worker(SyntheticEnv(obs_shape, nact, max_steps, min_episode_steps=2, seed=1 + i)) for i in range(W)]
+    tr = trainer_mod.PPOTrainer(cfg, run_id="t", device=torch.device(DEV), workers=workers, summary_writer=False)
+    tr.model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in sd.items()})
+    for upd in range(2):
+        pre = "u%d." % upd
+        tr._forced_actions = dev(g[pre + "actions"]).permute(1, 0, 2).contiguous()
+        tr._sample_training_data()
+        tr.buffer.prepare_batch_dict()
+        b = tr.buffer
+        for k in ("actions", "memory_mask", "memory_index", "memory_indices"):
+            assert np.array_equal(getattr(b, k).cpu().numpy(), g[pre + k]), k
+        assert np.array_equal(b.dones, g[pre + "dones"]) and np.array_equal(b.rewards, g[pre + "rewards"])
+        assert np.array_equal(b.obs.cpu().numpy(), g[pre + "obs"])
+        for k in ("values", "log_probs", "advantages", "memories"):
+            np.testing.assert_allclose(getattr(b, k).cpu().numpy(), g[pre + k], atol=1e-4, err_msg=k)
+        assert np.array_equal(tr.worker_current_episode_step.numpy(), g[pre + "worker_step"])
+        np.testing.assert_allclose(tr.memory.cpu().numpy(), g[pre + "live_memory"], atol=1e-4)
+        torch.manual_seed(200 + upd)
+        stats, grad_info = tr._train_epochs(float(g[pre + "lr"]), 0.2, 1e-3)
+        np.testing.assert_allclose(np.array(stats, dtype=np.float64), g[pre + "stats"], rtol=2e-3, atol=2e-5)
+        for k, v in grad_info.items():
+            np.testing.assert_allclose(np.array(v), g[pre + "gradnorm." + k], rtol=5e-3, err_msg=k)
+        for pname, p in tr.model.named_parameters():
+            np.testing.assert_allclose(p.detach().cpu().numpy(), g[pre + "after." + pname], atol=1e-4, err_msg=pname)
+    tr.close(exit_process=False)

@@ -1,0 +1,221 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports exactly what
+include/trxl_ppo.h declares, the parameter layout reproduces the reference's state_dict, the integer
+tables are bit-exact, the product refuses to run without CUDA, and the multi-rank plumbing works
+(world_size 2, gloo).  No kernel is launched here."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import PKG, ROOT, golden_names, load_golden
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "trxl_ppo.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(trxl_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_loads_and_exports_header_symbols():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as entry
+    lib_path = entry.build()
+    assert os.path.exists(lib_path)
+    import trxl_native as native
+    native.load()
+    declared = _header_functions()
+    assert declared, "no functions parsed from the header"
+    assert sorted(native.SIGNATURES) == declared, set(native.SIGNATURES) ^ set(declared)
+    exported = subprocess.run(["nm", "-D", "--defined-only", lib_path], capture_output=True, text=True).stdout
+    for fn in declared:
+        assert re.search(r" T %s$" % fn, exported, flags=re.M), "%s not exported" % fn
+    assert native._lib.trxl_abi_version() == 1
+
+
+def test_sass_is_sm100():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as entry
+    out = subprocess.run(["cuobjdump", "--list-elf", entry.LIB], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out[:400]
+
+
+def test_tables_bit_exact():
+    from trainer import build_mask_table, build_window_index_table
+    g = load_golden("tables")
+    for k, v in g.items():
+        if k.startswith("mask_L"):
+            got = build_mask_table(int(k[6:])).numpy()
+            assert got.dtype == v.dtype and np.array_equal(got, v)
+        else:
+            L, M = (int(s[1:]) for s in k.split("_")[1:])
+            got = build_window_index_table(M, L).numpy()
+            assert got.dtype == np.int64 and np.array_equal(got, v)
+    with pytest.raises(ValueError):
+        build_window_index_table(4, 5)
+
+
+@pytest.mark.parametrize("name", golden_names("forward_"))
+def test_layout_matches_reference_state_dict(name):
+    from parity_util import HEADS, build_model
+    g = load_golden(name)
+    case = name[len("forward_"):]
+    model, _ = build_model(g, HEADS[case], g["mask"].shape[1], tuple(g["obs"].shape[1:]), g["action_shape"], g["max_steps"], "cpu")
+    sd = model.state_dict()
+    ref = {k[3:]: v for k, v in g.items() if k.startswith("sd.")}
+    assert set(sd) == set(ref)
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(ref[k].shape), k
+        assert np.array_equal(v.numpy(), ref[k]), k                      # load_state_dict wrote through to the arena
+    # every parameter is a view of the flat arena, in non-overlapping 16-byte aligned slices
+    arena = model.flat_parameters()
+    spans = sorted((off, off + numel) for _, off, numel, _ in model._param_slices)
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))
+    for pname, p in model.named_parameters():
+        assert p.data_ptr() >= arena.data_ptr() and p.data_ptr() < arena.data_ptr() + arena.numel() * 4
+        assert p.grad is not None and p.grad.shape == p.shape
+    # moving the module repacks the arena and keeps values
+    before = {k: v.clone() for k, v in sd.items()}
+    model.to(torch.float32)
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, before[k])
+
+
+def test_no_cpu_fallback():
+    import trxl_native as native
+    from parity_util import HEADS, build_model
+    from trainer import PPOTrainer
+    g = load_golden("forward_post_rel")
+    model, _ = build_model(g, 2, 4, (5,), g["action_shape"], g["max_steps"], "cpu")
+    with pytest.raises(native.NativeLibraryError):
+        model(torch.zeros(2, 5), torch.zeros(2, 4, 2, 16), torch.ones(2, 4, dtype=torch.bool), torch.zeros(2, 4, dtype=torch.long))
+    with pytest.raises(native.NativeLibraryError):
+        PPOTrainer({"n_workers": 1, "learning_rate_schedule": {}, "beta_schedule": {}, "clip_range_schedule": {},
+                    "transformer": {"memory_length": 1, "num_blocks": 1, "embed_dim": 4}}, device=torch.device("cpu"))
+    with pytest.raises(native.NativeLibraryError):
+        native.gae(torch.zeros(1, 1), torch.zeros(1, 1, dtype=torch.uint8), torch.zeros(1, 1), torch.zeros(1), torch.zeros(1, 1),
+                   0.99, 0.95)
+
+
+def test_invalid_configs_are_rejected():
+    import trxl_native as native
+    bad = native.make_config(30, 4, 1, 4, 16, 3, "post", "relative", False, 8, (2,))     # 30 % 4 != 0
+    with pytest.raises(ValueError):
+        native.layout(bad)
+    bad = native.make_config(32, 5, 1, 4, 16, 3, "post", "relative", False, 8, (2,))     # heads do not divide
+    with pytest.raises(ValueError):
+        native.layout(bad)
+    ok = native.make_config(32, 4, 2, 4, 16, 3, "pre", "learned", True, 8, (2, 3))
+    entries, total, groups = native.layout(ok)
+    assert groups == 6 + 2 + 2 and total % 4 == 0
+    assert native.workspace_floats(ok, 8) > 0
+
+
+def test_utils_and_yaml(tmp_path):
+    from utils import polynomial_decay, process_episode_info
+    from yaml_parser import YamlParser
+    g = load_golden("units")
+    got = [polynomial_decay(3e-4, 1e-5, 100, p, s) for p in (1.0, 2.0) for s in (0, 1, 50, 100, 101)]
+    assert np.array_equal(np.array(got), g["poly"])
+    res = process_episode_info([{"reward": 1.0, "length": 3, "success": True}, {"reward": 3.0, "length": 5, "success": False}])
+    assert res["reward_mean"] == 2.0 and res["success_percent"] == 0.5 and res["length_std"] == 1.0
+    assert process_episode_info([]) == {}
+    cfg = YamlParser(os.path.join(PKG, "configs", "c3_minigrid_synthetic.yaml")).get_config()
+    assert cfg["transformer"]["memory_length"] == 128 and cfg["n_workers"] == 32 and isinstance(cfg, dict)
+
+
+def test_minibatch_is_lazy_and_reference_shaped():
+    """The buffer yields the reference's keys; nothing is gathered until a key is read."""
+    from buffer import Buffer, MiniBatch
+
+    class Space:
+        shape = (3,)
+    cfg = {"n_workers": 2, "worker_steps": 6, "n_mini_batch": 3,
+           "transformer": {"memory_length": 4, "num_blocks": 1, "embed_dim": 8}}
+    buf = Buffer(cfg, Space(), (2,), 7, torch.device("cpu"))
+    buf.memories = [torch.zeros(7, 1, 8), torch.ones(7, 1, 8)]
+    buf.memory_index[1] = 1
+    buf.values[:] = torch.arange(12.0).reshape(2, 6)
+    buf.prepare_batch_dict()
+    assert buf.memories.shape == (2, 7, 1, 8) and buf.samples_flat["values"].shape == (12,)
+    torch.manual_seed(0)
+    batches = list(buf.mini_batch_generator())
+    torch.manual_seed(0)
+    perm = torch.randperm(12)
+    assert len(batches) == 3 and all(isinstance(b, MiniBatch) for b in batches)
+    assert torch.equal(torch.cat([b.sample_index for b in batches]), perm)          # same index stream as torch.randperm
+    mb = batches[0]
+    assert dict.__len__(mb) == 0                                                    # nothing materialised yet
+    assert set(mb.keys()) == {"actions", "values", "log_probs", "advantages", "obs", "memory_mask", "memory_indices", "memories"}
+    assert torch.equal(mb["values"], buf.samples_flat["values"][mb.sample_index])
+    assert mb["memories"].shape == (4, 7, 1, 8)
+    assert torch.equal(mb["memories"][:, 0, 0, 0], (mb.sample_index >= 6).float())
+
+
+_RANK_SCRIPT = r'''
+import os, sys
+sys.path.insert(0, {pkg!r}); sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np, torch
+import torch.distributed as dist
+import parallel
+from oracle import ppo_oracle as O, trxl_oracle as X
+from parity_util import load_golden, config_from_golden
+parallel.init_from_env(backend="gloo")
+dp = parallel.DataParallelContext()
+assert dp.world_size == 2
+g = load_golden("minibatch_post_rel")
+cfg, sd = config_from_golden(g, 2, 4)
+cfg.update(max_episode_steps=int(g["max_steps"]), action_space_shape=tuple(int(a) for a in g["action_shape"]))
+P = {{k: torch.from_numpy(v.copy()) for k, v in sd.items()}}
+mb = {{k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("in.")}}
+n = mb["obs"].shape[0]
+mine = parallel.shard_workers(n, dp.rank, dp.world_size)
+shard = {{k: v[mine.start:mine.stop] for k, v in mb.items()}}
+# global advantage statistics: all-reduce (sum, sum of squares, count), as the native path does
+a = shard["advantages"].double()
+st = torch.tensor([a.sum(), (a * a).sum(), float(len(a))], dtype=torch.float64)
+dp.all_reduce_(st)
+mean = st[0] / st[2]; std = torch.sqrt((st[1] - st[2] * mean * mean) / (st[2] - 1))
+names = X.trainable_names(P)
+for k in names: P[k].requires_grad_(True)
+window = X.select_window(shard["memories"], shard["memory_indices"])
+logits, value, _ = X.model_forward(P, cfg, shard["obs"], window, shard["memory_mask"], shard["memory_indices"])
+# same loss as ppo_loss but normalised by the GLOBAL batch so that summing rank gradients is exact
+nadv = ((shard["advantages"] - mean.float()) / (std.float() + 1e-8)).unsqueeze(1)
+lp = torch.stack([X.categorical_log_prob(lg, shard["actions"][:, i]) for i, lg in enumerate(logits)], 1)
+ent = torch.stack([X.categorical_entropy(lg) for lg in logits], 1).sum(1)
+ratio = torch.exp(lp - shard["log_probs"])
+pl = torch.min(ratio * nadv, torch.clamp(ratio, 0.8, 1.2) * nadv).sum() / (n * lp.shape[1])
+ret = shard["values"] + shard["advantages"]
+cv = shard["values"] + (value - shard["values"]).clamp(-0.2, 0.2)
+vl = torch.max((value - ret) ** 2, (cv - ret) ** 2).sum() / n
+loss = -(pl - 0.25 * vl + 1e-3 * ent.sum() / n)
+loss.backward()
+flat = torch.cat([P[k].grad.reshape(-1) for k in names])
+dp.all_reduce_(flat)                                  # ONE collective for the whole gradient arena
+coef = min(1.0, 0.5 / (float(torch.linalg.vector_norm(flat)) + 1e-6))
+off = 0
+for k in names:
+    got = flat[off:off + P[k].numel()].reshape(P[k].shape).numpy() * coef
+    off += P[k].numel()
+    want = g["it0.grad." + k]
+    np.testing.assert_allclose(got, want, rtol=2e-4, atol=1e-4 * max(1e-12, float(np.abs(want).max())), err_msg=k)
+dist.barrier()
+sys.stdout.write("rank %d ok\n" % dp.rank); sys.stdout.flush()
+'''
+
+
+def test_two_rank_gradient_allreduce_matches_single_rank(tmp_path):
+    """world_size 2 over gloo: each rank differentiates its half of the minibatch (oracle arithmetic),
+    statistics and the flat gradient buffer are all-reduced exactly as the native trainer does, and the
+    result equals the reference's single-process gradient."""
+    script = tmp_path / "rank.py"
+    script.write_text(_RANK_SCRIPT.format(pkg=PKG, root=ROOT))
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29611", str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
