@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Benchmark of the PPO + TrXL hot path on BASELINE.json's metric: env-steps/sec on synthetic
+Minigrid-shaped observations (3x84x84), memory_length 128, embed_dim 256, 4 heads, 4 blocks,
+n_workers 32 x worker_steps 512 per GPU (configs[2], the configuration the metric is quoted on).
+
+    python bench.py --gpus 1 --steps 3 --warmup 3            # this engine (one JSON line)
+    python bench.py --impl reference --steps 2 --warmup 1    # reference algorithm on the host CPU cores
+    torchrun ... bench.py --gpus N ...                       # one rank per GPU, weak scaling
+
+One "step" = one PPO update = worker_steps rollout forwards over all workers + GAE + epochs x
+minibatches of forward/backward/clip/AdamW.
+  value : env-steps/s with the synthetic env resident on the device (device_feed.py), timed with CUDA
+          events, max over ranks.
+  e2e   : the same metric through PPOTrainer with real env worker processes (worker.py pipes):
+          observations arrive in host memory every step and are copied host->device, actions are
+          copied device->host, inside the timed region.
+  roofline : the fused window-attention forward kernel (training launches), CUDA-event timed inside
+          the timed region; algorithmic bytes = 4*L*D per (sample, block).
+  cpu_baseline / --impl reference : the oracle port (oracle/*.py, a restatement of the reference pinned
+          to reference-generated fixtures; the Python reference itself cannot travel to the GPU box)
+          timed on the host cores on a bounded sample and extrapolated to one update.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "episodic-transformer-memory-ppo_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "env-steps/sec (whole box) Minigrid 3x84x84 mem_len=128"
+UNIT = "env-steps/s"
+
+
+def load_workload(name):
+    from yaml_parser import YamlParser
+    return YamlParser(os.path.join(PKG, "configs", name + ".yaml")).get_config()
+
+
+def workload_desc(cfg, name, n_gpus):
+    t = cfg["transformer"]
+    return {"workload": name, "obs_shape": cfg["environment"]["obs_shape"], "n_workers_per_gpu": cfg["n_workers"],
+            "worker_steps": cfg["worker_steps"], "memory_length": t["memory_length"], "embed_dim": t["embed_dim"],
+            "num_heads": t["num_heads"], "num_blocks": t["num_blocks"], "epochs": cfg["epochs"],
+            "n_mini_batch": cfg["n_mini_batch"], "layer_norm": t["layer_norm"], "positional_encoding": t["positional_encoding"],
+            "global_env_steps_per_update": cfg["n_workers"] * cfg["worker_steps"] * n_gpus,
+            "parallelism": "dp%d (workers sharded, 1 flat-grad all-reduce / optimiser step)" % n_gpus,
+            "l2_note": "per-step inputs (1.4 GB obs buffer + 168 MB memory table + 173 MB minibatch obs) exceed the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, flag in zip(names, r[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_sample(cfg, rollout_steps=8, threads=None, seed=0, mb_sample=512, reps=2):
+    """Time the oracle port on the host cores: `rollout_steps` rollout steps over all workers plus ONE
+    full-size minibatch step (episode gather + window gather + forward + backward + clip + AdamW, as the
+    reference does them), extrapolated to a whole update.  Returns (env_steps_per_s, detail dict)."""
+    from oracle import ppo_oracle as O
+    from oracle import trxl_oracle as X
+    from environments.synthetic_env import SyntheticEnv
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    torch.manual_seed(seed)
+    env_cfg = cfg["environment"]
+    obs_shape, nact, M = tuple(env_cfg["obs_shape"]), env_cfg["n_actions"], env_cfg["max_episode_steps"]
+    W, T, t = cfg["n_workers"], cfg["worker_steps"], cfg["transformer"]
+    ocfg = dict(cfg, max_episode_steps=M, action_space_shape=(nact,))
+    P = X.init_params(ocfg, obs_shape, seed=seed)
+    envs = [SyntheticEnv(obs_shape, nact, M, env_cfg.get("min_episode_steps"), seed=seed + 1 + w) for w in range(W)]
+    st = O.new_rollout_state(ocfg, obs_shape, envs)
+    short = dict(ocfg, worker_steps=rollout_steps)
+    t0 = time.perf_counter()
+    O.sample_rollout(P, short, st, envs)
+    t_roll = (time.perf_counter() - t0) / rollout_steps
+    # one optimiser step on a bounded slice of a real minibatch (cost is linear in the sample count)
+    mb_full = W * T // cfg["n_mini_batch"]
+    mb_size = min(mb_full, mb_sample)
+    g = torch.Generator().manual_seed(seed)
+    n_eps = max(W, W * T // max(1, M // 2))
+    table = torch.randn((n_eps, M, t["num_blocks"], t["embed_dim"]), generator=g)
+    idx_table = X.window_index_table(M, t["memory_length"])
+    mask_table = X.attention_mask_table(t["memory_length"])
+    steps = torch.randint(0, M, (mb_size,), generator=g)
+    flat = {"obs": torch.rand((mb_size,) + obs_shape, generator=g), "memory_index": torch.randint(0, n_eps, (mb_size,), generator=g),
+            "memory_indices": idx_table[steps], "memory_mask": mask_table[torch.clip(steps, 0, t["memory_length"] - 1)].bool(),
+            "actions": torch.randint(0, nact, (mb_size, 1), generator=g), "values": torch.randn(mb_size, generator=g),
+            "advantages": torch.randn(mb_size, generator=g), "log_probs": -torch.rand((mb_size, 1), generator=g) - 0.5}
+    opt = {}
+    t_best = float("inf")
+    for _ in range(reps):                                                        # best of `reps`: first touch of fresh pages is slow
+        t0 = time.perf_counter()
+        mb = next(O.minibatches(flat, table, 1, perm=torch.arange(mb_size)))     # episode gather (buffer.py:90)
+        O.train_minibatch(P, opt, ocfg, mb, 3e-4, 0.1, 1e-3)
+        t_best = min(t_best, time.perf_counter() - t0)
+        del mb
+    t_mb = t_best * (mb_full / mb_size)
+    n_opt = cfg["epochs"] * cfg["n_mini_batch"]
+    update_s = T * t_roll + n_opt * t_mb
+    detail = {"rollout_step_s": t_roll, "minibatch_step_s": t_mb, "optimiser_steps_per_update": n_opt,
+              "sample": "%d rollout steps (W=%d, in-process synthetic envs) + optimiser step on %d of the %d minibatch samples "
+                        "(best of %d, scaled x%.0f) timed on %d threads; update = %d*rollout_step + %d*minibatch_step"
+                        % (rollout_steps, W, mb_size, mb_full, reps, mb_full / mb_size, threads, T, n_opt)}
+    return W * T / update_s, detail
+
+
+def run_reference(args, cfg, name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, detail = [], None
+    for i in range(args.warmup + args.steps):
+        v, detail = cpu_reference_sample(cfg, rollout_steps=4 if args.steps + args.warmup > 4 else 8, seed=i)
+        if i >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    cores = os.cpu_count()
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * cfg["n_workers"] * cfg["worker_steps"] / value,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_desc(cfg, name, 1),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": detail["sample"],
+                             "rollout_step_s": detail["rollout_step_s"], "minibatch_step_s": detail["minibatch_step_s"]},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args, cfg, name):
+    import parallel
+    import trxl_native as native
+    from device_feed import SyntheticDeviceFeed
+    from trainer import PPOTrainer
+    from utils import polynomial_decay
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    native.load()
+    parallel.init_from_env("nccl")
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dp = parallel.DataParallelContext(device)
+    rank, world = dp.rank, dp.world_size
+    env_cfg = cfg["environment"]
+    W, T = cfg["n_workers"], cfg["worker_steps"]
+    torch.manual_seed(1234 + rank)
+    os.chdir(os.environ.get("TMPDIR", "/tmp"))
+
+    # ---------------- e2e arm first (forks env processes before the big allocations) ----------------
+    e2e = None
+    if not args.no_e2e:
+        tr = PPOTrainer(cfg, run_id="bench_e2e", device=device, summary_writer=False)
+        sched = lambda u: (polynomial_decay(**_s(cfg["learning_rate_schedule"]), current_step=u),   # noqa: E731
+                           polynomial_decay(**_s(cfg["clip_range_schedule"]), current_step=u),
+                           polynomial_decay(**_s(cfg["beta_schedule"]), current_step=u))
+        def one_update(trainer, u):
+            lr, clip, beta = sched(u)
+            trainer._sample_training_data()
+            trainer.buffer.prepare_batch_dict()
+            trainer._train_epochs(lr, clip, beta)
+        for u in range(min(args.warmup, 1)):
+            one_update(tr, u)
+        dp.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_e2e = max(1, min(args.steps, args.e2e_steps))
+        for u in range(n_e2e):
+            one_update(tr, u)
+        torch.cuda.synchronize(); dp.barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+        dp.max_(dt)
+        obs_bytes = int(np.prod(env_cfg["obs_shape"])) * 4
+        e2e = {"value": world * W * T * n_e2e / float(dt), "unit": UNIT,
+               "h2d_bytes_per_step": T * (W * obs_bytes + 2 * W * 8), "d2h_bytes_per_step": T * W * 8 + 40 * 4 * 32,
+               "updates_timed": n_e2e, "env_transport": "1 process per env, pipes (worker.py)",
+               "env_wait_s_per_update": tr.timers["env"] / (n_e2e + min(args.warmup, 1)),
+               "rollout_s_per_update": tr.timers["rollout"] / (n_e2e + min(args.warmup, 1)),
+               "train_s_per_update": tr.timers["train"] / (n_e2e + min(args.warmup, 1))}
+        tr.close(exit_process=False)
+        del tr
+        torch.cuda.empty_cache()
+
+    # ---------------- device-resident arm ----------------
+    tr = PPOTrainer(cfg, run_id="bench", device=device, workers=[], summary_writer=False)
+    tr.device_feed = SyntheticDeviceFeed(W, T, tuple(env_cfg["obs_shape"]), env_cfg["max_episode_steps"],
+                                         env_cfg.get("min_episode_steps"), seed=100 + rank, device=device)
+
+    def update(u):
+        lr = polynomial_decay(**_s(cfg["learning_rate_schedule"]), current_step=u)
+        clip = polynomial_decay(**_s(cfg["clip_range_schedule"]), current_step=u)
+        beta = polynomial_decay(**_s(cfg["beta_schedule"]), current_step=u)
+        tr._sample_training_data()
+        tr.buffer.prepare_batch_dict()
+        return tr._train_epochs(lr, clip, beta)
+
+    for u in range(args.warmup):
+        update(u)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    native.profile_enable(True)
+    launches0 = native.launch_count()
+    tr.timers = {"rollout": 0.0, "train": 0.0, "env": 0.0}
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dp.barrier(); torch.cuda.synchronize()
+    start.record()
+    for u in range(args.steps):
+        stats, _ = update(args.warmup + u)
+    stop.record()
+    torch.cuda.synchronize(); dp.barrier()
+    ms = torch.tensor([start.elapsed_time(stop)], dtype=torch.float64, device=device)
+    dp.max_(ms)
+    ms = float(ms)
+    launches = native.launch_count() - launches0
+    native.profile_enable(False) if False else None
+    clock_info = clocks.stop() if rank == 0 else None
+    mb = W * T // cfg["n_mini_batch"]
+    t = cfg["transformer"]
+    fwd_ms, fwd_n, fwd_samples = native.profile_read(0, mb)
+    bwd_ms, bwd_n, bwd_samples = native.profile_read(1, mb)
+    native.profile_enable(False)
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    bytes_per_launch = mb * 4.0 * t["memory_length"] * t["embed_dim"]
+    achieved = bytes_per_launch / (fwd_ms / max(1, fwd_n) * 1e-3) / 1e9 if fwd_n else None
+    roofline = {"kernel": "window_attn_fwd_kernel (training launches, N=%d samples x 1 block each)" % mb, "bound": "hbm",
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": fwd_ms / max(1, fwd_n), "launches_timed": fwd_n,
+                "traffic": None,
+                "bwd_kernel": {"avg_launch_ms": bwd_ms / max(1, bwd_n), "launches_timed": bwd_n,
+                               "achieved": (bytes_per_launch / (bwd_ms / max(1, bwd_n) * 1e-3) / 1e9) if bwd_n else None},
+                "share_of_step": (fwd_ms + bwd_ms) / ms if ms else None}
+    value = world * W * T * args.steps / (ms * 1e-3)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_desc(cfg, name, world), "clocks": clock_info, "gpu_launches": launches,
+            "roofline": roofline, "e2e": e2e,
+            "breakdown_s_per_update": {"rollout": tr.timers["rollout"] / args.steps, "train": tr.timers["train"] / args.steps},
+            "last_stats": [float(x) for x in np.mean(np.array(stats, dtype=np.float64), axis=0)]}
+    if world == 1 and not args.no_cpu_baseline:
+        v, detail = cpu_reference_sample(cfg, rollout_steps=8)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": detail["sample"],
+                                "rollout_step_s": detail["rollout_step_s"], "minibatch_step_s": detail["minibatch_step_s"]}
+    print(json.dumps(line))
+
+
+def _s(schedule):
+    return {"initial": schedule["initial"], "final": schedule["final"], "max_decay_steps": schedule["max_decay_steps"],
+            "power": schedule["power"]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3_minigrid_synthetic")
+    ap.add_argument("--e2e-steps", type=int, default=2, help="PPO updates timed for the e2e (env-process) arm")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = load_workload(args.workload)
+    if args.impl == "reference":
+        run_reference(args, cfg, args.workload)
+    else:
+        run_b200(args, cfg, args.workload)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -19,6 +19,33 @@ void trxl_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+long long g_trxl_launches = 0;
+
+// ---- optional launch timing of the two attention kernels (bench.py roofline) ----
+namespace {
+constexpr int PROF_KINDS = 2, PROF_CAP = 8192;
+struct ProfSlot { cudaEvent_t a, b; int n; };
+bool g_prof_on = false;
+ProfSlot* g_prof[PROF_KINDS] = {nullptr, nullptr};
+int g_prof_count[PROF_KINDS] = {0, 0};
+}  // namespace
+
+void trxl_prof_begin(int kind, int n, cudaStream_t st) {
+    if (!g_prof_on || g_prof_count[kind] >= PROF_CAP) return;
+    if (!g_prof[kind]) {
+        g_prof[kind] = new ProfSlot[PROF_CAP];
+        for (int i = 0; i < PROF_CAP; ++i) { cudaEventCreate(&g_prof[kind][i].a); cudaEventCreate(&g_prof[kind][i].b); }
+    }
+    ProfSlot& s = g_prof[kind][g_prof_count[kind]];
+    s.n = n;
+    cudaEventRecord(s.a, st);
+}
+void trxl_prof_end(int kind, cudaStream_t st) {
+    if (!g_prof_on || g_prof_count[kind] >= PROF_CAP || !g_prof[kind]) return;
+    cudaEventRecord(g_prof[kind][g_prof_count[kind]].b, st);
+    ++g_prof_count[kind];
+}
+
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 typedef const long long* cll;
 
@@ -38,6 +65,26 @@ extern "C" {
 
 const char* trxl_last_error(void) { return g_err; }
 int trxl_abi_version(void) { return TRXL_ABI_VERSION; }
+int64_t trxl_launch_count(void) { return g_trxl_launches; }
+
+int trxl_profile_enable(int on) {
+    g_prof_on = on != 0;
+    if (on) { g_prof_count[0] = 0; g_prof_count[1] = 0; }
+    return TRXL_OK;
+}
+int trxl_profile_read(int kind, int min_samples, double* total_ms, int64_t* launches, int64_t* samples) {
+    TRXL_CHECK_ARG(kind >= 0 && kind < PROF_KINDS && total_ms && launches && samples, "profile_read: bad arguments");
+    *total_ms = 0.0; *launches = 0; *samples = 0;
+    for (int i = 0; i < g_prof_count[kind]; ++i) {
+        ProfSlot& s = g_prof[kind][i];
+        if (s.n < min_samples) continue;
+        if (cudaEventSynchronize(s.b) != cudaSuccess) { trxl_set_error("profile_read: event sync failed"); return TRXL_ERR_CUDA; }
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.a, s.b) != cudaSuccess) { trxl_set_error("profile_read: elapsed failed"); return TRXL_ERR_CUDA; }
+        *total_ms += ms; *launches += 1; *samples += s.n;
+    }
+    return TRXL_OK;
+}
 
 int trxl_layout_num_entries(const trxl_model_config* cfg) {
     std::vector<trxl_param_entry> e;

@@ -467,6 +467,7 @@ template <int NV4, int HPW>
 int launch_fwd(const AttnArgs& a, cudaStream_t st) {
     dim3 grid(a.N, trxl_cdiv(a.H, HPW));
     const size_t smem = (size_t)a.L * 16 + (size_t)HPW * ((a.L + 3) & ~3) * 4 + (size_t)HPW * a.D * 4 + NW * HPW * 3 * 4 + a.L + 16;
+    trxl_prof_begin(0, a.N, st);
     if (a.ln) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(window_attn_fwd_kernel<NV4, HPW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         window_attn_fwd_kernel<NV4, HPW, true><<<grid, NW * 32, smem, st>>>(a);
@@ -474,6 +475,7 @@ int launch_fwd(const AttnArgs& a, cudaStream_t st) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(window_attn_fwd_kernel<NV4, HPW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         window_attn_fwd_kernel<NV4, HPW, false><<<grid, NW * 32, smem, st>>>(a);
     }
+    trxl_prof_end(0, st);
     TRXL_CHECK_LAUNCH("window_attn_fwd");
     return TRXL_OK;
 }
@@ -482,6 +484,7 @@ template <int NV4, int HPW>
 int launch_bwd(const AttnArgs& a, const AttnBwdArgs& g, cudaStream_t st) {
     dim3 grid(a.N, trxl_cdiv(a.H, HPW));
     const size_t smem = (size_t)a.L * 16 + (size_t)HPW * ((a.L + 3) & ~3) * 4 + (size_t)HPW * a.D * 4 + NW * HPW * 2 * 4 + a.L + 16;
+    trxl_prof_begin(1, a.N, st);
     if (a.ln) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(window_attn_bwd_kernel<NV4, HPW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         window_attn_bwd_kernel<NV4, HPW, true><<<grid, NW * 32, smem, st>>>(a, g);
@@ -489,6 +492,7 @@ int launch_bwd(const AttnArgs& a, const AttnBwdArgs& g, cudaStream_t st) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(window_attn_bwd_kernel<NV4, HPW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         window_attn_bwd_kernel<NV4, HPW, false><<<grid, NW * 32, smem, st>>>(a, g);
     }
+    trxl_prof_end(1, st);
     TRXL_CHECK_LAUNCH("window_attn_bwd");
     return TRXL_OK;
 }

@@ -11,6 +11,11 @@
 
 // thread-local last-error string (set by host wrappers, read through trxl_last_error()).
 void trxl_set_error(const char* fmt, ...);
+// number of kernels this library has launched (bench.py reports it as gpu_launches)
+extern long long g_trxl_launches;
+// optional per-launch timing of the attention kernels (CUDA events on the launch stream); see api.cu
+void trxl_prof_begin(int kind, int n, cudaStream_t st);
+void trxl_prof_end(int kind, cudaStream_t st);
 
 #define TRXL_CHECK_ARG(cond, ...)                 \
     do {                                          \
@@ -23,6 +28,7 @@ void trxl_set_error(const char* fmt, ...);
 #define TRXL_CHECK_LAUNCH(what)                                                       \
     do {                                                                              \
         cudaError_t e__ = cudaGetLastError();                                         \
+        ++g_trxl_launches;                                                            \
         if (e__ != cudaSuccess) {                                                     \
             trxl_set_error("%s: CUDA launch failed: %s", what, cudaGetErrorString(e__)); \
             return TRXL_ERR_CUDA;                                                     \

@@ -87,6 +87,7 @@ class PPOTrainer:
 
         # env workers: anything with a ``child`` pipe end speaking the reference protocol
         self.workers = workers if workers is not None else [Worker(self._env_config(w)) for w in range(self.num_workers)]
+        # (pass workers=[] together with trainer.device_feed = SyntheticDeviceFeed(...) to run without env processes)
         self.worker_ids = range(self.num_workers)
         self.worker_current_episode_step = torch.zeros((self.num_workers,), dtype=torch.long)
         for worker in self.workers:
@@ -94,6 +95,7 @@ class PPOTrainer:
         self.obs = np.zeros((self.num_workers,) + self.obs_shape, dtype=np.float32)
         for w, worker in enumerate(self.workers):
             self.obs[w] = worker.child.recv()
+        self._feed_last_obs = None
 
         # bit-exact integer tables, built on the host and uploaded once
         self.memory_mask = build_mask_table(self.memory_length)
@@ -123,6 +125,7 @@ class PPOTrainer:
         self._win_last = torch.zeros((W, L), dtype=torch.long, device=dev)
         self._mask_last = torch.zeros((W, L), dtype=torch.uint8, device=dev)
         self._train_state = {}
+        self.device_feed = None         # optional device_feed.SyntheticDeviceFeed replacing the env workers (bench.py)
         self._forced_actions = None     # optional (T, W, n_branches) int64 device tensor: replay these actions (parity tests)
         self.timers = {"rollout": 0.0, "train": 0.0, "env": 0.0}
 
@@ -203,44 +206,56 @@ class PPOTrainer:
             s[0], s[1], s[3], s[2], torch.mean(self.buffer.values).item(), torch.mean(self.buffer.advantages).item()))
 
     # ------------------------------------------------------------------------------------------ rollout
+    def _rollout_ctx(self):
+        buf, W, T, L = self.buffer, self.num_workers, self.config["worker_steps"], self.memory_length
+        nb = len(self.action_space_shape)
+        return {
+            "flat_mask": buf.memory_mask.view(torch.uint8).view(W * T, L), "flat_idx": buf.memory_indices.view(W * T, L),
+            "flat_ep": buf.memory_index.view(W * T), "inner": self.num_blocks * self.embed_dim,
+            "uniforms": torch.rand((T, W, nb), device=self.device), "ws": self.model.workspace(W),
+            "outs": self.model._alloc_outputs(W, self.device),
+        }
+
+    def _device_step(self, t, obs_dev, step_dev, ep_dev, ctx):
+        """Everything the GPU does for rollout step t (trainer.py:161-186): store obs, write the mask /
+        window-index rows, run the model with the window read in place, write the new memory row,
+        sample actions, store actions / log-probs / values."""
+        buf, model = self.buffer, self.model
+        W, T, L, nb = self.num_workers, self.config["worker_steps"], self.memory_length, len(self.action_space_shape)
+        buf.obs[:, t] = obs_dev
+        native.rollout_prepare(step_dev, ep_dev, self._mask_table_dev, self._index_table_dev,
+                               ctx["flat_mask"].data_ptr() + t * L, T * L, ctx["flat_idx"].data_ptr() + t * L * 8, T * L,
+                               ctx["flat_ep"].data_ptr() + t * 8, T, W, L)
+        feat = model.encode(obs_dev)
+        logits, value, new_mem = model.forward_table(feat, self._table, ctx["flat_ep"], ctx["flat_idx"], ctx["flat_mask"],
+                                                     ctx["flat_idx"], sample_index=self._rollout_rows[t], n=W, ws=ctx["ws"],
+                                                     out=ctx["outs"])
+        native.memory_scatter(self._table, ep_dev, step_dev, new_mem, self.max_episode_length, ctx["inner"])
+        forced = None if self._forced_actions is None else self._forced_actions[t]
+        native.sample_actions(logits, ctx["uniforms"][t], self.action_space_shape, buf.actions.data_ptr() + t * nb * 8, T * nb,
+                              buf.log_probs.data_ptr() + t * nb * 4, T * nb, self._act_dev, W, forced=forced)
+        buf.values[:, t] = value
+
     def _sample_training_data(self):
         """Run every worker for ``worker_steps`` steps (trainer.py:145-225)."""
+        if self.device_feed is not None:
+            return self._sample_from_device_feed(self.device_feed)
         t0 = time.perf_counter()
-        cfg, buf, model = self.config, self.buffer, self.model
-        W, T, L = self.num_workers, cfg["worker_steps"], self.memory_length
-        nb = len(self.action_space_shape)
+        cfg, buf = self.config, self.buffer
+        T = cfg["worker_steps"]
         episode_infos = []
         self._begin_rollout()
-        flat_mask = buf.memory_mask.view(torch.uint8).view(W * T, L)
-        flat_idx = buf.memory_indices.view(W * T, L)
-        flat_ep = buf.memory_index.view(W * T)
-        inner = self.num_blocks * self.embed_dim
-        uniforms = torch.rand((T, W, nb), device=self.device)
-        ws = model.workspace(W)
-        outs = model._alloc_outputs(W, self.device)
+        ctx = self._rollout_ctx()
         stream = torch.cuda.current_stream()
         env_time = 0.0
         with torch.no_grad():
             for t in range(T):
-                # observations: host -> pinned -> device, and into the buffer
+                # observations: host -> pinned -> device; cursors of every worker's live episode
                 self._obs_pinned.copy_(torch.from_numpy(self.obs))
                 self._obs_dev.copy_(self._obs_pinned, non_blocking=True)
-                buf.obs[:, t] = self._obs_dev
                 self._step_dev.copy_(self._step_host, non_blocking=True)
                 self._ep_dev.copy_(self._ep_host, non_blocking=True)
-                # mask / window rows of every worker's episode step straight into buffer[:, t]
-                native.rollout_prepare(self._step_dev, self._ep_dev, self._mask_table_dev, self._index_table_dev,
-                                       flat_mask.data_ptr() + t * L, T * L, flat_idx.data_ptr() + t * L * 8, T * L,
-                                       flat_ep.data_ptr() + t * 8, T, W, L)
-                rows = self._rollout_rows[t]
-                feat = model.encode(self._obs_dev)
-                logits, value, new_mem = model.forward_table(feat, self._table, flat_ep, flat_idx, flat_mask, flat_idx,
-                                                             sample_index=rows, n=W, ws=ws, out=outs)
-                native.memory_scatter(self._table, self._ep_dev, self._step_dev, new_mem, self.max_episode_length, inner)
-                forced = None if self._forced_actions is None else self._forced_actions[t]
-                native.sample_actions(logits, uniforms[t], self.action_space_shape, buf.actions.data_ptr() + t * nb * 8, T * nb,
-                                      buf.log_probs.data_ptr() + t * nb * 4, T * nb, self._act_dev, W, forced=forced)
-                buf.values[:, t] = value
+                self._device_step(t, self._obs_dev, self._step_dev, self._ep_dev, ctx)
                 self._act_pinned.copy_(self._act_dev, non_blocking=True)
                 stream.synchronize()
                 actions = self._act_pinned.numpy()
@@ -269,6 +284,51 @@ class PPOTrainer:
         self.timers["rollout"] += time.perf_counter() - t0
         return episode_infos
 
+    def _sample_from_device_feed(self, feed):
+        """Rollout against a device-resident synthetic feed (device_feed.py): the episode schedule of the
+        whole update is known up front, so the per-step cursors (episode step, table row) are uploaded
+        once and the T steps run back to back without host synchronisation."""
+        t0 = time.perf_counter()
+        cfg, buf = self.config, self.buffer
+        W, T = self.num_workers, cfg["worker_steps"]
+        self._begin_rollout()
+        feed.begin_update()
+        # replay the reference's bookkeeping (trainer.py:195-216) on the host for all T steps at once
+        step_sched = np.zeros((T + 1, W), dtype=np.int64)
+        ep_sched = np.zeros((T + 1, W), dtype=np.int64)
+        step_sched[0], ep_sched[0] = self._step_host.numpy(), self._ep_host.numpy()
+        episode_infos = []
+        n_rows = self._n_rows
+        for t in range(T):
+            step_sched[t + 1] = step_sched[t] + 1
+            ep_sched[t + 1] = ep_sched[t]
+            for w, info in feed.infos[t]:
+                step_sched[t + 1, w] = 0
+                ep_sched[t + 1, w] = n_rows
+                n_rows += 1
+                if t < T - 1:
+                    self._n_episodes = n_rows
+                episode_infos.append(info)
+        while n_rows > self._table_cap:
+            self._alloc_table(self._table_cap * 2)
+        self._n_rows = n_rows
+        buf.rewards[:] = feed.rewards.T
+        buf.dones[:] = feed.dones.T
+        step_dev = torch.from_numpy(step_sched).to(self.device)
+        ep_dev = torch.from_numpy(ep_sched).to(self.device)
+        ctx = self._rollout_ctx()
+        with torch.no_grad():
+            for t in range(T):
+                self._device_step(t, feed.obs(t), step_dev[t], ep_dev[t], ctx)
+        self._step_host.copy_(torch.from_numpy(step_sched[T]))
+        self._ep_host.copy_(torch.from_numpy(ep_sched[T]))
+        self._feed_last_obs = feed.obs(T)
+        last_value = self.get_last_value()
+        buf.calc_advantages(last_value, cfg["gamma"], cfg["lamda"])
+        buf.memories = self._table[:self._n_episodes]
+        self.timers["rollout"] += time.perf_counter() - t0
+        return episode_infos
+
     def get_last_value(self):
         """Bootstrap value of the current observation (trainer.py:227-237).  Quirks kept: the window is
         ``[clip(s-L,0), clip(s,L))`` and the positional indices are those of the last rollout step."""
@@ -280,8 +340,11 @@ class PPOTrainer:
         self._step_dev.copy_(self._step_host, non_blocking=True)
         self._ep_dev.copy_(self._ep_host, non_blocking=True)
         with torch.no_grad():
-            self._obs_pinned.copy_(torch.from_numpy(self.obs))
-            self._obs_dev.copy_(self._obs_pinned, non_blocking=True)
+            if self.device_feed is not None:
+                self._obs_dev.copy_(self._feed_last_obs)
+            else:
+                self._obs_pinned.copy_(torch.from_numpy(self.obs))
+                self._obs_dev.copy_(self._obs_pinned, non_blocking=True)
             feat = self.model.encode(self._obs_dev)
             pe_idx = self.buffer.memory_indices[:, -1].contiguous()
             _, value, _ = self.model.forward_table(feat, self._table, self._ep_dev, self._win_last, self._mask_last, pe_idx, n=W)

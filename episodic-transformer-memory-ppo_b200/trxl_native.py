@@ -39,6 +39,9 @@ CFGP = C.POINTER(ModelConfig)
 SIGNATURES = {
     "trxl_last_error": (C.c_char_p, []),
     "trxl_abi_version": (i32, []),
+    "trxl_launch_count": (i64, []),
+    "trxl_profile_enable": (i32, [i32]),
+    "trxl_profile_read": (i32, [i32, i32, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "trxl_layout_num_entries": (i32, [CFGP]),
     "trxl_layout_total_floats": (i64, [CFGP]),
     "trxl_layout_entry": (i32, [CFGP, i32, C.POINTER(ParamEntry)]),
@@ -143,6 +146,22 @@ def layout(cfg):
         _check(lib.trxl_layout_entry(C.byref(cfg), i, C.byref(e)), "trxl_layout_entry")
         out.append((e.name.decode(), int(e.offset), tuple(int(e.shape[k]) for k in range(e.ndim)), int(e.group)))
     return out, int(lib.trxl_layout_total_floats(C.byref(cfg))), int(lib.trxl_layout_groups(C.byref(cfg)))
+
+
+def launch_count():
+    return int(load().trxl_launch_count())
+
+
+def profile_enable(on):
+    _check(load().trxl_profile_enable(int(bool(on))), "trxl_profile_enable")
+
+
+def profile_read(kind, min_samples=0):
+    """(total_ms, launches, samples) of the timed attention launches of `kind` (0 fwd, 1 bwd)."""
+    ms, launches, samples = C.c_double(0), C.c_int64(0), C.c_int64(0)
+    _check(load().trxl_profile_read(int(kind), int(min_samples), C.byref(ms), C.byref(launches), C.byref(samples)),
+           "trxl_profile_read")
+    return ms.value, launches.value, samples.value
 
 
 def workspace_floats(cfg, n):

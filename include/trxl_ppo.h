@@ -55,6 +55,13 @@ typedef struct trxl_param_entry {
 
 const char* trxl_last_error(void);
 int trxl_abi_version(void);
+/* kernels launched by this library since load (bench.py reports the delta as gpu_launches) */
+int64_t trxl_launch_count(void);
+/* Measurement aid: when enabled, every window-attention launch is bracketed by CUDA events on its own
+ * stream.  trxl_profile_read sums the durations of launches of `kind` (0 forward, 1 backward) that
+ * processed at least min_samples samples; synchronises on those events only. */
+int trxl_profile_enable(int on);
+int trxl_profile_read(int kind, int min_samples, double* total_ms, int64_t* launches, int64_t* samples);
 
 /* ---- parameter arena layout ------------------------------------------------------------------ */
 /* Number of entries / total floats of the arena for a config (<0 on invalid config). */
