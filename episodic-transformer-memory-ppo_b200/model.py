@@ -20,11 +20,18 @@ from transformer import Transformer
 
 
 def _conv_features(obs, c1, c2, c3):
-    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):      # fp32 parity with the CPU reference
-        h = F.relu(F.conv2d(obs, c1.weight, c1.bias, stride=4))
-        h = F.relu(F.conv2d(h, c2.weight, c2.bias, stride=2))
-        h = F.relu(F.conv2d(h, c3.weight, c3.bias, stride=1))
+    h = F.relu(F.conv2d(obs, c1.weight, c1.bias, stride=4))
+    h = F.relu(F.conv2d(h, c2.weight, c2.bias, stride=2))
+    h = F.relu(F.conv2d(h, c3.weight, c3.bias, stride=1))
     return h.reshape(obs.shape[0], -1)
+
+
+def _require_fp32_convolutions():
+    """The engine's parity contract is fp32 (1e-4 against the CPU reference).  cuDNN would otherwise
+    run the encoder's convolutions -- forward AND backward, which executes outside any local context
+    manager -- in TF32, so the switch is process-wide."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
 
 
 class _TrunkFunction(torch.autograd.Function):
@@ -70,6 +77,7 @@ class ActorCriticModel(nn.Module):
         self.action_space_shape = tuple(int(a) for a in action_space_shape)
         tcfg = config["transformer"]
         self._visual = len(self.observation_space_shape) > 1
+        _require_fp32_convolutions()
 
         # ---- parameter holders with the reference's names and init recipes (model.py:27-69) ----
         if self._visual:
