@@ -178,6 +178,7 @@ def run_b200(args, cfg, name):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     native.load()
+    torch.set_num_threads(min(8, os.cpu_count() or 1))     # the trainer process only runs small host ops
     parallel.init_from_env("nccl")
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)

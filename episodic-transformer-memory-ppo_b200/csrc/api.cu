@@ -30,8 +30,13 @@ ProfSlot* g_prof[PROF_KINDS] = {nullptr, nullptr};
 int g_prof_count[PROF_KINDS] = {0, 0};
 }  // namespace
 
+static bool stream_capturing(cudaStream_t st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    return cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
+}
+
 void trxl_prof_begin(int kind, int n, cudaStream_t st) {
-    if (!g_prof_on || g_prof_count[kind] >= PROF_CAP) return;
+    if (!g_prof_on || g_prof_count[kind] >= PROF_CAP || stream_capturing(st)) return;
     if (!g_prof[kind]) {
         g_prof[kind] = new ProfSlot[PROF_CAP];
         for (int i = 0; i < PROF_CAP; ++i) { cudaEventCreate(&g_prof[kind][i].a); cudaEventCreate(&g_prof[kind][i].b); }
@@ -41,7 +46,7 @@ void trxl_prof_begin(int kind, int n, cudaStream_t st) {
     cudaEventRecord(s.a, st);
 }
 void trxl_prof_end(int kind, cudaStream_t st) {
-    if (!g_prof_on || g_prof_count[kind] >= PROF_CAP || !g_prof[kind]) return;
+    if (!g_prof_on || g_prof_count[kind] >= PROF_CAP || !g_prof[kind] || stream_capturing(st)) return;
     cudaEventRecord(g_prof[kind][g_prof_count[kind]].b, st);
     ++g_prof_count[kind];
 }

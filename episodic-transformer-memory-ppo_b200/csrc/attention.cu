@@ -181,20 +181,29 @@ window_attn_fwd_kernel(const AttnArgs a) {
                 float e = LN ? fmaf(rstd, red[h] - mu * sg[h], qb[h]) : red[h];
                 e = all_masked ? 0.f : __fdiv_rn(e, a.scale);
                 if (lane == 0) s_e[h * Lp + ll] = e;
-                const float m_new = fmaxf(m_run[h], e);
-                const float corr = __expf(m_run[h] - m_new);          // exp(-inf) = 0 on first row
-                const float pe_ = __expf(e - m_new);
-                s_run[h] = s_run[h] * corr + pe_;
+                // online softmax with a lazy rescale: the running max rises O(log L) times per sample, so the
+                // accumulator is only rescaled on those rows (e is identical on all lanes -> warp-uniform branch)
+                if (e > m_run[h]) {
+                    const float corr = __expf(m_run[h] - e);          // exp(-inf) = 0 on the first row
+                    s_run[h] *= corr;
+                    if (LN) c_run[h] *= corr;
+#pragma unroll
+                    for (int c = 0; c < NV4; ++c) {
+                        acc[h][c].x *= corr; acc[h][c].y *= corr; acc[h][c].z *= corr; acc[h][c].w *= corr;
+                    }
+                    m_run[h] = e;
+                }
+                const float pe_ = __expf(e - m_run[h]);
+                s_run[h] += pe_;
                 const float wgt = pe_ * rstd;
-                if (LN) c_run[h] = c_run[h] * corr + wgt * mu;
+                if (LN) c_run[h] = fmaf(wgt, mu, c_run[h]);
 #pragma unroll
                 for (int c = 0; c < NV4; ++c) {
-                    acc[h][c].x = fmaf(wgt, x[c].x, acc[h][c].x * corr);
-                    acc[h][c].y = fmaf(wgt, x[c].y, acc[h][c].y * corr);
-                    acc[h][c].z = fmaf(wgt, x[c].z, acc[h][c].z * corr);
-                    acc[h][c].w = fmaf(wgt, x[c].w, acc[h][c].w * corr);
+                    acc[h][c].x = fmaf(wgt, x[c].x, acc[h][c].x);
+                    acc[h][c].y = fmaf(wgt, x[c].y, acc[h][c].y);
+                    acc[h][c].z = fmaf(wgt, x[c].z, acc[h][c].z);
+                    acc[h][c].w = fmaf(wgt, x[c].w, acc[h][c].w);
                 }
-                m_run[h] = m_new;
             }
         }
     }

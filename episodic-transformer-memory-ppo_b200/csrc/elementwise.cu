@@ -258,7 +258,8 @@ __global__ void unfold_kernel(const float* __restrict__ dWg, const float* __rest
     dbeta[j] = accumulate ? dbeta[j] + sb : sb;
 }
 
-int chunks_for(int rows) { return rows >= 4096 ? 32 : (rows >= 512 ? 16 : (rows >= 64 ? 4 : 1)); }
+// row chunks of the two-pass column reductions: enough CTAs to cover the SMs at training batch sizes
+int chunks_for(int rows) { return rows >= 1024 ? 64 : (rows >= 256 ? 16 : (rows >= 32 ? 4 : 1)); }
 
 }  // namespace
 

@@ -27,7 +27,9 @@ sgemm_kernel(const GemmArgs g) {
     const int tid = threadIdx.x;
     const int tx = tid % (BN / TN), ty = tid / (BN / TN);
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int b = blockIdx.z;
+    const int b = blockIdx.z / g.ksplit, split = blockIdx.z % g.ksplit;
+    const int k_begin = split * g.k_per_split;
+    const int k_end = min(g.K, k_begin + g.k_per_split);
     const float* __restrict__ A = g.A + (long long)b * g.sA;
     const float* __restrict__ B = g.B + (long long)b * g.sB;
     float* __restrict__ C = g.C + (long long)b * g.sC;
@@ -48,17 +50,17 @@ sgemm_kernel(const GemmArgs g) {
                     const int m = m0 + v / (BK / 4), k = k0 + (v % (BK / 4)) * 4;
                     if (m < g.M) {
                         const float* p = A + (long long)m * g.lda + k;
-                        if (g.vecA && k + 3 < g.K) val = *reinterpret_cast<const float4*>(p);
+                        if (g.vecA && k + 3 < k_end) val = *reinterpret_cast<const float4*>(p);
                         else {
-                            if (k < g.K) val.x = p[0];
-                            if (k + 1 < g.K) val.y = p[1];
-                            if (k + 2 < g.K) val.z = p[2];
-                            if (k + 3 < g.K) val.w = p[3];
+                            if (k < k_end) val.x = p[0];
+                            if (k + 1 < k_end) val.y = p[1];
+                            if (k + 2 < k_end) val.z = p[2];
+                            if (k + 3 < k_end) val.w = p[3];
                         }
                     }
                 } else {
                     const int k = k0 + v / (BM / 4), m = m0 + (v % (BM / 4)) * 4;
-                    if (k < g.K) {
+                    if (k < k_end) {
                         const float* p = A + (long long)k * g.lda + m;
                         if (g.vecA && m + 3 < g.M) val = *reinterpret_cast<const float4*>(p);
                         else {
@@ -83,17 +85,17 @@ sgemm_kernel(const GemmArgs g) {
                     const int n = n0 + v / (BK / 4), k = k0 + (v % (BK / 4)) * 4;
                     if (n < g.N) {
                         const float* p = B + (long long)n * g.ldb + k;
-                        if (g.vecB && k + 3 < g.K) val = *reinterpret_cast<const float4*>(p);
+                        if (g.vecB && k + 3 < k_end) val = *reinterpret_cast<const float4*>(p);
                         else {
-                            if (k < g.K) val.x = p[0];
-                            if (k + 1 < g.K) val.y = p[1];
-                            if (k + 2 < g.K) val.z = p[2];
-                            if (k + 3 < g.K) val.w = p[3];
+                            if (k < k_end) val.x = p[0];
+                            if (k + 1 < k_end) val.y = p[1];
+                            if (k + 2 < k_end) val.z = p[2];
+                            if (k + 3 < k_end) val.w = p[3];
                         }
                     }
                 } else {
                     const int k = k0 + v / (BN / 4), n = n0 + (v % (BN / 4)) * 4;
-                    if (k < g.K) {
+                    if (k < k_end) {
                         const float* p = B + (long long)k * g.ldb + n;
                         if (g.vecB && n + 3 < g.N) val = *reinterpret_cast<const float4*>(p);
                         else {
@@ -145,16 +147,16 @@ sgemm_kernel(const GemmArgs g) {
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-    const int nk = (g.K + BK - 1) / BK;
-    load_a(0);
-    load_b(0);
+    const int nk = (k_end - k_begin + BK - 1) / BK;
+    load_a(k_begin);
+    load_b(k_begin);
     store_tiles(0);
     __syncthreads();
     for (int kt = 0; kt < nk; ++kt) {
         const int buf = kt & 1;
         if (kt + 1 < nk) {
-            load_a((kt + 1) * BK);
-            load_b((kt + 1) * BK);
+            load_a(k_begin + (kt + 1) * BK);
+            load_b(k_begin + (kt + 1) * BK);
         }
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
@@ -182,6 +184,10 @@ sgemm_kernel(const GemmArgs g) {
         for (int j = 0; j < TN; ++j) {
             const int n = n0 + tx * TN + j;
             if (n >= g.N) continue;
+            if (g.ksplit > 1) {      // raw partial; the epilogue runs in splitk_reduce_kernel
+                g.ws[((long long)blockIdx.z * g.M + m) * g.N + n] = acc[i][j];
+                continue;
+            }
             float v = acc[i][j] * g.alpha;
             if (bias) v += bias[n];
             if (g.relu) v = fmaxf(v, 0.f);
@@ -193,9 +199,27 @@ sgemm_kernel(const GemmArgs g) {
     }
 }
 
+// sums the split-K partials in split order (deterministic) and applies the epilogue
+__global__ void splitk_reduce_kernel(const GemmArgs g) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long mn = (long long)g.M * g.N;
+    if (i >= mn * g.batch) return;
+    const int b = (int)(i / mn);
+    const int m = (int)((i % mn) / g.N), n = (int)(i % g.N);
+    float v = 0.f;
+    for (int s = 0; s < g.ksplit; ++s) v += g.ws[((long long)(b * g.ksplit + s) * g.M + m) * g.N + n];
+    v *= g.alpha;
+    if (g.bias) v += g.bias[(long long)b * g.sBias + n];
+    if (g.relu) v = fmaxf(v, 0.f);
+    if (g.R) v += g.R[(long long)b * g.sR + (long long)m * g.ldr + n];
+    float* cp = g.C + (long long)b * g.sC + (long long)m * g.ldc + n;
+    if (g.accumulate) v += *cp;
+    *cp = v;
+}
+
 template <int BM, int BN, int TM, int TN>
 int launch_cfg(const GemmArgs& g, cudaStream_t st) {
-    dim3 grid(trxl_cdiv(g.N, BN), trxl_cdiv(g.M, BM), g.batch);
+    dim3 grid(trxl_cdiv(g.N, BN), trxl_cdiv(g.M, BM), g.batch * g.ksplit);
     dim3 block((BM / TM) * (BN / TN));
     if (g.a_kc && g.b_kc) sgemm_kernel<BM, BN, TM, TN, true, true><<<grid, block, 0, st>>>(g);
     else if (g.a_kc && !g.b_kc) sgemm_kernel<BM, BN, TM, TN, true, false><<<grid, block, 0, st>>>(g);
@@ -218,6 +242,26 @@ int trxl_gemm(GemmArgs g, cudaStream_t st) {
     if (g.alpha == 0.f) g.alpha = 1.f;
     // tile choice: small problems get small tiles so more CTAs are in flight
     const long long tiles64 = (long long)trxl_cdiv(g.M, 64) * trxl_cdiv(g.N, 64) * g.batch;
-    if (g.M <= 32 || g.N <= 32 || tiles64 < 96) return launch_cfg<32, 32, 2, 2>(g, st);
-    return launch_cfg<64, 64, 4, 4>(g, st);
+    // split-K: weight-gradient shapes (small M x N, long K = samples) would otherwise occupy a handful of SMs
+    g.ksplit = 1;
+    g.k_per_split = g.K;
+    if (g.ws && g.K >= 512 && tiles64 * 4 <= 148) {
+        int want = (int)((148 * 2 + tiles64 - 1) / tiles64);
+        int maxs = g.K / 128;
+        int s = want < maxs ? want : maxs;
+        if (s > 32) s = 32;
+        while (s > 1 && (long long)s * g.batch * g.M * g.N > g.ws_floats) --s;
+        if (s > 1) {
+            g.k_per_split = ((g.K + s - 1) / s + BK - 1) / BK * BK;
+            g.ksplit = (g.K + g.k_per_split - 1) / g.k_per_split;
+        }
+    }
+    int rc;
+    if (g.ksplit == 1 && (g.M <= 32 || g.N <= 32 || tiles64 < 96)) rc = launch_cfg<32, 32, 2, 2>(g, st);
+    else rc = launch_cfg<64, 64, 4, 4>(g, st);
+    if (rc != TRXL_OK || g.ksplit == 1) return rc;
+    const long long total = (long long)g.M * g.N * g.batch;
+    splitk_reduce_kernel<<<trxl_cdiv(total, 256), 256, 0, st>>>(g);
+    TRXL_CHECK_LAUNCH("splitk_reduce");
+    return TRXL_OK;
 }

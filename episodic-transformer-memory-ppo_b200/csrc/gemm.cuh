@@ -12,7 +12,8 @@ struct GemmArgs {
     int accumulate = 0;                   // C += result
     float alpha = 1.f;
     int batch = 1; long long sA = 0, sB = 0, sC = 0, sBias = 0, sR = 0;
-    int vecA = 0, vecB = 0;               // filled by trxl_gemm
+    float* ws = nullptr; long long ws_floats = 0;   // optional split-K workspace
+    int vecA = 0, vecB = 0, ksplit = 1, k_per_split = 0;   // filled by trxl_gemm
 };
 
 int trxl_gemm(GemmArgs g, cudaStream_t st);
@@ -34,8 +35,8 @@ static inline int gemm_nn(cudaStream_t st, int M, int K, int N, const float* dy,
 }
 // dW (N,K) = dy^T (N,M) * x (M,K)
 static inline int gemm_tn(cudaStream_t st, int N, int K, int M, const float* dy, long long lddy, const float* x, long long ldx,
-                          float* dW, long long lddw, int accumulate = 0) {
+                          float* dW, long long lddw, int accumulate = 0, float* ws = nullptr, long long ws_floats = 0) {
     GemmArgs g; g.M = N; g.N = K; g.K = M; g.A = dy; g.lda = lddy; g.a_kc = 0; g.B = x; g.ldb = ldx; g.b_kc = 0;
-    g.C = dW; g.ldc = lddw; g.accumulate = accumulate;
+    g.C = dW; g.ldc = lddw; g.accumulate = accumulate; g.ws = ws; g.ws_floats = ws_floats;
     return trxl_gemm(g, st);
 }

@@ -166,6 +166,7 @@ struct Acts {
     // backward scratch
     float *pool[2][9], *dH0;
     float *dctx, *dqk, *dqkb, *dA1, *dz, *drx, *dWg, *dvec, *dhp, *dhv, *ew;
+    float* gemm_ws; long long gemm_ws_n;      // split-K partials of the weight-gradient GEMMs
     long long total;
 };
 
@@ -206,6 +207,8 @@ void carve(const trxl_model_config* c, int N, float* ws, Acts& A) {
     A.dhp = b.take(N * hid); A.dhv = b.take(N * hid);
     long long widest = 3 * D; if (hid > widest) widest = hid; if (sumA > widest) widest = sumA; if (c->feat_dim > widest) widest = c->feat_dim;
     A.ew = b.take(ew_scratch_floats(N, (int)widest));
+    A.gemm_ws_n = 32LL * D * (D > hid ? D : hid);
+    A.gemm_ws = b.take(A.gemm_ws_n);
     A.total = b.cur;
 }
 
@@ -235,11 +238,11 @@ int gate_backward(cudaStream_t st, const float* P, float* G, const GateP& gp, co
                   const float* x, long long ldx, const float* y, long long ldy, float* dx, float* dy, int N, int D) {
     const long long D3 = 3LL * D;
     TRXL_PROPAGATE(ew_gate_bwd_a(st, dout, D, x, ldx, ga.z, ga.hc, A.dA1, A.dz, dx, D, 0, N, D));
-    TRXL_PROPAGATE(gemm_tn(st, D, D, N, A.dA1 + 2 * D, D3, ga.rx, D, G + gp.Ug, D));
+    TRXL_PROPAGATE(gemm_tn(st, D, D, N, A.dA1 + 2 * D, D3, ga.rx, D, G + gp.Ug, D, 0, A.gemm_ws, A.gemm_ws_n));
     TRXL_PROPAGATE(gemm_nn(st, N, D, D, A.dA1 + 2 * D, D3, P + gp.Ug, D, A.drx, D));
     TRXL_PROPAGATE(ew_gate_bwd_b(st, A.drx, x, ldx, ga.r, ga.z, A.dz, A.dA1, dx, D, N, D));
-    TRXL_PROPAGATE(gemm_tn(st, 3 * D, D, N, A.dA1, D3, y, ldy, G + gp.Wr, D));
-    TRXL_PROPAGATE(gemm_tn(st, 2 * D, D, N, A.dA1, D3, x, ldx, G + gp.Ur, D));
+    TRXL_PROPAGATE(gemm_tn(st, 3 * D, D, N, A.dA1, D3, y, ldy, G + gp.Wr, D, 0, A.gemm_ws, A.gemm_ws_n));
+    TRXL_PROPAGATE(gemm_tn(st, 2 * D, D, N, A.dA1, D3, x, ldx, G + gp.Ur, D, 0, A.gemm_ws, A.gemm_ws_n));
     TRXL_PROPAGATE(ew_colsum(st, A.dA1 + D, D3, G + gp.bg, N, D, -1.f, 0, A.ew));
     TRXL_PROPAGATE(gemm_nn(st, N, D, 3 * D, A.dA1, D3, P + gp.Wr, D, dy, D));
     TRXL_PROPAGATE(gemm_nn(st, N, D, 2 * D, A.dA1, D3, P + gp.Ur, D, dx, D, 1));
@@ -248,10 +251,10 @@ int gate_backward(cudaStream_t st, const float* P, float* G, const GateP& gp, co
 
 int per_head_gemm(cudaStream_t st, int M, int Nn, int K, const float* A, long long lda, int a_kc, long long sA, const float* B,
                   long long ldb, int b_kc, long long sB, float* C, long long ldc, long long sC, int H, const float* bias = nullptr,
-                  long long sBias = 0) {
+                  long long sBias = 0, float* ws = nullptr, long long ws_n = 0) {
     GemmArgs g;
     g.M = M; g.N = Nn; g.K = K; g.A = A; g.lda = lda; g.a_kc = a_kc; g.sA = sA; g.B = B; g.ldb = ldb; g.b_kc = b_kc; g.sB = sB;
-    g.C = C; g.ldc = ldc; g.sC = sC; g.batch = H; g.bias = bias; g.sBias = sBias;
+    g.C = C; g.ldc = ldc; g.sC = sC; g.batch = H; g.bias = bias; g.sBias = sBias; g.ws = ws; g.ws_floats = ws_n;
     return trxl_gemm(g, st);
 }
 
@@ -364,18 +367,18 @@ int model_backward(const trxl_model_config* c, const float* P, float* G, const M
 
     // ---- heads ----
     float* dH = A.dH0;        // gradient w.r.t. the current block output; never inside the pool being used
-    TRXL_PROPAGATE(gemm_tn(st, L.sumA, hid, N, dlogits, L.sumA, A.hp, hid, G + L.Wbr, hid));
+    TRXL_PROPAGATE(gemm_tn(st, L.sumA, hid, N, dlogits, L.sumA, A.hp, hid, G + L.Wbr, hid, 0, A.gemm_ws, A.gemm_ws_n));
     TRXL_PROPAGATE(ew_colsum(st, dlogits, L.sumA, G + L.bbr, N, L.sumA, 1.f, 0, A.ew));
     TRXL_PROPAGATE(gemm_nn(st, N, hid, L.sumA, dlogits, L.sumA, P + L.Wbr, hid, A.dhp, hid));
     TRXL_PROPAGATE(ew_relu_bwd(st, A.dhp, hid, A.hp, hid, A.dhp, hid, N, hid, 0));
-    TRXL_PROPAGATE(gemm_tn(st, hid, D, N, A.dhp, hid, A.h_final, D, G + L.Wp, D));
+    TRXL_PROPAGATE(gemm_tn(st, hid, D, N, A.dhp, hid, A.h_final, D, G + L.Wp, D, 0, A.gemm_ws, A.gemm_ws_n));
     TRXL_PROPAGATE(ew_colsum(st, A.dhp, hid, G + L.bp, N, hid, 1.f, 0, A.ew));
     TRXL_PROPAGATE(gemm_nn(st, N, D, hid, A.dhp, hid, P + L.Wp, D, dH, D));
-    TRXL_PROPAGATE(gemm_tn(st, 1, hid, N, dvalue, 1, A.hv, hid, G + L.wval, hid));
+    TRXL_PROPAGATE(gemm_tn(st, 1, hid, N, dvalue, 1, A.hv, hid, G + L.wval, hid, 0, A.gemm_ws, A.gemm_ws_n));
     TRXL_PROPAGATE(ew_colsum(st, dvalue, 1, G + L.bval, N, 1, 1.f, 0, A.ew));
     TRXL_PROPAGATE(gemm_nn(st, N, hid, 1, dvalue, 1, P + L.wval, hid, A.dhv, hid));
     TRXL_PROPAGATE(ew_relu_bwd(st, A.dhv, hid, A.hv, hid, A.dhv, hid, N, hid, 0));
-    TRXL_PROPAGATE(gemm_tn(st, hid, D, N, A.dhv, hid, A.h_final, D, G + L.Wlv, D));
+    TRXL_PROPAGATE(gemm_tn(st, hid, D, N, A.dhv, hid, A.h_final, D, G + L.Wlv, D, 0, A.gemm_ws, A.gemm_ws_n));
     TRXL_PROPAGATE(ew_colsum(st, A.dhv, hid, G + L.blv, N, hid, 1.f, 0, A.ew));
     TRXL_PROPAGATE(gemm_nn(st, N, D, hid, A.dhv, hid, P + L.Wlv, D, dH, D, 1));
 
@@ -403,7 +406,7 @@ int model_backward(const trxl_model_config* c, const float* P, float* G, const M
         }
         // f = relu(h_ Wff^T + bff)
         TRXL_PROPAGATE(ew_relu_bwd(st, dF, D, a.f, D, S[3], D, N, D, 0));
-        TRXL_PROPAGATE(gemm_tn(st, D, D, N, S[3], D, h_, D, G + p.Wff, D));
+        TRXL_PROPAGATE(gemm_tn(st, D, D, N, S[3], D, h_, D, G + p.Wff, D, 0, A.gemm_ws, A.gemm_ws_n));
         TRXL_PROPAGATE(ew_colsum(st, S[3], D, G + p.bff, N, D, 1.f, 0, A.ew));
         if (pre) {
             TRXL_PROPAGATE(gemm_nn(st, N, D, D, S[3], D, P + p.Wff, D, S[4], D));
@@ -424,14 +427,14 @@ int model_backward(const trxl_model_config* c, const float* P, float* G, const M
             dHin = dH1pre; dAtt = dH1pre;
         }
         // att = att_o Wo^T + bo
-        TRXL_PROPAGATE(gemm_tn(st, D, D, N, dAtt, D, a.att_o, D, G + p.Wo, D));
+        TRXL_PROPAGATE(gemm_tn(st, D, D, N, dAtt, D, a.att_o, D, G + p.Wo, D, 0, A.gemm_ws, A.gemm_ws_n));
         TRXL_PROPAGATE(ew_colsum(st, dAtt, D, G + p.bo, N, D, 1.f, 0, A.ew));
         float* dAtto = S[3];
         TRXL_PROPAGATE(gemm_nn(st, N, D, D, dAtt, D, P + p.Wo, D, dAtto, D));
         const float* Wkg = pre ? a.Wkg : P + p.Wk;
         const float* Wvg = pre ? a.Wvg : P + p.Wv;
         // dWvg[h*dh + j, :] = sum_n dAtto[n, h*dh + j] ctx[n,h,:]
-        TRXL_PROPAGATE(per_head_gemm(st, dh, D, N, dAtto, D, 0, dh, a.ctx, HD, 0, D, pre ? A.dWg : G + p.Wv, D, (long long)dh * D, H));
+        TRXL_PROPAGATE(per_head_gemm(st, dh, D, N, dAtto, D, 0, dh, a.ctx, HD, 0, D, pre ? A.dWg : G + p.Wv, D, (long long)dh * D, H, nullptr, 0, A.gemm_ws, A.gemm_ws_n));
         // dctx[n,h,:] = sum_j dAtto[n, h*dh + j] Wvg[h*dh + j, :]
         TRXL_PROPAGATE(per_head_gemm(st, N, D, dh, dAtto, D, 1, dh, Wvg, D, 0, (long long)dh * D, A.dctx, HD, D, H));
         if (pre) {
@@ -446,13 +449,13 @@ int model_backward(const trxl_model_config* c, const float* P, float* G, const M
         float* dQ = S[4];
         TRXL_PROPAGATE(per_head_gemm(st, N, dh, D, A.dqk, HD, 1, D, Wkg, D, 1, (long long)dh * D, dQ, D, dh, H));
         // dWkg[h*dh + j, :] = sum_n Q[n, h*dh + j] dqk[n,h,:]
-        TRXL_PROPAGATE(per_head_gemm(st, dh, D, N, a.Q, D, 0, dh, A.dqk, HD, 0, D, pre ? A.dWg : G + p.Wk, D, (long long)dh * D, H));
+        TRXL_PROPAGATE(per_head_gemm(st, dh, D, N, a.Q, D, 0, dh, A.dqk, HD, 0, D, pre ? A.dWg : G + p.Wk, D, (long long)dh * D, H, nullptr, 0, A.gemm_ws, A.gemm_ws_n));
         if (pre) {
             TRXL_PROPAGATE(ew_head_dot_bwd(st, a.Q, A.dqkb, a.kb, dQ, A.dvec, N, H, dh, A.ew));
             TRXL_PROPAGATE(ew_unfold(st, A.dWg, A.dvec, P + p.Wk, P + p.nkw, P + p.nkb, G + p.Wk, G + p.nkw, G + p.nkb, D, D, 1));
         }
         // Q = q_in Wq^T
-        TRXL_PROPAGATE(gemm_tn(st, D, D, N, dQ, D, q_in, ld_q, G + p.Wq, D));
+        TRXL_PROPAGATE(gemm_tn(st, D, D, N, dQ, D, q_in, ld_q, G + p.Wq, D, 0, A.gemm_ws, A.gemm_ws_n));
         if (pre) {
             TRXL_PROPAGATE(gemm_nn(st, N, D, D, dQ, D, P + p.Wq, D, S[8], D));
             TRXL_PROPAGATE(ew_layernorm_bwd(st, S[8], D, h_in, BD, a.m1, a.r1, P + p.n1w, dHin, D, 1, G + p.n1w, G + p.n1b, 0, A.ew, N, D));
@@ -465,12 +468,12 @@ int model_backward(const trxl_model_config* c, const float* P, float* G, const M
     float** S = A.pool[1];                      // block 0 used pool[0]; pool[1] is free again
     float* dE = S[0];
     TRXL_PROPAGATE(ew_relu_bwd(st, dH, D, out_mem, BD, dE, D, N, D, 0));
-    TRXL_PROPAGATE(gemm_tn(st, D, D, N, dE, D, A.h0, D, G + L.We, D));
+    TRXL_PROPAGATE(gemm_tn(st, D, D, N, dE, D, A.h0, D, G + L.We, D, 0, A.gemm_ws, A.gemm_ws_n));
     TRXL_PROPAGATE(ew_colsum(st, dE, D, G + L.be, N, D, 1.f, 0, A.ew));
     float* dh0 = S[1];
     TRXL_PROPAGATE(gemm_nn(st, N, D, D, dE, D, P + L.We, D, dh0, D));
     TRXL_PROPAGATE(ew_relu_bwd(st, dh0, D, A.h0, D, dh0, D, N, D, 0));
-    TRXL_PROPAGATE(gemm_tn(st, D, c->feat_dim, N, dh0, D, io.feat, c->feat_dim, G + L.Wh, c->feat_dim));
+    TRXL_PROPAGATE(gemm_tn(st, D, c->feat_dim, N, dh0, D, io.feat, c->feat_dim, G + L.Wh, c->feat_dim, 0, A.gemm_ws, A.gemm_ws_n));
     TRXL_PROPAGATE(ew_colsum(st, dh0, D, G + L.bh, N, D, 1.f, 0, A.ew));
     if (dfeat) TRXL_PROPAGATE(gemm_nn(st, N, c->feat_dim, D, dh0, D, P + L.Wh, c->feat_dim, dfeat, c->feat_dim));
     return TRXL_OK;

@@ -251,21 +251,24 @@ __global__ void sumsq_chunks_kernel(const float* __restrict__ g, const long long
     if (threadIdx.x == 0) part[blockIdx.x] = s;
 }
 // norms[0..G-1] = per-group L2 norms (unclipped), norms[G] = total norm, norms[G+1] = clip coefficient
+// One warp per group (warp G = the total): lanes stride over the chunk partials, then a fixed-order
+// butterfly -> deterministic.  Launched with (G + 1) warps.
 __global__ void clip_finalize_kernel(const float* __restrict__ part, const long long* __restrict__ chunks, int nchunks, int G,
                                      float max_norm, float* __restrict__ norms) {
-    __shared__ float total_sm;
-    const int gidx = threadIdx.x;
-    if (gidx <= G) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int gidx = warp; gidx <= G; gidx += nwarps) {
         float s = 0.f;
-        for (int c = 0; c < nchunks; ++c)
+        for (int c = lane; c < nchunks; c += 32)
             if (gidx == G || chunks[c * 3 + 2] == gidx) s += part[c];
-        norms[gidx] = sqrtf(s);
-        if (gidx == G) total_sm = sqrtf(s);
-    }
-    __syncthreads();
-    if (gidx == 0) {
-        const float coef = max_norm / (total_sm + 1e-6f);
-        norms[G + 1] = coef < 1.f ? coef : 1.f;
+        s = warp_sum(s);
+        if (lane == 0) {
+            const float nrm = sqrtf(s);
+            norms[gidx] = nrm;
+            if (gidx == G) {
+                const float coef = max_norm / (nrm + 1e-6f);
+                norms[G + 1] = coef < 1.f ? coef : 1.f;
+            }
+        }
     }
 }
 __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
@@ -367,13 +370,10 @@ long long ppo_loss_partial_floats(int N) { return (long long)trxl_cdiv(N, 128) *
 
 int ppo_clip_adamw(cudaStream_t st, float* params, float* grads, float* m, float* v, long long total, const long long* chunks,
                    int nchunks, int ngroups, float max_norm, float* partial, float* norms, const AdamWArgs& h) {
-    TRXL_CHECK_ARG(ngroups + 1 <= 1024, "clip_adamw: too many groups");
     if (nchunks > 0) {
         sumsq_chunks_kernel<<<nchunks, 256, 0, st>>>(grads, chunks, partial);
         TRXL_CHECK_LAUNCH("sumsq_chunks");
-        int threads = 32;
-        while (threads < ngroups + 1) threads *= 2;
-        clip_finalize_kernel<<<1, threads, 0, st>>>(partial, chunks, nchunks, ngroups, max_norm, norms);
+        clip_finalize_kernel<<<1, 32 * (ngroups + 1 < 32 ? ngroups + 1 : 32), 0, st>>>(partial, chunks, nchunks, ngroups, max_norm, norms);
         TRXL_CHECK_LAUNCH("clip_finalize");
     }
     int blocks = trxl_cdiv(total, 256 * 4);

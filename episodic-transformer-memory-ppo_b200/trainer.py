@@ -86,15 +86,26 @@ class PPOTrainer:
         self.optimizer = FusedClipAdamW(self.model, lr=self.lr_schedule["initial"], max_grad_norm=config["max_grad_norm"])
 
         # env workers: anything with a ``child`` pipe end speaking the reference protocol
-        self.workers = workers if workers is not None else [Worker(self._env_config(w)) for w in range(self.num_workers)]
+        # Own workers write observations into a shared-memory slab that is also registered as pinned host memory,
+        # so the per-step image payload goes env process -> slab -> (DMA) GPU without pickling or staging copies.
         # (pass workers=[] together with trainer.device_feed = SyntheticDeviceFeed(...) to run without env processes)
+        self._obs_slab = None
+        if workers is None:
+            self._obs_slab = torch.zeros((self.num_workers,) + self.obs_shape, dtype=torch.float32).share_memory_()
+            workers = [Worker(self._env_config(w), self._obs_slab, w) for w in range(self.num_workers)]
+            rc = torch.cuda.cudart().cudaHostRegister(self._obs_slab.data_ptr(), self._obs_slab.numel() * 4, 0)
+            self._slab_pinned = (int(rc) == 0) if not isinstance(rc, tuple) else (int(rc[0]) == 0)
+        self.workers = workers
         self.worker_ids = range(self.num_workers)
         self.worker_current_episode_step = torch.zeros((self.num_workers,), dtype=torch.long)
         for worker in self.workers:
             worker.child.send(("reset", None))
-        self.obs = np.zeros((self.num_workers,) + self.obs_shape, dtype=np.float32)
+        self.obs = self._obs_slab.numpy() if self._obs_slab is not None else np.zeros((self.num_workers,) + self.obs_shape,
+                                                                                      dtype=np.float32)
         for w, worker in enumerate(self.workers):
-            self.obs[w] = worker.child.recv()
+            first = worker.child.recv()
+            if first is not None:
+                self.obs[w] = first
         self._feed_last_obs = None
 
         # bit-exact integer tables, built on the host and uploaded once
@@ -125,6 +136,9 @@ class PPOTrainer:
         self._win_last = torch.zeros((W, L), dtype=torch.long, device=dev)
         self._mask_last = torch.zeros((W, L), dtype=torch.uint8, device=dev)
         self._train_state = {}
+        self._ctx = None
+        self.use_cuda_graphs = os.environ.get("TRXL_NO_GRAPHS", "0") != "1"
+        self._graphs, self._graph_pool, self._capture_stream = {}, None, None
         self.device_feed = None         # optional device_feed.SyntheticDeviceFeed replacing the env workers (bench.py)
         self._forced_actions = None     # optional (T, W, n_branches) int64 device tensor: replay these actions (parity tests)
         self.timers = {"rollout": 0.0, "train": 0.0, "env": 0.0}
@@ -206,15 +220,74 @@ class PPOTrainer:
             s[0], s[1], s[3], s[2], torch.mean(self.buffer.values).item(), torch.mean(self.buffer.advantages).item()))
 
     # ------------------------------------------------------------------------------------------ rollout
+    def _upload_obs(self):
+        """Current observations of all workers -> device.  Shared pinned slab: one DMA; otherwise stage
+        through a pinned buffer."""
+        if self._obs_slab is not None and self._slab_pinned:
+            self._obs_dev.copy_(self._obs_slab, non_blocking=True)
+        else:
+            self._obs_pinned.copy_(torch.from_numpy(self.obs))
+            self._obs_dev.copy_(self._obs_pinned, non_blocking=True)
+
     def _rollout_ctx(self):
-        buf, W, T, L = self.buffer, self.num_workers, self.config["worker_steps"], self.memory_length
-        nb = len(self.action_space_shape)
-        return {
-            "flat_mask": buf.memory_mask.view(torch.uint8).view(W * T, L), "flat_idx": buf.memory_indices.view(W * T, L),
-            "flat_ep": buf.memory_index.view(W * T), "inner": self.num_blocks * self.embed_dim,
-            "uniforms": torch.rand((T, W, nb), device=self.device), "ws": self.model.workspace(W),
-            "outs": self.model._alloc_outputs(W, self.device),
-        }
+        """Persistent per-trainer rollout buffers (their addresses are baked into the captured CUDA
+        graphs); the sampling uniforms are redrawn in place every update."""
+        if self._ctx is None:
+            buf, W, T, L = self.buffer, self.num_workers, self.config["worker_steps"], self.memory_length
+            nb = len(self.action_space_shape)
+            self._ctx = {
+                "flat_mask": buf.memory_mask.view(torch.uint8).view(W * T, L), "flat_idx": buf.memory_indices.view(W * T, L),
+                "flat_ep": buf.memory_index.view(W * T), "inner": self.num_blocks * self.embed_dim,
+                "uniforms": torch.empty((T, W, nb), device=self.device), "ws": self.model.workspace(W),
+                "outs": self.model._alloc_outputs(W, self.device),
+                "step_sched": torch.zeros((T + 1, W), dtype=torch.long, device=self.device),
+                "ep_sched": torch.zeros((T + 1, W), dtype=torch.long, device=self.device),
+            }
+        self._ctx["uniforms"].uniform_()
+        return self._ctx
+
+    # -- CUDA graphs: the ~60 small launches of one rollout step are captured once per step index and replayed,
+    #    which removes the host launch overhead that otherwise dominates a W=32 forward.
+    def _graph_key(self, mode):
+        return (mode, self._table.data_ptr(), self.model.flat_parameters().data_ptr())
+
+    def _step_via_graph(self, mode, t, obs_dev, step_dev, ep_dev, ctx):
+        if not self.use_cuda_graphs or self._forced_actions is not None:
+            return self._device_step(t, obs_dev, step_dev, ep_dev, ctx)
+        key = self._graph_key(mode)
+        if self._graphs.get("key") != key:                       # table or parameter arena moved: start over
+            self._graphs = {"key": key, "warm": 0, "steps": {}}
+        if self._graphs["warm"] < 1:                             # first rollout for this key runs eagerly (warm-up)
+            return self._device_step(t, obs_dev, step_dev, ep_dev, ctx)
+        g = self._graphs["steps"].get(t)
+        if g is None:
+            try:
+                if self._graph_pool is None:
+                    self._graph_pool = torch.cuda.graph_pool_handle()
+                    self._capture_stream = torch.cuda.Stream(device=self.device)
+                g = torch.cuda.CUDAGraph()
+                cs = self._capture_stream
+                cs.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(cs):
+                    g.capture_begin(pool=self._graph_pool)
+                    self._device_step(t, obs_dev, step_dev, ep_dev, ctx)
+                    g.capture_end()
+                torch.cuda.current_stream().wait_stream(cs)
+                self._graphs["steps"][t] = g
+            except Exception as e:  # noqa: BLE001 -- capture is an optimisation; the eager path is the same kernels
+                try:
+                    g.capture_end()                              # leave capture mode even if the capture is invalid
+                except Exception:  # noqa: BLE001
+                    pass
+                torch.cuda.synchronize()
+                print("[trxl] CUDA-graph capture failed (%s); continuing with eager launches" % e)
+                self.use_cuda_graphs = False
+                return self._device_step(t, obs_dev, step_dev, ep_dev, ctx)
+        g.replay()
+
+    def _graphs_finish_rollout(self, mode):
+        if self.use_cuda_graphs and self._graphs.get("key") == self._graph_key(mode):
+            self._graphs["warm"] += 1
 
     def _device_step(self, t, obs_dev, step_dev, ep_dev, ctx):
         """Everything the GPU does for rollout step t (trainer.py:161-186): store obs, write the mask /
@@ -250,12 +323,11 @@ class PPOTrainer:
         env_time = 0.0
         with torch.no_grad():
             for t in range(T):
-                # observations: host -> pinned -> device; cursors of every worker's live episode
-                self._obs_pinned.copy_(torch.from_numpy(self.obs))
-                self._obs_dev.copy_(self._obs_pinned, non_blocking=True)
+                # observations: host -> (pinned) -> device; cursors of every worker's live episode
+                self._upload_obs()
                 self._step_dev.copy_(self._step_host, non_blocking=True)
                 self._ep_dev.copy_(self._ep_host, non_blocking=True)
-                self._device_step(t, self._obs_dev, self._step_dev, self._ep_dev, ctx)
+                self._step_via_graph("workers", t, self._obs_dev, self._step_dev, self._ep_dev, ctx)
                 self._act_pinned.copy_(self._act_dev, non_blocking=True)
                 stream.synchronize()
                 actions = self._act_pinned.numpy()
@@ -275,8 +347,10 @@ class PPOTrainer:
                             self._n_episodes = self._n_rows
                     else:
                         self._step_host[w] += 1
-                    self.obs[w] = obs
+                    if obs is not None:                        # None: the worker already wrote it into the shared slab
+                        self.obs[w] = obs
                 env_time += time.perf_counter() - te
+        self._graphs_finish_rollout("workers")
         last_value = self.get_last_value()
         buf.calc_advantages(last_value, cfg["gamma"], cfg["lamda"])
         buf.memories = self._table[:self._n_episodes]
@@ -314,12 +388,14 @@ class PPOTrainer:
         self._n_rows = n_rows
         buf.rewards[:] = feed.rewards.T
         buf.dones[:] = feed.dones.T
-        step_dev = torch.from_numpy(step_sched).to(self.device)
-        ep_dev = torch.from_numpy(ep_sched).to(self.device)
         ctx = self._rollout_ctx()
+        step_dev, ep_dev = ctx["step_sched"], ctx["ep_sched"]
+        step_dev.copy_(torch.from_numpy(step_sched))
+        ep_dev.copy_(torch.from_numpy(ep_sched))
         with torch.no_grad():
             for t in range(T):
-                self._device_step(t, feed.obs(t), step_dev[t], ep_dev[t], ctx)
+                self._step_via_graph("feed", t, feed.obs(t), step_dev[t], ep_dev[t], ctx)
+        self._graphs_finish_rollout("feed")
         self._step_host.copy_(torch.from_numpy(step_sched[T]))
         self._ep_host.copy_(torch.from_numpy(ep_sched[T]))
         self._feed_last_obs = feed.obs(T)
@@ -343,8 +419,7 @@ class PPOTrainer:
             if self.device_feed is not None:
                 self._obs_dev.copy_(self._feed_last_obs)
             else:
-                self._obs_pinned.copy_(torch.from_numpy(self.obs))
-                self._obs_dev.copy_(self._obs_pinned, non_blocking=True)
+                self._upload_obs()
             feat = self.model.encode(self._obs_dev)
             pe_idx = self.buffer.memory_indices[:, -1].contiguous()
             _, value, _ = self.model.forward_table(feat, self._table, self._ep_dev, self._win_last, self._mask_last, pe_idx, n=W)
@@ -505,6 +580,12 @@ class PPOTrainer:
             except Exception:
                 pass
         time.sleep(0.2)
+        if getattr(self, "_obs_slab", None) is not None and getattr(self, "_slab_pinned", False):
+            try:
+                torch.cuda.cudart().cudaHostUnregister(self._obs_slab.data_ptr())
+            except Exception:
+                pass
+            self._slab_pinned = False
         for worker in self.workers:
             proc = getattr(worker, "process", None)
             if proc is not None:

@@ -1,6 +1,12 @@
 """One environment per OS process behind a pipe -- the reference's rollout transport (worker.py:6-62),
 kept in Python as BASELINE.json's north_star asks.  Protocol: ("reset", None) -> obs,
-("step", action) -> (obs, reward, done, info), ("close", None)."""
+("step", action) -> (obs, reward, done, info), ("close", None).
+
+Optional zero-copy observations: when a worker is given a slot of a shared-memory slab
+(``obs_slab[index]``, a torch tensor in shared memory that the trainer also registers as pinned host
+memory), it writes every observation there and sends ``None`` in the obs position of its reply.  The
+control protocol is unchanged; only the 85 KB-per-step image payload stops being pickled through
+the pipe, and the trainer DMAs the slab to the GPU directly."""
 import multiprocessing
 import multiprocessing.connection
 import sys
@@ -19,7 +25,7 @@ class WorkerException(Exception):
         raise self.ee
 
 
-def worker_process(remote, config):
+def worker_process(remote, config, obs_slab=None, index=0):
     import os
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     from utils import create_env
@@ -27,7 +33,22 @@ def worker_process(remote, config):
         env = create_env(config)
     except KeyboardInterrupt:
         return
-    handlers = {"step": lambda data: env.step(data), "reset": lambda data: env.reset()}
+    slot = None if obs_slab is None else obs_slab.numpy()[index]
+
+    def do_step(data):
+        obs, reward, done, info = env.step(data)
+        if slot is not None:
+            slot[...] = obs
+            obs = None
+        return obs, reward, done, info
+
+    def do_reset(data):
+        obs = env.reset()
+        if slot is not None:
+            slot[...] = obs
+            obs = None
+        return obs
+    handlers = {"step": do_step, "reset": do_reset}
     while True:
         try:
             cmd, data = remote.recv()
@@ -49,8 +70,8 @@ class Worker:
     child: multiprocessing.connection.Connection
     process: multiprocessing.Process
 
-    def __init__(self, env_config):
+    def __init__(self, env_config, obs_slab=None, index=0):
         ctx = multiprocessing.get_context("fork")
         self.child, parent = ctx.Pipe()
-        self.process = ctx.Process(target=worker_process, args=(parent, env_config), daemon=True)
+        self.process = ctx.Process(target=worker_process, args=(parent, env_config, obs_slab, index), daemon=True)
         self.process.start()

@@ -122,7 +122,7 @@ int trxl_linear_forward(const float* x, const float* W, const float* bias, float
 /* dx = dy W ; dW = dy^T x ; db = colsum(dy)   (any of dx/dW/db may be NULL); scratch >= 64*N+64 floats */
 int trxl_linear_backward(const float* dy, const float* x, const float* W, float* dx, float* dW, float* db, int M, int N, int K,
                          float* scratch, void* stream);
-/* nn.LayerNorm(D) forward, eps 1e-5; saves mean/rstd (rows,) */
+/* nn.LayerNorm(D) forward, eps 1e-5; saves mean/rstd (rows,).  backward scratch >= 128*D+64 floats */
 int trxl_layernorm_forward(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd, int rows,
                            int D, void* stream);
 int trxl_layernorm_backward(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, float* dx,

@@ -93,7 +93,7 @@ def test_layernorm_forward_backward(rows, d):
     dy = torch.randn(rows, d, device=DEV)
     want.backward(dy)
     dx, dg, db = torch.empty(rows, d, device=DEV), torch.empty(d, device=DEV), torch.empty(d, device=DEV)
-    scratch = torch.empty(64 * d + 64, device=DEV)
+    scratch = torch.empty(128 * d + 64, device=DEV)
     native.layernorm_backward(dy, x.detach(), mean, rstd, gamma.detach(), dx, dg, db, scratch)
     assert torch.allclose(dx, x.grad, atol=5e-5, rtol=1e-4)
     assert torch.allclose(dg, gamma.grad, atol=1e-4 * rows ** 0.5, rtol=1e-4)

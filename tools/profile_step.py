@@ -48,6 +48,8 @@ def main():
     ap.add_argument("--minibatches", type=int, default=2)
     ap.add_argument("--rollout-steps", type=int, default=2)
     args = ap.parse_args()
+    if args.kineto:
+        args.kineto = os.path.abspath(args.kineto)
     tr, cfg = build(args.workload)
     update(tr, cfg)                     # warm-up: allocations, cuDNN heuristics, first-touch
     torch.cuda.synchronize()
