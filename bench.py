@@ -102,8 +102,6 @@ def cpu_reference_sample(cfg, rollout_steps=8, threads=None, seed=0, mb_sample=5
     from oracle import ppo_oracle as O
     from oracle import trxl_oracle as X
     from environments.synthetic_env import SyntheticEnv
-    threads = threads or os.cpu_count()
-    torch.set_num_threads(threads)
     torch.manual_seed(seed)
     env_cfg = cfg["environment"]
     obs_shape, nact, M = tuple(env_cfg["obs_shape"]), env_cfg["n_actions"], env_cfg["max_episode_steps"]
@@ -112,6 +110,18 @@ def cpu_reference_sample(cfg, rollout_steps=8, threads=None, seed=0, mb_sample=5
     P = X.init_params(ocfg, obs_shape, seed=seed)
     envs = [SyntheticEnv(obs_shape, nact, M, env_cfg.get("min_episode_steps"), seed=seed + 1 + w) for w in range(W)]
     st = O.new_rollout_state(ocfg, obs_shape, envs)
+    if threads is None:
+        # torch's default (one thread per host core) can be far from the best choice for these op sizes;
+        # give the CPU arm its best case: probe a few pool sizes on two rollout steps and keep the fastest
+        cores = os.cpu_count() or 1
+        best = (float("inf"), cores)
+        for cand in sorted({c for c in (4, 8, 16, 32, 64, cores) if c <= cores}):
+            torch.set_num_threads(cand)
+            t0 = time.perf_counter()
+            O.sample_rollout(P, dict(ocfg, worker_steps=2), st, envs)
+            best = min(best, (time.perf_counter() - t0, cand))
+        threads = best[1]
+    torch.set_num_threads(threads)
     short = dict(ocfg, worker_steps=rollout_steps)
     t0 = time.perf_counter()
     O.sample_rollout(P, short, st, envs)
@@ -144,6 +154,7 @@ def cpu_reference_sample(cfg, rollout_steps=8, threads=None, seed=0, mb_sample=5
               "sample": "%d rollout steps (W=%d, in-process synthetic envs) + optimiser step on %d of the %d minibatch samples "
                         "(best of %d, scaled x%.0f) timed on %d threads; update = %d*rollout_step + %d*minibatch_step"
                         % (rollout_steps, W, mb_size, mb_full, reps, mb_full / mb_size, threads, T, n_opt)}
+    detail["threads"] = threads
     return W * T / update_s, detail
 
 
@@ -157,7 +168,7 @@ def run_reference(args, cfg, name):
         if i >= args.warmup:
             vals.append(v)
     value = float(np.mean(vals))
-    cores = os.cpu_count()
+    cores = detail["threads"]
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * cfg["n_workers"] * cfg["worker_steps"] / value,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -202,8 +213,9 @@ def run_b200(args, cfg, name):
             trainer._sample_training_data()
             trainer.buffer.prepare_batch_dict()
             trainer._train_epochs(lr, clip, beta)
-        for u in range(min(args.warmup, 1)):
+        for u in range(min(args.warmup, 2)):
             one_update(tr, u)
+        tr.timers = {"rollout": 0.0, "train": 0.0, "env": 0.0}
         dp.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
         n_e2e = max(1, min(args.steps, args.e2e_steps))
@@ -216,9 +228,8 @@ def run_b200(args, cfg, name):
         e2e = {"value": world * W * T * n_e2e / float(dt), "unit": UNIT,
                "h2d_bytes_per_step": T * (W * obs_bytes + 2 * W * 8), "d2h_bytes_per_step": T * W * 8 + 40 * 4 * 32,
                "updates_timed": n_e2e, "env_transport": "1 process per env, pipes (worker.py)",
-               "env_wait_s_per_update": tr.timers["env"] / (n_e2e + min(args.warmup, 1)),
-               "rollout_s_per_update": tr.timers["rollout"] / (n_e2e + min(args.warmup, 1)),
-               "train_s_per_update": tr.timers["train"] / (n_e2e + min(args.warmup, 1))}
+               "env_wait_s_per_update": tr.timers["env"] / n_e2e, "rollout_s_per_update": tr.timers["rollout"] / n_e2e,
+               "train_s_per_update": tr.timers["train"] / n_e2e}
         tr.close(exit_process=False)
         del tr
         torch.cuda.empty_cache()
@@ -289,7 +300,8 @@ def run_b200(args, cfg, name):
             "last_stats": [float(x) for x in np.mean(np.array(stats, dtype=np.float64), axis=0)]}
     if world == 1 and not args.no_cpu_baseline:
         v, detail = cpu_reference_sample(cfg, rollout_steps=8)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": detail["sample"],
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": detail["threads"], "host_cores": os.cpu_count(),
+                                "kind": "port", "sample": detail["sample"],
                                 "rollout_step_s": detail["rollout_step_s"], "minibatch_step_s": detail["minibatch_step_s"]}
     print(json.dumps(line))
 

@@ -27,7 +27,6 @@
 
 namespace {
 
-constexpr int NW = 4;                 // warps per CTA
 constexpr float LN_EPS = 1e-5f;
 
 struct RowMeta {                      // per-CTA shared staging of the sample's index rows
@@ -81,7 +80,7 @@ __device__ __forceinline__ bool stage_meta(const AttnArgs& a, long long row, Row
     return all_masked;
 }
 
-template <int NV4, int HPW, bool LN>
+template <int NV4, int HPW, bool LN, int NW>
 __global__ void __launch_bounds__(NW * 32)
 window_attn_fwd_kernel(const AttnArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -273,7 +272,7 @@ window_attn_fwd_kernel(const AttnArgs a) {
 // for a learned positional table, scatter-add d(PE).  The memory rows themselves carry no gradient
 // (reference transformer.py:248: memories are detached inputs).
 // ---------------------------------------------------------------------------------------------
-template <int NV4, int HPW, bool LN>
+template <int NV4, int HPW, bool LN, int NW>
 __global__ void __launch_bounds__(NW * 32)
 window_attn_bwd_kernel(const AttnArgs a, const AttnBwdArgs g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -472,38 +471,41 @@ window_attn_bwd_kernel(const AttnArgs a, const AttnBwdArgs g) {
     }
 }
 
-template <int NV4, int HPW>
-int launch_fwd(const AttnArgs& a, cudaStream_t st) {
+// Warps per sample: 4 when there are enough samples to fill the GPU (training minibatches), 8 for the
+// rollout's W-sample forwards, whose latency is the per-warp chain of window rows.
+template <int NV4, int HPW, bool LN, int NW>
+int launch_fwd_nw(const AttnArgs& a, cudaStream_t st) {
     dim3 grid(a.N, trxl_cdiv(a.H, HPW));
     const size_t smem = (size_t)a.L * 16 + (size_t)HPW * ((a.L + 3) & ~3) * 4 + (size_t)HPW * a.D * 4 + NW * HPW * 3 * 4 + a.L + 16;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(window_attn_fwd_kernel<NV4, HPW, LN, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     trxl_prof_begin(0, a.N, st);
-    if (a.ln) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(window_attn_fwd_kernel<NV4, HPW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        window_attn_fwd_kernel<NV4, HPW, true><<<grid, NW * 32, smem, st>>>(a);
-    } else {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(window_attn_fwd_kernel<NV4, HPW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        window_attn_fwd_kernel<NV4, HPW, false><<<grid, NW * 32, smem, st>>>(a);
-    }
+    window_attn_fwd_kernel<NV4, HPW, LN, NW><<<grid, NW * 32, smem, st>>>(a);
     trxl_prof_end(0, st);
     TRXL_CHECK_LAUNCH("window_attn_fwd");
     return TRXL_OK;
 }
-
 template <int NV4, int HPW>
-int launch_bwd(const AttnArgs& a, const AttnBwdArgs& g, cudaStream_t st) {
+int launch_fwd(const AttnArgs& a, cudaStream_t st) {
+    const bool wide = (long long)a.N * trxl_cdiv(a.H, HPW) < 148 * 2 && a.L >= 32;
+    if (a.ln) return wide ? launch_fwd_nw<NV4, HPW, true, 8>(a, st) : launch_fwd_nw<NV4, HPW, true, 4>(a, st);
+    return wide ? launch_fwd_nw<NV4, HPW, false, 8>(a, st) : launch_fwd_nw<NV4, HPW, false, 4>(a, st);
+}
+
+template <int NV4, int HPW, bool LN>
+int launch_bwd_ln(const AttnArgs& a, const AttnBwdArgs& g, cudaStream_t st) {
+    constexpr int NW = 4;
     dim3 grid(a.N, trxl_cdiv(a.H, HPW));
     const size_t smem = (size_t)a.L * 16 + (size_t)HPW * ((a.L + 3) & ~3) * 4 + (size_t)HPW * a.D * 4 + NW * HPW * 2 * 4 + a.L + 16;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(window_attn_bwd_kernel<NV4, HPW, LN, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     trxl_prof_begin(1, a.N, st);
-    if (a.ln) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(window_attn_bwd_kernel<NV4, HPW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        window_attn_bwd_kernel<NV4, HPW, true><<<grid, NW * 32, smem, st>>>(a, g);
-    } else {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(window_attn_bwd_kernel<NV4, HPW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        window_attn_bwd_kernel<NV4, HPW, false><<<grid, NW * 32, smem, st>>>(a, g);
-    }
+    window_attn_bwd_kernel<NV4, HPW, LN, NW><<<grid, NW * 32, smem, st>>>(a, g);
     trxl_prof_end(1, st);
     TRXL_CHECK_LAUNCH("window_attn_bwd");
     return TRXL_OK;
+}
+template <int NV4, int HPW>
+int launch_bwd(const AttnArgs& a, const AttnBwdArgs& g, cudaStream_t st) {
+    return a.ln ? launch_bwd_ln<NV4, HPW, true>(a, g, st) : launch_bwd_ln<NV4, HPW, false>(a, g, st);
 }
 
 // heads per warp pass: keep (qk + acc) register arrays <= ~64 float4-lanes

@@ -231,6 +231,10 @@ int launch_cfg(const GemmArgs& g, cudaStream_t st) {
 
 }  // namespace
 
+static thread_local float* tl_ws = nullptr;
+static thread_local long long tl_ws_floats = 0;
+void trxl_gemm_set_workspace(float* ws, long long floats) { tl_ws = ws; tl_ws_floats = floats; }
+
 int trxl_gemm(GemmArgs g, cudaStream_t st) {
     TRXL_CHECK_ARG(g.M >= 0 && g.N >= 0 && g.K >= 0 && g.batch >= 1, "gemm: bad dims M=%d N=%d K=%d batch=%d", g.M, g.N, g.K, g.batch);
     if (g.M == 0 || g.N == 0) return TRXL_OK;
@@ -240,14 +244,18 @@ int trxl_gemm(GemmArgs g, cudaStream_t st) {
     g.vecA = aligned(g.A, g.lda, g.sA);
     g.vecB = aligned(g.B, g.ldb, g.sB);
     if (g.alpha == 0.f) g.alpha = 1.f;
+    if (!g.ws && tl_ws) { g.ws = tl_ws; g.ws_floats = tl_ws_floats; }
     // tile choice: small problems get small tiles so more CTAs are in flight
     const long long tiles64 = (long long)trxl_cdiv(g.M, 64) * trxl_cdiv(g.N, 64) * g.batch;
-    // split-K: weight-gradient shapes (small M x N, long K = samples) would otherwise occupy a handful of SMs
+    const bool small = (g.M <= 32 || g.N <= 32 || tiles64 < 96);
+    const long long tiles = small ? (long long)trxl_cdiv(g.M, 32) * trxl_cdiv(g.N, 32) * g.batch : tiles64;
+    // split-K: shapes with few output tiles and a long reduction (weight gradients: K = samples; the
+    // rollout's lin_hidden: M = n_workers, K = 3136) would otherwise occupy a handful of SMs
     g.ksplit = 1;
     g.k_per_split = g.K;
-    if (g.ws && g.K >= 512 && tiles64 * 4 <= 148) {
-        int want = (int)((148 * 2 + tiles64 - 1) / tiles64);
-        int maxs = g.K / 128;
+    if (g.ws && g.K >= 512 && tiles * 2 <= 148) {
+        int want = (int)((148 * 2 + tiles - 1) / tiles);
+        int maxs = g.K / 64;
         int s = want < maxs ? want : maxs;
         if (s > 32) s = 32;
         while (s > 1 && (long long)s * g.batch * g.M * g.N > g.ws_floats) --s;
@@ -257,7 +265,7 @@ int trxl_gemm(GemmArgs g, cudaStream_t st) {
         }
     }
     int rc;
-    if (g.ksplit == 1 && (g.M <= 32 || g.N <= 32 || tiles64 < 96)) rc = launch_cfg<32, 32, 2, 2>(g, st);
+    if (small) rc = launch_cfg<32, 32, 2, 2>(g, st);
     else rc = launch_cfg<64, 64, 4, 4>(g, st);
     if (rc != TRXL_OK || g.ksplit == 1) return rc;
     const long long total = (long long)g.M * g.N * g.batch;

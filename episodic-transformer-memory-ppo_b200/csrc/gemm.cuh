@@ -17,6 +17,8 @@ struct GemmArgs {
 };
 
 int trxl_gemm(GemmArgs g, cudaStream_t st);
+// default split-K workspace for GEMMs issued by this host thread (set around a model forward/backward)
+void trxl_gemm_set_workspace(float* ws, long long floats);
 
 // convenience wrappers (row-major x (M,K), W (N,K))
 static inline int gemm_nt(cudaStream_t st, int M, int N, int K, const float* x, long long ldx, const float* W, long long ldw,

@@ -207,7 +207,7 @@ void carve(const trxl_model_config* c, int N, float* ws, Acts& A) {
     A.dhp = b.take(N * hid); A.dhv = b.take(N * hid);
     long long widest = 3 * D; if (hid > widest) widest = hid; if (sumA > widest) widest = sumA; if (c->feat_dim > widest) widest = c->feat_dim;
     A.ew = b.take(ew_scratch_floats(N, (int)widest));
-    A.gemm_ws_n = 32LL * D * (D > hid ? D : hid);
+    A.gemm_ws_n = 32LL * 74 * 4096;     // 32 splits x (at most 74 output tiles of 64x64): the largest split-K GEMM trxl_gemm picks
     A.gemm_ws = b.take(A.gemm_ws_n);
     A.total = b.cur;
 }
@@ -286,6 +286,7 @@ int model_forward(const trxl_model_config* c, const float* P, const ModelIO& io,
     TRXL_CHECK_ARG(c->pos_enc == TRXL_PE_NONE || io.pe_index, "model_forward: positional encoding needs pe_index");
     Acts A;
     carve(c, io.N, ws, A);
+    trxl_gemm_set_workspace(A.gemm_ws, A.gemm_ws_n);
     const int N = io.N, D = c->embed_dim, H = c->num_heads, B = c->num_blocks, dh = D / H, hid = c->hidden_size;
     const long long BD = (long long)B * D;
     const bool pre = c->layer_norm == TRXL_LN_PRE, post = c->layer_norm == TRXL_LN_POST;
@@ -360,6 +361,7 @@ int model_backward(const trxl_model_config* c, const float* P, float* G, const M
     TRXL_CHECK_ARG(P && G && io.feat && io.table && ws && out_mem && dlogits && dvalue, "model_backward: null pointer");
     Acts A;
     carve(c, io.N, ws, A);
+    trxl_gemm_set_workspace(A.gemm_ws, A.gemm_ws_n);
     const int N = io.N, D = c->embed_dim, H = c->num_heads, B = c->num_blocks, dh = D / H, hid = c->hidden_size;
     const long long BD = (long long)B * D, HD = (long long)H * D;
     const bool pre = c->layer_norm == TRXL_LN_PRE, post = c->layer_norm == TRXL_LN_POST;

@@ -32,6 +32,7 @@ def _require_fp32_convolutions():
     manager -- in TF32, so the switch is process-wide."""
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True      # let cuDNN time its fp32 algorithms once per conv shape
 
 
 class _TrunkFunction(torch.autograd.Function):
