@@ -1,0 +1,96 @@
+#!/usr/bin/env python
+"""Turn the raw artefacts a gpurun profiling call leaves in gpurun_out/ into the small text summaries
+committed under profiles/ (runs in the CPU container; needs `ncu` only for .ncu-rep inputs).
+
+    python tools/summarize_profiles.py --round r1
+"""
+import argparse
+import collections
+import csv
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+METRICS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__waves_per_multiprocessor", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+]
+
+
+def short_name(name):
+    name = name.replace("<unnamed>::", "").replace("(anonymous namespace)::", "")
+    m = re.match(r"(void )?([\w:]+)(<[^(]*>)?", name)
+    return (m.group(2) + (m.group(3) or "")) if m else name[:80]
+
+
+def launch_list(path, out):
+    with open(path) as f:
+        rows = list(csv.DictReader([ln for ln in f if not ln.startswith("==")]))
+    agg, total = collections.OrderedDict(), 0.0
+    for r in rows:
+        v = float(r["Metric Value"].replace(",", ""))
+        v = v / 1000.0 if r["Metric Unit"] == "ns" else (v * 1000.0 if r["Metric Unit"] == "ms" else v)
+        key = short_name(r["Kernel Name"])
+        if "sgemm_kernel" in key:
+            key += " grid=" + r["Grid Size"].replace(" ", "")
+        a = agg.setdefault(key, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+        total += v
+    with open(out, "w") as f:
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold cache, serialised: compare SHARES)\n")
+        f.write("# slice: 2 rollout steps (W=32) + 2 PPO minibatch steps (mb=2048) of the c3 workload; %d launches, %.1f us total\n"
+                % (len(rows), total))
+        f.write("%-86s %6s %11s %7s %9s\n" % ("kernel", "n", "total_us", "share", "avg_us"))
+        for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write("%-86s %6d %11.1f %6.1f%% %9.1f\n" % (k[:86], n, t, 100 * t / total, t / n))
+    print("wrote", out)
+
+
+def ncu_report(path, out, title):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {m: hdr.index(m) for m in METRICS if m in hdr}
+    kn = hdr.index("Kernel Name")
+    with open(out, "w") as f:
+        f.write("# %s\n# source: ncu --set full --clock-control none (values per launch)\n" % title)
+        for r in rows[2:]:
+            f.write("\n[%s]\n" % short_name(r[kn]))
+            for m, i in idx.items():
+                f.write("  %-66s %16s %s\n" % (m, r[i], units[i]))
+    print("wrote", out)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--round", default="r1")
+    ap.add_argument("--src", default=os.path.join(ROOT, "gpurun_out"))
+    args = ap.parse_args()
+    dst = os.path.join(ROOT, "profiles")
+    os.makedirs(dst, exist_ok=True)
+    p = os.path.join(args.src, "launches_c3.csv")
+    if os.path.exists(p):
+        launch_list(p, os.path.join(dst, "%s_launches_c3.txt" % args.round))
+    p = os.path.join(args.src, "kernels_c3.txt")
+    if os.path.exists(p):
+        with open(p) as fsrc, open(os.path.join(dst, "%s_kineto_update_c3.txt" % args.round), "w") as fdst:
+            fdst.write("# torch.profiler (CUPTI) over ONE full PPO update of the c3 workload, device feed; top rows by device time\n")
+            fdst.write(fsrc.read())
+        print("wrote kineto table")
+    for rep, title in (("attn_%s" % args.round, "fused window attention fwd/bwd, training minibatch (N=2048, L=128, D=256, H=4)"),
+                       ("sgemm_%s" % args.round, "SIMT sgemm launches: 1 rollout step (M=32) + 1 minibatch step (M=2048)")):
+        p = os.path.join(args.src, rep + ".ncu-rep")
+        if os.path.exists(p):
+            ncu_report(p, os.path.join(dst, "%s_ncu_%s.txt" % (args.round, rep.split("_")[0])), title)
+
+
+if __name__ == "__main__":
+    main()
