@@ -8,9 +8,9 @@
 // projections fold onto the query side exactly (up to fp32 re-association):
 //   energy[h,l] = sum_{d in head h} Q[d] (Wk[d,:] . x_l)          = qk[h,:] . x_l ,  qk[h,:] = Q_h Wk_h
 //   out[d]      = sum_l p[h(d),l] (Wv[d,:] . x_l) = Wv[d,:] . ctx[h(d),:],  ctx[h,:] = sum_l p[h,l] x_l
-// so the only per-(sample, window-slot) work left is streaming the raw fp32 memory row once:
-// H dot products + H axpys per row.  qk (N,H,D) comes from two small GEMMs before this kernel and
-// ctx (N,H,D) feeds one small GEMM after it.  The pre-LayerNorm case streams the same raw rows and
+// so the only per-(sample, window-slot) work left is streaming the raw fp32 memory row: H dot
+// products + H axpys per row.  qk (N,H,D) comes from two small GEMMs before this kernel and ctx
+// (N,H,D) feeds one small GEMM after it.  The pre-LayerNorm case streams the same raw rows and
 // normalises on the fly (row mean/rstd from the same pass; gamma/beta are folded into Wk/Wv by the
 // caller): energy = rstd*(qkg.x - mu*sum(qkg)) + qkb,  ctx_hat = sum_l p*rstd*(x - mu).
 //
@@ -22,18 +22,20 @@
 // (exp(-6e18 - max) == 0), so its row is never read.  A fully-masked sample (episode step 0) is the
 // exception: the reference yields a uniform distribution over all L slots, and so does this kernel.
 //
+// Structure (r1 ncu: the single-pass online-softmax version was instruction-issue bound -- ~355
+// instructions per row, DRAM 3 %, L2 9 % of peak -- so instructions are traded for L2 reads):
+//   pass 1  each warp streams its rows, H dot products per row, one packed multi-value butterfly
+//           (the H partial sums share shuffles), energies -> shared memory
+//   softmax one warp per head over the L energies in shared memory (each exp evaluated once)
+//   pass 2  rows are streamed again (L2 hits) and accumulated with the final weights: no running-max
+//           bookkeeping, no per-lane repetition of the softmax scalars
 // Algorithmic bytes per (sample, block): 4*L*D (the fp32 window) -> HBM/L2-bandwidth bound.
 #include "attention.cuh"
 
 namespace {
 
 constexpr float LN_EPS = 1e-5f;
-
-struct RowMeta {                      // per-CTA shared staging of the sample's index rows
-    long long* win;                   // [L] slot in episode
-    long long* pe;                    // [L] PE row
-    unsigned char* vis;               // [L] 1 = read this row
-};
+constexpr unsigned FULL = 0xffffffffu;
 
 template <int NV4>
 __device__ __forceinline__ void load_row(const float* __restrict__ src, const float* __restrict__ pe_row, int D,
@@ -57,41 +59,93 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
     return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
 }
 
+// Packed warp reduction of NV (power of two <= 8) independent sums.  Each halving stage exchanges
+// half of the remaining values, so NV values cost NV-1 + (5 - log2 NV) shuffles instead of 5*NV.
+// On return v[0] holds the warp-wide total of value `packed_index<NV>(lane)`; every lane with the same
+// index holds the same bits.
+template <int NV>
+__device__ __forceinline__ void packed_reduce(float (&v)[NV], int lane) {
+    int off = 16;
+#pragma unroll
+    for (int half = NV / 2; half >= 1; half /= 2) {
+        const bool hi = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float keep = hi ? v[i + half] : v[i];
+            const float send = hi ? v[i] : v[i + half];
+            v[i] = keep + __shfl_xor_sync(FULL, send, off);
+        }
+        off >>= 1;
+    }
+    for (; off >= 1; off >>= 1) v[0] += __shfl_xor_sync(FULL, v[0], off);
+}
+template <int NV>
+__device__ __forceinline__ int packed_index(int lane) {
+    int idx = 0, off = 16;
+#pragma unroll
+    for (int half = NV / 2; half >= 1; half /= 2) {
+        if (lane & off) idx += half;
+        off >>= 1;
+    }
+    return idx;
+}
+// first lane holding value `idx` after packed_reduce<NV>
+template <int NV>
+__device__ __forceinline__ int packed_holder(int idx) {
+    int lane = 0, off = 16;
+#pragma unroll
+    for (int half = NV / 2; half >= 1; half /= 2) {
+        if (idx & half) lane |= off;
+        off >>= 1;
+    }
+    return lane;
+}
+__host__ __device__ constexpr int pow2_at_least(int n) { return n <= 1 ? 1 : (n <= 2 ? 2 : (n <= 4 ? 4 : 8)); }
+
 // stage the sample's mask / window / PE index rows in shared memory; returns all_masked
-__device__ __forceinline__ bool stage_meta(const AttnArgs& a, long long row, RowMeta& sm, int* s_flag) {
+__device__ __forceinline__ bool stage_meta(const AttnArgs& a, long long row, long long* s_win, long long* s_pe,
+                                           unsigned char* s_vis, int* s_flag) {
     const int tid = threadIdx.x;
     if (tid == 0) *s_flag = 0;
     __syncthreads();
     int any = 0;
     for (int l = tid; l < a.L; l += blockDim.x) {
         const unsigned char m = a.mask ? a.mask[row * a.L + l] : 1;
-        sm.vis[l] = m;
+        s_vis[l] = m;
         any |= m;
-        sm.win[l] = a.win_index ? a.win_index[row * a.L + l] : (long long)l;
-        sm.pe[l] = a.pe_index ? a.pe_index[row * a.L + l] : 0;
+        s_win[l] = a.win_index ? a.win_index[row * a.L + l] : (long long)l;
+        s_pe[l] = a.pe_index ? a.pe_index[row * a.L + l] : 0;
     }
     if (any) *s_flag = 1;
     __syncthreads();
     const bool all_masked = (*s_flag == 0);
     if (all_masked) {
-        for (int l = tid; l < a.L; l += blockDim.x) sm.vis[l] = 1;     // uniform softmax over every slot
+        for (int l = tid; l < a.L; l += blockDim.x) s_vis[l] = 1;     // uniform softmax over every slot
         __syncthreads();
     }
     return all_masked;
+}
+
+// shared-memory carve shared by forward and backward:
+//   win[L] i64 | pe[L] i64 | p[HPW][Lp] f32 | acc[HPW][D] f32 | rowstat[2][Lp] f32 | misc[NW*HPW*2 + 4*HPW] f32 | vis[L] u8
+__host__ __device__ inline size_t attn_smem_bytes(int L, int D, int HPW, int NW) {
+    const int Lp = (L + 3) & ~3;
+    return (size_t)L * 16 + (size_t)HPW * Lp * 4 + (size_t)HPW * D * 4 + (size_t)2 * Lp * 4 + (size_t)(NW * HPW * 2 + 4 * HPW) * 4 + L + 16;
 }
 
 template <int NV4, int HPW, bool LN, int NW>
 __global__ void __launch_bounds__(NW * 32)
 window_attn_fwd_kernel(const AttnArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: win[L] i64 | pe[L] i64 | energies[HPW][L] f32 | ctx[HPW][D] f32 | stats[NW][HPW][3] | vis[L] u8
+    const int Lp = (a.L + 3) & ~3;
     long long* s_win = reinterpret_cast<long long*>(smem_raw);
     long long* s_pe = s_win + a.L;
-    const int Lp = (a.L + 3) & ~3;                              // keeps the float4 regions 16-byte aligned
-    float* s_e = reinterpret_cast<float*>(s_pe + a.L);
-    float* s_ctx = s_e + HPW * Lp;
-    float* s_stat = s_ctx + HPW * a.D;
-    unsigned char* s_vis = reinterpret_cast<unsigned char*>(s_stat + NW * HPW * 3);
+    float* s_p = reinterpret_cast<float*>(s_pe + a.L);           // energies, then softmax weights [HPW][Lp]
+    float* s_ctx = s_p + HPW * Lp;                               // [HPW][D]
+    float* s_mu = s_ctx + HPW * a.D;                             // [Lp]   (LN)
+    float* s_rstd = s_mu + Lp;                                   // [Lp]   (LN)
+    float* s_misc = s_rstd + Lp;                                 // [NW][HPW] c-sums | [HPW] inv_sum
+    unsigned char* s_vis = reinterpret_cast<unsigned char*>(s_misc + NW * HPW * 2 + 4 * HPW);
     __shared__ int s_flag;
 
     const int n = blockIdx.x;
@@ -99,8 +153,8 @@ window_attn_fwd_kernel(const AttnArgs a) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const long long row = a.sample_index ? a.sample_index[n] : n;
     const long long ep = a.ep_index ? a.ep_index[row] : row;
-    RowMeta sm{s_win, s_pe, s_vis};
-    const bool all_masked = stage_meta(a, row, sm, &s_flag);
+    const bool all_masked = stage_meta(a, row, s_win, s_pe, s_vis, &s_flag);
+    for (int i = threadIdx.x; i < HPW * a.D; i += blockDim.x) s_ctx[i] = 0.f;
 
     // folded query vectors for this head group
     float4 qk[HPW][NV4];
@@ -116,24 +170,23 @@ window_attn_fwd_kernel(const AttnArgs a) {
             qk[h][c] = (hv && col < a.D) ? *reinterpret_cast<const float4*>(qp + col) : make_float4(0.f, 0.f, 0.f, 0.f);
             s += qk[h][c].x + qk[h][c].y + qk[h][c].z + qk[h][c].w;
         }
-        sg[h] = LN ? warp_sum(s) : 0.f;
-        qb[h] = (LN && a.qkb && hv) ? a.qkb[(long long)n * a.H + h0 + h] : 0.f;
-    }
-
-    float m_run[HPW], s_run[HPW], c_run[HPW];
-    float4 acc[HPW][NV4];
+        sg[h] = 0.f; qb[h] = 0.f;
+        if (LN) {
 #pragma unroll
-    for (int h = 0; h < HPW; ++h) {
-        m_run[h] = -INFINITY; s_run[h] = 0.f; c_run[h] = 0.f;
-#pragma unroll
-        for (int c = 0; c < NV4; ++c) acc[h][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+            sg[h] = s;
+            qb[h] = (a.qkb && hv) ? a.qkb[(long long)n * a.H + h0 + h] : 0.f;
+        }
     }
 
     const float* tab = a.table + ((ep * a.slots) * a.B + a.blk) * (long long)a.D;
     const long long slot_stride = (long long)a.B * a.D;
     const float invD = 1.f / (float)a.D;
+    constexpr int NRED = pow2_at_least(HPW + (LN ? 2 : 0));
+    const int my_idx = packed_index<NRED>(lane);
+    const bool writer = (lane == packed_holder<NRED>(my_idx)) && (my_idx < HPW);
 
-    // two rows in flight per warp
+    // ---------------- pass 1: energies ----------------
     for (int l = w; l < a.L; l += 2 * NW) {
         const int l1 = l + NW;
         const bool v0 = s_vis[l] != 0;
@@ -147,7 +200,9 @@ window_attn_fwd_kernel(const AttnArgs a) {
             const int ll = r ? l1 : l;
             if (!vis) continue;                       // warp-uniform
             float4 (&x)[NV4] = r ? x1 : x0;
-            float red[HPW + 2];
+            float red[NRED];
+#pragma unroll
+            for (int i = 0; i < NRED; ++i) red[i] = 0.f;
 #pragma unroll
             for (int h = 0; h < HPW; ++h) {
                 float d = 0.f;
@@ -155,47 +210,88 @@ window_attn_fwd_kernel(const AttnArgs a) {
                 for (int c = 0; c < NV4; ++c) d += dot4(qk[h][c], x[c]);
                 red[h] = d;
             }
-            float s1 = 0.f, s2 = 0.f;
             if (LN) {
+                float s1 = 0.f, s2 = 0.f;
 #pragma unroll
                 for (int c = 0; c < NV4; ++c) {
                     s1 += x[c].x + x[c].y + x[c].z + x[c].w;
                     s2 += dot4(x[c], x[c]);
                 }
+                red[HPW] = s1; red[HPW + 1] = s2;
             }
-            red[HPW] = s1; red[HPW + 1] = s2;
-            if (LN) warp_sum_multi<HPW + 2>(red);
-            else {
-                float (&rh)[HPW] = *reinterpret_cast<float(*)[HPW]>(&red[0]);
-                warp_sum_multi<HPW>(rh);
-            }
-            float mu = 0.f, rstd = 1.f;
+            packed_reduce<NRED>(red, lane);
+            float e = red[0];
             if (LN) {
-                mu = red[HPW] * invD;
-                const float var = fmaxf(red[HPW + 1] * invD - mu * mu, 0.f);
-                rstd = rsqrtf(var + LN_EPS);
+                const float t1 = __shfl_sync(FULL, red[0], packed_holder<NRED>(HPW));
+                const float t2 = __shfl_sync(FULL, red[0], packed_holder<NRED>(HPW + 1));
+                const float mu = t1 * invD;
+                const float rstd = rsqrtf(fmaxf(t2 * invD - mu * mu, 0.f) + LN_EPS);
+                if (lane == 0) { s_mu[ll] = mu; s_rstd[ll] = rstd; }
+                // sg/qb of this lane's head: select without dynamic register indexing
+                float sgh = 0.f, qbh = 0.f;
+#pragma unroll
+                for (int h = 0; h < HPW; ++h) if (my_idx == h) { sgh = sg[h]; qbh = qb[h]; }
+                e = fmaf(rstd, e - mu * sgh, qbh);
             }
+            if (writer) s_p[my_idx * Lp + ll] = all_masked ? 0.f : __fdiv_rn(e, a.scale);
+        }
+    }
+    __syncthreads();
+
+    // ---------------- softmax: warp h handles head h (NW >= HPW) ----------------
+    if (w < HPW) {
+        float* e = s_p + w * Lp;
+        float m = -INFINITY;
+        for (int l = lane; l < a.L; l += 32) if (s_vis[l]) m = fmaxf(m, e[l]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+        float s = 0.f;
+        for (int l = lane; l < a.L; l += 32) {
+            const float p = s_vis[l] ? __expf(e[l] - m) : 0.f;
+            e[l] = p;
+            s += p;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+        const float inv = 1.f / s;
+        const bool hv = (h0 + w) < a.H;
+        float* pp = a.probs + ((long long)n * a.H + (hv ? h0 + w : 0)) * a.L;
+        for (int l = lane; l < a.L; l += 32) {
+            const float p = e[l] * inv;
+            e[l] = p;
+            if (hv) pp[l] = p;
+        }
+    }
+    __syncthreads();
+
+    // ---------------- pass 2: ctx[h,:] = sum_l p[h,l] * x_l (rows come back from L2) ----------------
+    float4 acc[HPW][NV4];
+    float csum[HPW];
+#pragma unroll
+    for (int h = 0; h < HPW; ++h) {
+        csum[h] = 0.f;
+#pragma unroll
+        for (int c = 0; c < NV4; ++c) acc[h][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int l = w; l < a.L; l += 2 * NW) {
+        const int l1 = l + NW;
+        const bool v0 = s_vis[l] != 0;
+        const bool v1 = (l1 < a.L) && (s_vis[l1] != 0);
+        float4 x0[NV4], x1[NV4];
+        if (v0) load_row<NV4>(tab + s_win[l] * slot_stride, a.pe ? a.pe + s_pe[l] * a.D : nullptr, a.D, lane, x0);
+        if (v1) load_row<NV4>(tab + s_win[l1] * slot_stride, a.pe ? a.pe + s_pe[l1] * a.D : nullptr, a.D, lane, x1);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const bool vis = r ? v1 : v0;
+            const int ll = r ? l1 : l;
+            if (!vis) continue;
+            float4 (&x)[NV4] = r ? x1 : x0;
+            const float rstd = LN ? s_rstd[ll] : 1.f;
+            const float mu = LN ? s_mu[ll] : 0.f;
 #pragma unroll
             for (int h = 0; h < HPW; ++h) {
-                float e = LN ? fmaf(rstd, red[h] - mu * sg[h], qb[h]) : red[h];
-                e = all_masked ? 0.f : __fdiv_rn(e, a.scale);
-                if (lane == 0) s_e[h * Lp + ll] = e;
-                // online softmax with a lazy rescale: the running max rises O(log L) times per sample, so the
-                // accumulator is only rescaled on those rows (e is identical on all lanes -> warp-uniform branch)
-                if (e > m_run[h]) {
-                    const float corr = __expf(m_run[h] - e);          // exp(-inf) = 0 on the first row
-                    s_run[h] *= corr;
-                    if (LN) c_run[h] *= corr;
-#pragma unroll
-                    for (int c = 0; c < NV4; ++c) {
-                        acc[h][c].x *= corr; acc[h][c].y *= corr; acc[h][c].z *= corr; acc[h][c].w *= corr;
-                    }
-                    m_run[h] = e;
-                }
-                const float pe_ = __expf(e - m_run[h]);
-                s_run[h] += pe_;
-                const float wgt = pe_ * rstd;
-                if (LN) c_run[h] = fmaf(wgt, mu, c_run[h]);
+                const float wgt = s_p[h * Lp + ll] * rstd;
+                if (LN) csum[h] = fmaf(wgt, mu, csum[h]);
 #pragma unroll
                 for (int c = 0; c < NV4; ++c) {
                     acc[h][c].x = fmaf(wgt, x[c].x, acc[h][c].x);
@@ -206,36 +302,11 @@ window_attn_fwd_kernel(const AttnArgs a) {
             }
         }
     }
-
-    // ---- merge the NW per-warp online-softmax states ----
-    if (lane == 0) {
+    if (LN && lane == 0) {
 #pragma unroll
-        for (int h = 0; h < HPW; ++h) {
-            s_stat[(w * HPW + h) * 3 + 0] = m_run[h];
-            s_stat[(w * HPW + h) * 3 + 1] = s_run[h];
-            s_stat[(w * HPW + h) * 3 + 2] = c_run[h];
-        }
+        for (int h = 0; h < HPW; ++h) s_misc[w * HPW + h] = csum[h];
     }
-    for (int i = threadIdx.x; i < HPW * a.D; i += blockDim.x) s_ctx[i] = 0.f;
-    __syncthreads();
-    float m_all[HPW], s_all[HPW], c_all[HPW], my_scale[HPW];
-#pragma unroll
-    for (int h = 0; h < HPW; ++h) {
-        float mm = -INFINITY;
-#pragma unroll
-        for (int ww = 0; ww < NW; ++ww) mm = fmaxf(mm, s_stat[(ww * HPW + h) * 3]);
-        float ss = 0.f, cc = 0.f;
-#pragma unroll
-        for (int ww = 0; ww < NW; ++ww) {
-            const float mw = s_stat[(ww * HPW + h) * 3];
-            const float f = (mw == -INFINITY) ? 0.f : __expf(mw - mm);
-            ss += s_stat[(ww * HPW + h) * 3 + 1] * f;
-            cc += s_stat[(ww * HPW + h) * 3 + 2] * f;
-        }
-        m_all[h] = mm; s_all[h] = ss; c_all[h] = cc;
-        my_scale[h] = (m_run[h] == -INFINITY) ? 0.f : __expf(m_run[h] - mm);
-    }
-    // deterministic merge: warps add their scaled accumulators in warp order
+    // deterministic merge: warps add their accumulators in warp order
     for (int ww = 0; ww < NW; ++ww) {
         if (w == ww) {
 #pragma unroll
@@ -246,43 +317,43 @@ window_attn_fwd_kernel(const AttnArgs a) {
                     if (col < a.D) {
                         float4* p = reinterpret_cast<float4*>(s_ctx + h * a.D + col);
                         float4 t = *p;
-                        t.x = fmaf(acc[h][c].x, my_scale[h], t.x); t.y = fmaf(acc[h][c].y, my_scale[h], t.y);
-                        t.z = fmaf(acc[h][c].z, my_scale[h], t.z); t.w = fmaf(acc[h][c].w, my_scale[h], t.w);
+                        t.x += acc[h][c].x; t.y += acc[h][c].y; t.z += acc[h][c].z; t.w += acc[h][c].w;
                         *p = t;
                     }
                 }
         }
         __syncthreads();
     }
-    // ---- write ctx (N,H,D) and probs (N,H,L) ----
 #pragma unroll
     for (int h = 0; h < HPW; ++h) {
         if (h0 + h >= a.H) continue;
-        const float inv = 1.f / s_all[h];
+        float c_all = 0.f;
+        if (LN) {
+#pragma unroll
+            for (int ww = 0; ww < NW; ++ww) c_all += s_misc[ww * HPW + h];
+        }
         float* cp = a.ctx + ((long long)n * a.H + h0 + h) * a.D;
-        for (int j = threadIdx.x; j < a.D; j += blockDim.x) cp[j] = (s_ctx[h * a.D + j] - c_all[h]) * inv;
-        float* pp = a.probs + ((long long)n * a.H + h0 + h) * a.L;
-        for (int l = threadIdx.x; l < a.L; l += blockDim.x)
-            pp[l] = s_vis[l] ? __expf(s_e[h * Lp + l] - m_all[h]) * inv : 0.f;
+        for (int j = threadIdx.x; j < a.D; j += blockDim.x) cp[j] = s_ctx[h * a.D + j] - c_all;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // backward: given d(ctx) (N,H,D) and the saved probs/ctx, produce d(qk) (N,H,D), d(qkb) (N,H) and,
 // for a learned positional table, scatter-add d(PE).  The memory rows themselves carry no gradient
-// (reference transformer.py:248: memories are detached inputs).
+// (reference transformer.py:248: memories are detached inputs).  Single pass: the weights are known.
 // ---------------------------------------------------------------------------------------------
 template <int NV4, int HPW, bool LN, int NW>
 __global__ void __launch_bounds__(NW * 32)
 window_attn_bwd_kernel(const AttnArgs a, const AttnBwdArgs g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int Lp = (a.L + 3) & ~3;
     long long* s_win = reinterpret_cast<long long*>(smem_raw);
     long long* s_pe = s_win + a.L;
-    const int Lp = (a.L + 3) & ~3;
     float* s_p = reinterpret_cast<float*>(s_pe + a.L);          // probs [HPW][Lp]
     float* s_acc = s_p + HPW * Lp;                              // [HPW][D]
-    float* s_stat = s_acc + HPW * a.D;                          // [NW][HPW][2]
-    unsigned char* s_vis = reinterpret_cast<unsigned char*>(s_stat + NW * HPW * 2);
+    float* s_unused = s_acc + HPW * a.D;                        // rowstat region (unused here)
+    float* s_stat = s_unused + 2 * Lp;                          // [NW][HPW][2]
+    unsigned char* s_vis = reinterpret_cast<unsigned char*>(s_stat + NW * HPW * 2 + 4 * HPW);
     __shared__ int s_flag;
 
     const int n = blockIdx.x;
@@ -290,8 +361,7 @@ window_attn_bwd_kernel(const AttnArgs a, const AttnBwdArgs g) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const long long row = a.sample_index ? a.sample_index[n] : n;
     const long long ep = a.ep_index ? a.ep_index[row] : row;
-    RowMeta sm{s_win, s_pe, s_vis};
-    const bool all_masked = stage_meta(a, row, sm, &s_flag);
+    const bool all_masked = stage_meta(a, row, s_win, s_pe, s_vis, &s_flag);
     const bool need_dx = g.dpe != nullptr;
 
     for (int i = threadIdx.x; i < HPW * a.L; i += blockDim.x) {
@@ -319,8 +389,13 @@ window_attn_bwd_kernel(const AttnArgs a, const AttnBwdArgs g) {
             }
             s += dc[h][c].x + dc[h][c].y + dc[h][c].z + dc[h][c].w;
         }
-        dot0[h] = warp_sum(d);
-        sdc[h] = LN ? warp_sum(s) : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            d += __shfl_xor_sync(FULL, d, o);
+            s += __shfl_xor_sync(FULL, s, o);
+        }
+        dot0[h] = d;
+        sdc[h] = LN ? s : 0.f;
     }
     __syncthreads();
 
@@ -335,97 +410,113 @@ window_attn_bwd_kernel(const AttnArgs a, const AttnBwdArgs g) {
     const float* tab = a.table + ((ep * a.slots) * a.B + a.blk) * (long long)a.D;
     const long long slot_stride = (long long)a.B * a.D;
     const float invD = 1.f / (float)a.D;
+    const float inv_scale = 1.f / a.scale;
     const bool skip_all = all_masked && !need_dx;      // constant energies: no gradient reaches qk
+    constexpr int NRED = pow2_at_least(HPW + (LN ? 2 : 0));
 
     if (!skip_all) {
-        for (int l = w; l < a.L; l += NW) {
-            if (!s_vis[l]) continue;
-            float4 x[NV4];
-            load_row<NV4>(tab + s_win[l] * slot_stride, a.pe ? a.pe + s_pe[l] * a.D : nullptr, a.D, lane, x);
-            float red[HPW + 2];
+        for (int l = w; l < a.L; l += 2 * NW) {
+            const int l1 = l + NW;
+            const bool v0 = s_vis[l] != 0;
+            const bool v1 = (l1 < a.L) && (s_vis[l1] != 0);
+            float4 x0[NV4], x1[NV4];
+            if (v0) load_row<NV4>(tab + s_win[l] * slot_stride, a.pe ? a.pe + s_pe[l] * a.D : nullptr, a.D, lane, x0);
+            if (v1) load_row<NV4>(tab + s_win[l1] * slot_stride, a.pe ? a.pe + s_pe[l1] * a.D : nullptr, a.D, lane, x1);
 #pragma unroll
-            for (int h = 0; h < HPW; ++h) {
-                float d = 0.f;
+            for (int r = 0; r < 2; ++r) {
+                const bool vis = r ? v1 : v0;
+                const int ll = r ? l1 : l;
+                if (!vis) continue;
+                float4 (&x)[NV4] = r ? x1 : x0;
+                float red[NRED];
 #pragma unroll
-                for (int c = 0; c < NV4; ++c) d += dot4(dc[h][c], x[c]);
-                red[h] = d;
-            }
-            float s1 = 0.f, s2 = 0.f;
-            if (LN) {
+                for (int i = 0; i < NRED; ++i) red[i] = 0.f;
 #pragma unroll
-                for (int c = 0; c < NV4; ++c) {
-                    s1 += x[c].x + x[c].y + x[c].z + x[c].w;
-                    s2 += dot4(x[c], x[c]);
-                }
-            }
-            red[HPW] = s1; red[HPW + 1] = s2;
-            if (LN) warp_sum_multi<HPW + 2>(red);
-            else {
-                float (&rh)[HPW] = *reinterpret_cast<float(*)[HPW]>(&red[0]);
-                warp_sum_multi<HPW>(rh);
-            }
-            float mu = 0.f, rstd = 1.f;
-            if (LN) {
-                mu = red[HPW] * invD;
-                const float var = fmaxf(red[HPW + 1] * invD - mu * mu, 0.f);
-                rstd = rsqrtf(var + LN_EPS);
-            }
-            float dE[HPW];
+                for (int h = 0; h < HPW; ++h) {
+                    float d = 0.f;
 #pragma unroll
-            for (int h = 0; h < HPW; ++h) {
-                const float gdot = LN ? rstd * (red[h] - mu * sdc[h]) : red[h];      // dctx . x_hat
-                dE[h] = all_masked ? 0.f : __fdiv_rn(s_p[h * Lp + l] * (gdot - dot0[h]), a.scale);
-                const float wgt = dE[h] * rstd;
-                accb[h] += dE[h];
-                if (LN) accmu[h] = fmaf(wgt, mu, accmu[h]);
-#pragma unroll
-                for (int c = 0; c < NV4; ++c) {
-                    acc[h][c].x = fmaf(wgt, x[c].x, acc[h][c].x); acc[h][c].y = fmaf(wgt, x[c].y, acc[h][c].y);
-                    acc[h][c].z = fmaf(wgt, x[c].z, acc[h][c].z); acc[h][c].w = fmaf(wgt, x[c].w, acc[h][c].w);
-                }
-            }
-            if (need_dx) {
-                // d(x_hat) = sum_h dE[h] qk[h] + p[h,l] dctx[h]; then LayerNorm backward (no affine) if LN
-                float4 dxh[NV4];
-                float t1 = 0.f, t2 = 0.f;
-#pragma unroll
-                for (int c = 0; c < NV4; ++c) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                    for (int h = 0; h < HPW; ++h) {
-                        const float p = s_p[h * Lp + l];
-                        v.x += dE[h] * qk[h][c].x + p * dc[h][c].x; v.y += dE[h] * qk[h][c].y + p * dc[h][c].y;
-                        v.z += dE[h] * qk[h][c].z + p * dc[h][c].z; v.w += dE[h] * qk[h][c].w + p * dc[h][c].w;
-                    }
-                    dxh[c] = v;
-                    if (LN) {
-                        const int col = c * 128 + lane * 4;
-                        if (col < a.D) {
-                            const float4 xh = make_float4((x[c].x - mu) * rstd, (x[c].y - mu) * rstd,
-                                                          (x[c].z - mu) * rstd, (x[c].w - mu) * rstd);
-                            t1 += v.x + v.y + v.z + v.w;
-                            t2 += dot4(v, xh);
-                        }
-                    }
+                    for (int c = 0; c < NV4; ++c) d += dot4(dc[h][c], x[c]);
+                    red[h] = d;
                 }
                 if (LN) {
-                    t1 = warp_sum(t1) * invD;
-                    t2 = warp_sum(t2) * invD;
-                }
-                float* dst = g.dpe + s_pe[l] * a.D;
+                    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                for (int c = 0; c < NV4; ++c) {
-                    const int col = c * 128 + lane * 4;
-                    if (col < a.D) {
-                        float4 v = dxh[c];
-                        if (LN) {
-                            v.x = rstd * (v.x - t1 - (x[c].x - mu) * rstd * t2);
-                            v.y = rstd * (v.y - t1 - (x[c].y - mu) * rstd * t2);
-                            v.z = rstd * (v.z - t1 - (x[c].z - mu) * rstd * t2);
-                            v.w = rstd * (v.w - t1 - (x[c].w - mu) * rstd * t2);
+                    for (int c = 0; c < NV4; ++c) {
+                        s1 += x[c].x + x[c].y + x[c].z + x[c].w;
+                        s2 += dot4(x[c], x[c]);
+                    }
+                    red[HPW] = s1; red[HPW + 1] = s2;
+                }
+                packed_reduce<NRED>(red, lane);
+                float mu = 0.f, rstd = 1.f;
+                if (LN) {
+                    const float t1 = __shfl_sync(FULL, red[0], packed_holder<NRED>(HPW));
+                    const float t2 = __shfl_sync(FULL, red[0], packed_holder<NRED>(HPW + 1));
+                    mu = t1 * invD;
+                    rstd = rsqrtf(fmaxf(t2 * invD - mu * mu, 0.f) + LN_EPS);
+                }
+                float dE[HPW];
+#pragma unroll
+                for (int h = 0; h < HPW; ++h) {
+                    const float dot = __shfl_sync(FULL, red[0], packed_holder<NRED>(h));      // dctx[h] . x_l (raw)
+                    const float gdot = LN ? rstd * (dot - mu * sdc[h]) : dot;                 // dctx[h] . x_hat
+                    dE[h] = all_masked ? 0.f : s_p[h * Lp + ll] * (gdot - dot0[h]) * inv_scale;
+                    const float wgt = dE[h] * rstd;
+                    accb[h] += dE[h];
+                    if (LN) accmu[h] = fmaf(wgt, mu, accmu[h]);
+#pragma unroll
+                    for (int c = 0; c < NV4; ++c) {
+                        acc[h][c].x = fmaf(wgt, x[c].x, acc[h][c].x); acc[h][c].y = fmaf(wgt, x[c].y, acc[h][c].y);
+                        acc[h][c].z = fmaf(wgt, x[c].z, acc[h][c].z); acc[h][c].w = fmaf(wgt, x[c].w, acc[h][c].w);
+                    }
+                }
+                if (need_dx) {
+                    // d(x_hat) = sum_h dE[h] qk[h] + p[h,l] dctx[h]; then LayerNorm backward (no affine) if LN
+                    float4 dxh[NV4];
+                    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+                    for (int c = 0; c < NV4; ++c) {
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int h = 0; h < HPW; ++h) {
+                            const float p = s_p[h * Lp + ll];
+                            v.x += dE[h] * qk[h][c].x + p * dc[h][c].x; v.y += dE[h] * qk[h][c].y + p * dc[h][c].y;
+                            v.z += dE[h] * qk[h][c].z + p * dc[h][c].z; v.w += dE[h] * qk[h][c].w + p * dc[h][c].w;
                         }
-                        atomicAdd(dst + col, v.x); atomicAdd(dst + col + 1, v.y);
-                        atomicAdd(dst + col + 2, v.z); atomicAdd(dst + col + 3, v.w);
+                        dxh[c] = v;
+                        if (LN) {
+                            const int col = c * 128 + lane * 4;
+                            if (col < a.D) {
+                                const float4 xh = make_float4((x[c].x - mu) * rstd, (x[c].y - mu) * rstd,
+                                                              (x[c].z - mu) * rstd, (x[c].w - mu) * rstd);
+                                t1 += v.x + v.y + v.z + v.w;
+                                t2 += dot4(v, xh);
+                            }
+                        }
+                    }
+                    if (LN) {
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            t1 += __shfl_xor_sync(FULL, t1, o);
+                            t2 += __shfl_xor_sync(FULL, t2, o);
+                        }
+                        t1 *= invD; t2 *= invD;
+                    }
+                    float* dst = g.dpe + s_pe[ll] * a.D;
+#pragma unroll
+                    for (int c = 0; c < NV4; ++c) {
+                        const int col = c * 128 + lane * 4;
+                        if (col < a.D) {
+                            float4 v = dxh[c];
+                            if (LN) {
+                                v.x = rstd * (v.x - t1 - (x[c].x - mu) * rstd * t2);
+                                v.y = rstd * (v.y - t1 - (x[c].y - mu) * rstd * t2);
+                                v.z = rstd * (v.z - t1 - (x[c].z - mu) * rstd * t2);
+                                v.w = rstd * (v.w - t1 - (x[c].w - mu) * rstd * t2);
+                            }
+                            atomicAdd(dst + col, v.x); atomicAdd(dst + col + 1, v.y);
+                            atomicAdd(dst + col + 2, v.z); atomicAdd(dst + col + 3, v.w);
+                        }
                     }
                 }
             }
@@ -476,7 +567,7 @@ window_attn_bwd_kernel(const AttnArgs a, const AttnBwdArgs g) {
 template <int NV4, int HPW, bool LN, int NW>
 int launch_fwd_nw(const AttnArgs& a, cudaStream_t st) {
     dim3 grid(a.N, trxl_cdiv(a.H, HPW));
-    const size_t smem = (size_t)a.L * 16 + (size_t)HPW * ((a.L + 3) & ~3) * 4 + (size_t)HPW * a.D * 4 + NW * HPW * 3 * 4 + a.L + 16;
+    const size_t smem = attn_smem_bytes(a.L, a.D, HPW, NW);
     if (smem > 48 * 1024) cudaFuncSetAttribute(window_attn_fwd_kernel<NV4, HPW, LN, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     trxl_prof_begin(0, a.N, st);
     window_attn_fwd_kernel<NV4, HPW, LN, NW><<<grid, NW * 32, smem, st>>>(a);
@@ -495,7 +586,7 @@ template <int NV4, int HPW, bool LN>
 int launch_bwd_ln(const AttnArgs& a, const AttnBwdArgs& g, cudaStream_t st) {
     constexpr int NW = 4;
     dim3 grid(a.N, trxl_cdiv(a.H, HPW));
-    const size_t smem = (size_t)a.L * 16 + (size_t)HPW * ((a.L + 3) & ~3) * 4 + (size_t)HPW * a.D * 4 + NW * HPW * 2 * 4 + a.L + 16;
+    const size_t smem = attn_smem_bytes(a.L, a.D, HPW, NW);
     if (smem > 48 * 1024) cudaFuncSetAttribute(window_attn_bwd_kernel<NV4, HPW, LN, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     trxl_prof_begin(1, a.N, st);
     window_attn_bwd_kernel<NV4, HPW, LN, NW><<<grid, NW * 32, smem, st>>>(a, g);
@@ -508,7 +599,7 @@ int launch_bwd(const AttnArgs& a, const AttnBwdArgs& g, cudaStream_t st) {
     return a.ln ? launch_bwd_ln<NV4, HPW, true>(a, g, st) : launch_bwd_ln<NV4, HPW, false>(a, g, st);
 }
 
-// heads per warp pass: keep (qk + acc) register arrays <= ~64 float4-lanes
+// heads per warp pass: keep the (qk + acc) register arrays <= ~64 float4-lanes
 int pick_hpw(int nv4, int H) {
     int hpw = nv4 <= 2 ? 4 : 2;
     if (nv4 > 4) hpw = 1;
