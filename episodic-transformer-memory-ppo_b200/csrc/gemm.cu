@@ -217,6 +217,125 @@ __global__ void splitk_reduce_kernel(const GemmArgs g) {
     *cp = v;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Skinny GEMM for the rollout path: M <= 32 rows (one per env worker).  The tiled kernel above is
+// latency-bound there (8 CTAs x 16 dependent k-iterations); here a CTA owns 16 output columns, pulls
+// its whole K panel (<= 256 deep per pass) into shared memory with every load in flight at once, and
+// then runs a register-blocked (1 row x 4 columns per thread) inner product out of shared memory.
+// A must be k-contiguous; B may be k- or n-contiguous.  Split-K and the fused epilogue work as above.
+// ------------------------------------------------------------------------------------------------
+constexpr int SK_KC = 256, SK_BN = 16, SK_LD = SK_KC + 4;
+
+template <bool BKC>
+__global__ void __launch_bounds__(128) skinny_gemm_kernel(const GemmArgs g) {
+    extern __shared__ __align__(16) float sk_smem[];
+    float* As = sk_smem;                    // [32][SK_LD]
+    float* Bs = sk_smem + 32 * SK_LD;       // [SK_BN][SK_LD]
+    const int tid = threadIdx.x;
+    const int n0 = blockIdx.x * SK_BN;
+    const int b = blockIdx.z / g.ksplit, split = blockIdx.z % g.ksplit;
+    const int k_begin = split * g.k_per_split;
+    const int k_end = min(g.K, k_begin + g.k_per_split);
+    const float* __restrict__ A = g.A + (long long)b * g.sA;
+    const float* __restrict__ B = g.B + (long long)b * g.sB;
+    const int m = tid & 31, ng = tid >> 5;            // this thread: row m, columns n0 + 4*ng .. +3
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+
+    for (int k0 = k_begin; k0 < k_end; k0 += SK_KC) {
+        const int kc = min(SK_KC, k_end - k0);
+        const int kc4 = (kc + 3) & ~3;
+        // ---- A panel: 32 rows x kc, k-contiguous ----
+        if (g.vecA && (k0 & 3) == 0) {
+            for (int v = tid; v < 32 * (kc4 >> 2); v += 128) {
+                const int r = v / (kc4 >> 2), k = (v % (kc4 >> 2)) * 4;
+                float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < g.M) {
+                    const float* p = A + (long long)r * g.lda + k0 + k;
+                    if (k + 3 < kc) val = *reinterpret_cast<const float4*>(p);
+                    else { if (k < kc) val.x = p[0]; if (k + 1 < kc) val.y = p[1]; if (k + 2 < kc) val.z = p[2]; }
+                }
+                *reinterpret_cast<float4*>(As + r * SK_LD + k) = val;
+            }
+        } else {
+            for (int v = tid; v < 32 * kc4; v += 128) {
+                const int r = v / kc4, k = v % kc4;
+                As[r * SK_LD + k] = (r < g.M && k < kc) ? A[(long long)r * g.lda + k0 + k] : 0.f;
+            }
+        }
+        // ---- B panel: 16 columns x kc ----
+        if (BKC) {
+            if (g.vecB && (k0 & 3) == 0) {
+                for (int v = tid; v < SK_BN * (kc4 >> 2); v += 128) {
+                    const int c = v / (kc4 >> 2), k = (v % (kc4 >> 2)) * 4;
+                    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (n0 + c < g.N) {
+                        const float* p = B + (long long)(n0 + c) * g.ldb + k0 + k;
+                        if (k + 3 < kc) val = *reinterpret_cast<const float4*>(p);
+                        else { if (k < kc) val.x = p[0]; if (k + 1 < kc) val.y = p[1]; if (k + 2 < kc) val.z = p[2]; }
+                    }
+                    *reinterpret_cast<float4*>(Bs + c * SK_LD + k) = val;
+                }
+            } else {
+                for (int v = tid; v < SK_BN * kc4; v += 128) {
+                    const int c = v / kc4, k = v % kc4;
+                    Bs[c * SK_LD + k] = (n0 + c < g.N && k < kc) ? B[(long long)(n0 + c) * g.ldb + k0 + k] : 0.f;
+                }
+            }
+        } else {
+            for (int v = tid; v < SK_BN * kc4; v += 128) {        // 16 consecutive n per k row (64 B segments)
+                const int k = v / SK_BN, c = v % SK_BN;
+                Bs[c * SK_LD + k] = (n0 + c < g.N && k < kc) ? B[(long long)(k0 + k) * g.ldb + n0 + c] : 0.f;
+            }
+        }
+        __syncthreads();
+        const float* ar = As + m * SK_LD;
+        const float* b0 = Bs + (4 * ng) * SK_LD;
+#pragma unroll 4
+        for (int k = 0; k < kc4; k += 4) {
+            const float4 a = *reinterpret_cast<const float4*>(ar + k);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 w = *reinterpret_cast<const float4*>(b0 + j * SK_LD + k);
+                acc[j] = fmaf(a.x, w.x, fmaf(a.y, w.y, fmaf(a.z, w.z, fmaf(a.w, w.w, acc[j]))));
+            }
+        }
+        __syncthreads();
+    }
+    if (m >= g.M) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int n = n0 + 4 * ng + j;
+        if (n >= g.N) continue;
+        if (g.ksplit > 1) {
+            g.ws[((long long)blockIdx.z * g.M + m) * g.N + n] = acc[j];
+            continue;
+        }
+        float v = acc[j] * g.alpha;
+        if (g.bias) v += g.bias[(long long)b * g.sBias + n];
+        if (g.relu) v = fmaxf(v, 0.f);
+        if (g.R) v += g.R[(long long)b * g.sR + (long long)m * g.ldr + n];
+        float* cp = g.C + (long long)b * g.sC + (long long)m * g.ldc + n;
+        if (g.accumulate) v += *cp;
+        *cp = v;
+    }
+}
+
+int launch_skinny(const GemmArgs& g, cudaStream_t st) {
+    static bool attr_set = false;
+    constexpr int smem = (32 + SK_BN) * SK_LD * (int)sizeof(float);
+    if (!attr_set) {
+        cudaFuncSetAttribute(skinny_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(skinny_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
+    dim3 grid(trxl_cdiv(g.N, SK_BN), 1, g.batch * g.ksplit);
+    if (g.b_kc) skinny_gemm_kernel<true><<<grid, 128, smem, st>>>(g);
+    else skinny_gemm_kernel<false><<<grid, 128, smem, st>>>(g);
+    TRXL_CHECK_LAUNCH("skinny_gemm");
+    return TRXL_OK;
+}
+
 template <int BM, int BN, int TM, int TN>
 int launch_cfg(const GemmArgs& g, cudaStream_t st) {
     dim3 grid(trxl_cdiv(g.N, BN), trxl_cdiv(g.M, BM), g.batch * g.ksplit);
@@ -265,7 +384,23 @@ int trxl_gemm(GemmArgs g, cudaStream_t st) {
         }
     }
     int rc;
-    if (small) rc = launch_cfg<32, 32, 2, 2>(g, st);
+    if (g.M <= 32 && g.a_kc && g.N >= 8) {
+        // rollout-sized batch: one CTA per 16 output columns; split K only when the panel is deep
+        g.ksplit = 1;
+        g.k_per_split = g.K;
+        const long long ctas = (long long)trxl_cdiv(g.N, SK_BN) * g.batch;
+        if (g.ws && g.K > 2 * SK_KC && ctas < 148) {
+            int s = (int)((148 * 2 + ctas - 1) / ctas);
+            const int maxs = trxl_cdiv(g.K, SK_KC);
+            if (s > maxs) s = maxs;
+            while (s > 1 && (long long)s * g.batch * g.M * g.N > g.ws_floats) --s;
+            if (s > 1) {
+                g.k_per_split = ((g.K + s - 1) / s + 3) / 4 * 4;
+                g.ksplit = (g.K + g.k_per_split - 1) / g.k_per_split;
+            }
+        }
+        rc = launch_skinny(g, st);
+    } else if (small) rc = launch_cfg<32, 32, 2, 2>(g, st);
     else rc = launch_cfg<64, 64, 4, 4>(g, st);
     if (rc != TRXL_OK || g.ksplit == 1) return rc;
     const long long total = (long long)g.M * g.N * g.batch;

@@ -60,7 +60,8 @@ def test_gather_window_and_rows_bit_exact():
     assert torch.equal(dst, rows[pick])
 
 
-@pytest.mark.parametrize("m,n,k", [(5, 7, 3), (32, 256, 256), (2048, 256, 256), (64, 3, 384), (300, 384, 3136), (1, 16, 16)])
+@pytest.mark.parametrize("m,n,k", [(5, 7, 3), (32, 256, 256), (2048, 256, 256), (64, 3, 384), (300, 384, 3136), (1, 16, 16),
+                                   (32, 256, 3136), (17, 40, 1001), (32, 384, 256), (2048, 384, 256)])
 def test_linear_forward_backward(m, n, k):
     import trxl_native as native
     torch.manual_seed(m + n + k)
@@ -235,3 +236,66 @@ def test_trainer_two_updates_vs_reference(name, tmp_path, monkeypatch):
         for pname, p in tr.model.named_parameters():
             np.testing.assert_allclose(p.detach().cpu().numpy(), g[pre + "after." + pname], atol=1e-4, err_msg=pname)
     tr.close(exit_process=False)
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE-sized shapes
+@pytest.mark.parametrize("n,ln,pe,gtrxl", [(32, "post", "relative", False), (300, "post", "relative", False),
+                                           (32, "pre", "learned", True), (130, "pre", "relative", True)])
+def test_forward_backward_c3_dims_vs_oracle(n, ln, pe, gtrxl):
+    """c3 dimensions (L=128, D=256, H=4, B=4, lin_hidden K=3136 fed directly as a vector observation) at rollout and
+    training batch sizes: exercises the skinny / split-K / tiled GEMM paths and the 128-slot window kernel against the
+    CPU oracle (forward 1e-4; gradients 2e-4 of the tensor max)."""
+    from model import ActorCriticModel
+    from oracle import ppo_oracle as O
+    from oracle import trxl_oracle as X
+    from parity_util import _Space
+    torch.manual_seed(n)
+    L, D, H, B, M, feat, hid = 128, 256, 4, 4, 256, 3136, 384
+    cfg = {"hidden_layer_size": hid, "value_loss_coefficient": 0.5, "max_grad_norm": 0.5,
+           "transformer": {"num_blocks": B, "embed_dim": D, "num_heads": H, "memory_length": L, "positional_encoding": pe,
+                           "layer_norm": ln, "gtrxl": gtrxl, "gtrxl_bias": 0.5}}
+    model = ActorCriticModel(cfg, _Space((feat,)), (3,), M).to(DEV)
+    P = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    ocfg = dict(cfg, max_episode_steps=M, action_space_shape=(3,))
+    n_eps = 12
+    table = torch.randn(n_eps, M, B, D)
+    steps = torch.randint(0, M, (n,))
+    steps[0] = 0
+    ep = torch.randint(0, n_eps, (n,))
+    idx = X.window_index_table(M, L)[steps]
+    mask = X.attention_mask_table(L)[torch.clip(steps, 0, L - 1)].bool()
+    obs = torch.rand(n, feat)
+    mb = {"obs": obs, "memories": table[ep], "memory_indices": idx, "memory_mask": mask,
+          "actions": torch.randint(0, 3, (n, 1)), "values": torch.randn(n), "advantages": torch.randn(n),
+          "log_probs": -torch.rand(n, 1) - 0.5}
+    # oracle forward + loss gradient
+    names = X.trainable_names(P)
+    for k in names:
+        P[k].requires_grad_(True)
+    window = X.select_window(mb["memories"], idx)
+    logits, value, new_mem = X.model_forward(P, ocfg, obs, window, mask, idx)
+    loss, stats = O.ppo_loss(logits, value, mb, 0.1, 1e-3, 0.5)
+    loss.backward()
+    # native: table read in place through (episode, slot) indices
+    dev = lambda t: t.to(DEV).contiguous()  # noqa: E731
+    with torch.no_grad():
+        lg, val, mem = model.forward_table(dev(obs), dev(table), dev(ep), dev(idx), dev(mask.to(torch.uint8)), dev(idx))
+    np.testing.assert_allclose(val.cpu().numpy(), value.detach().numpy(), atol=1e-4)
+    np.testing.assert_allclose(mem.cpu().numpy(), new_mem.detach().numpy(), atol=1e-4)
+    np.testing.assert_allclose(lg.cpu().numpy(), logits[0].detach().numpy(), atol=1e-4)
+    # native fused step pieces: loss + backward, compared before clipping
+    import trxl_native as native
+    st3 = torch.zeros(3, dtype=torch.float64, device=DEV)
+    native.adv_stats(dev(mb["advantages"]), None, n, st3)
+    dlogits, dvalue = torch.empty((n, 3), device=DEV), torch.empty(n, device=DEV)
+    stats_dev = torch.zeros(6, device=DEV)
+    native.ppo_loss(lg, val, dev(mb["actions"]), dev(mb["log_probs"]), dev(mb["values"]), dev(mb["advantages"]), None, st3, (3,), n,
+                    0.1, 1e-3, 0.5, dlogits, dvalue, stats_dev, torch.empty(n // 128 * 5 + 64, device=DEV))
+    np.testing.assert_allclose(stats_dev.cpu().numpy(), np.array([float(s) for s in stats]), rtol=2e-4, atol=1e-5)
+    model.flat_grads().zero_()
+    model.backward_table(dev(obs), dev(table), dev(ep), dev(idx), dev(mask.to(torch.uint8)), dev(idx), None, n, model.workspace(n),
+                         mem, dlogits, dvalue)
+    for k, p in model.named_parameters():
+        want = P[k].grad.numpy()
+        scale = max(1e-12, float(np.abs(want).max()))
+        np.testing.assert_allclose(p.grad.cpu().numpy(), want, rtol=2e-4, atol=2e-4 * scale, err_msg=k)
