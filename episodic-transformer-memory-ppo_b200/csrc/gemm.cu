@@ -10,6 +10,8 @@
 //   wgrad    dW = dy^T x    : A = dy (mc),  B = x  (nc)
 // fp32 accumulate in a fixed k order (deterministic).  The parity contract of this engine is 1e-4
 // against the reference's fp32 CPU path, so the linears stay in full fp32 on the CUDA cores here.
+#include <stdlib.h>
+
 #include "gemm.cuh"
 
 namespace {
@@ -350,6 +352,18 @@ int launch_cfg(const GemmArgs& g, cudaStream_t st) {
 
 }  // namespace
 
+int trxl_tc_gemm(const GemmArgs& g, cudaStream_t st);      // tc_gemm.cu
+
+// TRXL_TCGEN05=0 disables the tensor-core GEMM (falls back to the SIMT kernels above, same results to ~1e-6)
+static bool tc_enabled() {
+    static int state = -1;
+    if (state < 0) {
+        const char* e = getenv("TRXL_TCGEN05");
+        state = (e && e[0] == '1') ? 1 : 0;
+    }
+    return state == 1;
+}
+
 static thread_local float* tl_ws = nullptr;
 static thread_local long long tl_ws_floats = 0;
 void trxl_gemm_set_workspace(float* ws, long long floats) { tl_ws = ws; tl_ws_floats = floats; }
@@ -384,7 +398,25 @@ int trxl_gemm(GemmArgs g, cudaStream_t st) {
         }
     }
     int rc;
-    if (g.M <= 32 && g.a_kc && g.N >= 8) {
+    if (tc_enabled() && g.M >= 128 && g.N >= 48 && g.K >= 32) {
+        // tensor-core path (tc_gemm.cu): 128 x {64,128} tiles, 3xTF32 in TMEM; split K when the tile count is small
+        const int bn = g.N > 64 ? 128 : 64;
+        const long long tc_tiles = (long long)trxl_cdiv(g.M, 128) * trxl_cdiv(g.N, bn) * g.batch;
+        g.ksplit = 1;
+        g.k_per_split = g.K;
+        if (g.ws && g.K >= 256 && tc_tiles * 2 <= 148) {
+            int s = (int)((148 + tc_tiles - 1) / tc_tiles);
+            const int maxs = g.K / 64;
+            if (s > maxs) s = maxs;
+            if (s > 32) s = 32;
+            while (s > 1 && (long long)s * g.batch * g.M * g.N > g.ws_floats) --s;
+            if (s > 1) {
+                g.k_per_split = ((g.K + s - 1) / s + 31) / 32 * 32;
+                g.ksplit = (g.K + g.k_per_split - 1) / g.k_per_split;
+            }
+        }
+        rc = trxl_tc_gemm(g, st);
+    } else if (g.M <= 32 && g.a_kc && g.N >= 8) {
         // rollout-sized batch: one CTA per 16 output columns; split K only when the panel is deep
         g.ksplit = 1;
         g.k_per_split = g.K;

@@ -61,7 +61,8 @@ def test_gather_window_and_rows_bit_exact():
 
 
 @pytest.mark.parametrize("m,n,k", [(5, 7, 3), (32, 256, 256), (2048, 256, 256), (64, 3, 384), (300, 384, 3136), (1, 16, 16),
-                                   (32, 256, 3136), (17, 40, 1001), (32, 384, 256), (2048, 384, 256)])
+                                   (32, 256, 3136), (17, 40, 1001), (32, 384, 256), (2048, 384, 256), (129, 64, 40),
+                                   (1000, 200, 70), (256, 256, 2048), (4096, 128, 32)])
 def test_linear_forward_backward(m, n, k):
     import trxl_native as native
     torch.manual_seed(m + n + k)
