@@ -71,6 +71,8 @@ extern "C" {
 const char* trxl_last_error(void) { return g_err; }
 int trxl_abi_version(void) { return TRXL_ABI_VERSION; }
 int64_t trxl_launch_count(void) { return g_trxl_launches; }
+extern long long g_trxl_tc_launches;
+int64_t trxl_tc_gemm_launches(void) { return g_trxl_tc_launches; }
 
 int trxl_profile_enable(int on) {
     g_prof_on = on != 0;

@@ -229,6 +229,13 @@ __global__ void splitk_reduce_kernel(const GemmArgs g) {
 // ------------------------------------------------------------------------------------------------
 constexpr int SK_KC = 256, SK_BN = 16, SK_LD = SK_KC + 4;
 
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+
 template <bool BKC>
 __global__ void __launch_bounds__(128) skinny_gemm_kernel(const GemmArgs g) {
     extern __shared__ __align__(16) float sk_smem[];
@@ -247,17 +254,19 @@ __global__ void __launch_bounds__(128) skinny_gemm_kernel(const GemmArgs g) {
     for (int k0 = k_begin; k0 < k_end; k0 += SK_KC) {
         const int kc = min(SK_KC, k_end - k0);
         const int kc4 = (kc + 3) & ~3;
+        // Every copy of the panel is issued before anything waits (cp.async, 16 B each, zero-filled
+        // past the matrix edge): the CTA pays one L2 round trip per K panel, not one per element.
         // ---- A panel: 32 rows x kc, k-contiguous ----
         if (g.vecA && (k0 & 3) == 0) {
-            for (int v = tid; v < 32 * (kc4 >> 2); v += 128) {
-                const int r = v / (kc4 >> 2), k = (v % (kc4 >> 2)) * 4;
-                float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r < g.M) {
-                    const float* p = A + (long long)r * g.lda + k0 + k;
-                    if (k + 3 < kc) val = *reinterpret_cast<const float4*>(p);
-                    else { if (k < kc) val.x = p[0]; if (k + 1 < kc) val.y = p[1]; if (k + 2 < kc) val.z = p[2]; }
+#pragma unroll
+            for (int i = 0; i < (32 * SK_KC / 4) / 128; ++i) {
+                const int v = tid + i * 128;
+                const int r = v / (SK_KC / 4), k = (v % (SK_KC / 4)) * 4;
+                if (k < kc4) {
+                    const int valid = (r < g.M) ? max(0, min(4, kc - k)) : 0;
+                    const float* p = valid ? A + (long long)r * g.lda + k0 + k : A;
+                    cp_async16(As + r * SK_LD + k, p, valid * 4);
                 }
-                *reinterpret_cast<float4*>(As + r * SK_LD + k) = val;
             }
         } else {
             for (int v = tid; v < 32 * kc4; v += 128) {
@@ -268,15 +277,15 @@ __global__ void __launch_bounds__(128) skinny_gemm_kernel(const GemmArgs g) {
         // ---- B panel: 16 columns x kc ----
         if (BKC) {
             if (g.vecB && (k0 & 3) == 0) {
-                for (int v = tid; v < SK_BN * (kc4 >> 2); v += 128) {
-                    const int c = v / (kc4 >> 2), k = (v % (kc4 >> 2)) * 4;
-                    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (n0 + c < g.N) {
-                        const float* p = B + (long long)(n0 + c) * g.ldb + k0 + k;
-                        if (k + 3 < kc) val = *reinterpret_cast<const float4*>(p);
-                        else { if (k < kc) val.x = p[0]; if (k + 1 < kc) val.y = p[1]; if (k + 2 < kc) val.z = p[2]; }
+#pragma unroll
+                for (int i = 0; i < (SK_BN * SK_KC / 4) / 128; ++i) {
+                    const int v = tid + i * 128;
+                    const int c = v / (SK_KC / 4), k = (v % (SK_KC / 4)) * 4;
+                    if (k < kc4) {
+                        const int valid = (n0 + c < g.N) ? max(0, min(4, kc - k)) : 0;
+                        const float* p = valid ? B + (long long)(n0 + c) * g.ldb + k0 + k : B;
+                        cp_async16(Bs + c * SK_LD + k, p, valid * 4);
                     }
-                    *reinterpret_cast<float4*>(Bs + c * SK_LD + k) = val;
                 }
             } else {
                 for (int v = tid; v < SK_BN * kc4; v += 128) {
@@ -285,11 +294,15 @@ __global__ void __launch_bounds__(128) skinny_gemm_kernel(const GemmArgs g) {
                 }
             }
         } else {
-            for (int v = tid; v < SK_BN * kc4; v += 128) {        // 16 consecutive n per k row (64 B segments)
+            // 16 consecutive n per k row (64 B segments); 4-byte async copies keep every load in flight
+#pragma unroll 8
+            for (int v = tid; v < SK_BN * kc4; v += 128) {
                 const int k = v / SK_BN, c = v % SK_BN;
-                Bs[c * SK_LD + k] = (n0 + c < g.N && k < kc) ? B[(long long)(k0 + k) * g.ldb + n0 + c] : 0.f;
+                const bool ok = (n0 + c < g.N) && (k < kc);
+                cp_async4(Bs + c * SK_LD + k, ok ? B + (long long)(k0 + k) * g.ldb + n0 + c : B, ok ? 4 : 0);
             }
         }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         const float* ar = As + m * SK_LD;
         const float* b0 = Bs + (4 * ng) * SK_LD;

@@ -19,6 +19,8 @@
 // Every mbarrier wait is bounded and traps instead of hanging the GPU.
 #include "gemm.cuh"
 
+long long g_trxl_tc_launches = 0;
+
 namespace {
 
 constexpr int TC_BM = 128, TC_BK = 32;
@@ -257,6 +259,7 @@ int launch_tc(const GemmArgs& g, cudaStream_t st) {
     }
     dim3 grid(trxl_cdiv(g.N, BN), trxl_cdiv(g.M, TC_BM), g.batch * g.ksplit);
     tc_gemm_kernel<BN, STAGES><<<grid, TC_THREADS, smem, st>>>(g);
+    ++g_trxl_tc_launches;
     TRXL_CHECK_LAUNCH("tc_gemm");
     return TRXL_OK;
 }

@@ -40,6 +40,7 @@ SIGNATURES = {
     "trxl_last_error": (C.c_char_p, []),
     "trxl_abi_version": (i32, []),
     "trxl_launch_count": (i64, []),
+    "trxl_tc_gemm_launches": (i64, []),
     "trxl_profile_enable": (i32, [i32]),
     "trxl_profile_read": (i32, [i32, i32, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "trxl_layout_num_entries": (i32, [CFGP]),
@@ -150,6 +151,10 @@ def layout(cfg):
 
 def launch_count():
     return int(load().trxl_launch_count())
+
+
+def tc_gemm_launches():
+    return int(load().trxl_tc_gemm_launches())
 
 
 def profile_enable(on):

@@ -57,6 +57,8 @@ const char* trxl_last_error(void);
 int trxl_abi_version(void);
 /* kernels launched by this library since load (bench.py reports the delta as gpu_launches) */
 int64_t trxl_launch_count(void);
+/* of which launches of the tcgen05 3xTF32 GEMM (tc_gemm.cu; enabled with TRXL_TCGEN05=1) */
+int64_t trxl_tc_gemm_launches(void);
 /* Measurement aid: when enabled, every window-attention launch is bracketed by CUDA events on its own
  * stream.  trxl_profile_read sums the durations of launches of `kind` (0 forward, 1 backward) that
  * processed at least min_samples samples; synchronises on those events only. */

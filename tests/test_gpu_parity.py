@@ -300,3 +300,17 @@ def test_forward_backward_c3_dims_vs_oracle(n, ln, pe, gtrxl):
         want = P[k].grad.numpy()
         scale = max(1e-12, float(np.abs(want).max()))
         np.testing.assert_allclose(p.grad.cpu().numpy(), want, rtol=2e-4, atol=2e-4 * scale, err_msg=k)
+
+
+def test_tcgen05_gemm_is_used_when_enabled():
+    """With TRXL_TCGEN05=1 the large linears must actually run on the tcgen05 kernel (no silent SIMT fallback)."""
+    import os
+    import trxl_native as native
+    x, w = torch.randn(512, 256, device=DEV), torch.randn(256, 256, device=DEV)
+    y = torch.empty(512, 256, device=DEV)
+    before = native.tc_gemm_launches()
+    native.linear_forward(x, w, None, y)
+    torch.cuda.synchronize()
+    used = native.tc_gemm_launches() - before
+    assert used == (1 if os.environ.get("TRXL_TCGEN05", "0") == "1" else 0)
+    assert torch.allclose(y.double(), x.double() @ w.double().t(), atol=2e-4, rtol=1e-4)
