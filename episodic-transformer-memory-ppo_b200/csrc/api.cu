@@ -5,6 +5,7 @@
 
 #include "../../include/trxl_ppo.h"
 #include "attention.cuh"
+#include "conv.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "model.cuh"
@@ -137,6 +138,27 @@ int trxl_model_backward(const trxl_model_config* cfg, const float* params, float
     io.N = N; io.feat = feat; io.table = table; io.slots = slots; io.ep_index = (cll)ep_index; io.win_index = (cll)win_index;
     io.mask = mask; io.pe_index = (cll)pe_index; io.sample_index = (cll)sample_index; io.pe_table = pe_table;
     return model_backward(cfg, params, grads, io, workspace, out_mem, dlogits, dvalue, dfeat, S(stream));
+}
+
+int64_t trxl_conv_encoder_workspace_floats(const trxl_model_config* cfg, int N, int H, int W) {
+    if (!cfg || cfg->conv_in_channels <= 0 || N < 0) return -1;
+    return conv_encoder_workspace_floats(N, cfg->conv_in_channels, H, W);
+}
+
+int trxl_conv_encoder_forward(const trxl_model_config* cfg, const float* params, const float* obs, int N, int H, int W,
+                              float* workspace, float* feat, void* stream) {
+    TRXL_CHECK_ARG(cfg && cfg->conv_in_channels > 0, "conv_encoder: config has no convolutional encoder");
+    TRXL_CHECK_ARG(params && obs && workspace && feat, "conv_encoder: null pointer");
+    std::vector<trxl_param_entry> e;
+    TRXL_PROPAGATE(model_layout(cfg, e, nullptr, nullptr));
+    long long off[6] = {-1, -1, -1, -1, -1, -1};
+    const char* names[6] = {"conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias", "conv3.weight", "conv3.bias"};
+    for (const auto& en : e)
+        for (int i = 0; i < 6; ++i)
+            if (strcmp(en.name, names[i]) == 0) off[i] = en.offset;
+    for (int i = 0; i < 6; ++i) TRXL_CHECK_ARG(off[i] >= 0, "conv_encoder: parameter %s missing from the layout", names[i]);
+    return conv_encoder_forward(S(stream), params + off[0], params + off[1], params + off[2], params + off[3], params + off[4],
+                                params + off[5], obs, N, cfg->conv_in_channels, H, W, workspace, feat);
 }
 
 static AttnArgs make_attn(const float* table, int64_t slots, int num_blocks, int block, const int64_t* ep_index,

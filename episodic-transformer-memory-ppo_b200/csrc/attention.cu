@@ -577,7 +577,12 @@ int launch_fwd_nw(const AttnArgs& a, cudaStream_t st) {
 }
 template <int NV4, int HPW>
 int launch_fwd(const AttnArgs& a, cudaStream_t st) {
-    const bool wide = (long long)a.N * trxl_cdiv(a.H, HPW) < 148 * 2 && a.L >= 32;
+    // few samples (rollout: one per env worker): the latency is each warp's chain of dependent row loads, so
+    // spread a sample's window over 16 (or 8) warps; training minibatches fill the GPU with 4-warp CTAs
+    const long long ctas = (long long)a.N * trxl_cdiv(a.H, HPW);
+    if (NV4 <= 2 && ctas <= 148 && a.L >= 64)
+        return a.ln ? launch_fwd_nw<NV4, HPW, true, 16>(a, st) : launch_fwd_nw<NV4, HPW, false, 16>(a, st);
+    const bool wide = ctas < 148 * 2 && a.L >= 32;
     if (a.ln) return wide ? launch_fwd_nw<NV4, HPW, true, 8>(a, st) : launch_fwd_nw<NV4, HPW, true, 4>(a, st);
     return wide ? launch_fwd_nw<NV4, HPW, false, 8>(a, st) : launch_fwd_nw<NV4, HPW, false, 4>(a, st);
 }

@@ -170,6 +170,11 @@ struct Acts {
     long long total;
 };
 
+struct GemmWsGuard {       // the split-K workspace is only valid while this forward/backward is being enqueued
+    GemmWsGuard(float* p, long long n) { trxl_gemm_set_workspace(p, n); }
+    ~GemmWsGuard() { trxl_gemm_set_workspace(nullptr, 0); }
+};
+
 struct Bump {
     float* base; long long cur = 0;
     float* take(long long n) { float* p = base ? base + cur : nullptr; cur += (n + 3) / 4 * 4; return p; }
@@ -286,7 +291,7 @@ int model_forward(const trxl_model_config* c, const float* P, const ModelIO& io,
     TRXL_CHECK_ARG(c->pos_enc == TRXL_PE_NONE || io.pe_index, "model_forward: positional encoding needs pe_index");
     Acts A;
     carve(c, io.N, ws, A);
-    trxl_gemm_set_workspace(A.gemm_ws, A.gemm_ws_n);
+    GemmWsGuard ws_guard(A.gemm_ws, A.gemm_ws_n);
     const int N = io.N, D = c->embed_dim, H = c->num_heads, B = c->num_blocks, dh = D / H, hid = c->hidden_size;
     const long long BD = (long long)B * D;
     const bool pre = c->layer_norm == TRXL_LN_PRE, post = c->layer_norm == TRXL_LN_POST;
@@ -361,7 +366,7 @@ int model_backward(const trxl_model_config* c, const float* P, float* G, const M
     TRXL_CHECK_ARG(P && G && io.feat && io.table && ws && out_mem && dlogits && dvalue, "model_backward: null pointer");
     Acts A;
     carve(c, io.N, ws, A);
-    trxl_gemm_set_workspace(A.gemm_ws, A.gemm_ws_n);
+    GemmWsGuard ws_guard(A.gemm_ws, A.gemm_ws_n);
     const int N = io.N, D = c->embed_dim, H = c->num_heads, B = c->num_blocks, dh = D / H, hid = c->hidden_size;
     const long long BD = (long long)B * D, HD = (long long)H * D;
     const bool pre = c->layer_norm == TRXL_LN_PRE, post = c->layer_norm == TRXL_LN_POST;

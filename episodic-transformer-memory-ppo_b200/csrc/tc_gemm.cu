@@ -139,34 +139,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const GemmArgs g
 
     if (warp < 4) {
         // ---------------- producers ----------------
+        // Register-level software pipeline, two k-blocks deep: the global loads of k-block kb+2 are in flight
+        // while kb is split/stored and kb+1 waits in registers, so L2 latency is hidden behind the MMAs.
         const int r = threadIdx.x;                               // tile row owned by this thread (A: 0..127, B: 0..BN-1)
-        for (int kb = 0; kb < kblocks; ++kb) {
+        constexpr int NC = TC_BK / 4;                            // 16-byte k-chunks per row per k-block
+        const int row_off = (r >> 3) * 32 + (r & 7) * 4;         // core-matrix layout: chunk c at c*(ROWS*4) + (row/8)*32 + (row%8)*4
+        float4 ra[2][NC], rb[2][NC];
+        auto issue = [&](int kb, float4 (&xa)[NC], float4 (&xb)[NC]) {
+            const int k0 = k_begin + kb * TC_BK;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) xa[c] = load_chunk(A, g.lda, g.a_kc, g.vecA, m0 + r, g.M, k0 + 4 * c, k_end);
+            if (r < BN) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) xb[c] = load_chunk(B, g.ldb, g.b_kc, g.vecB, n0 + r, g.N, k0 + 4 * c, k_end);
+            }
+        };
+        auto commit = [&](int kb, const float4 (&xa)[NC], const float4 (&xb)[NC]) {
             const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
-            mbar_wait(&empty[s], ph ^ 1);
+            mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
             float* a_hi = tiles + s * STAGE_FLOATS;
             float* a_lo = a_hi + A_FLOATS;
             float* b_hi = a_lo + A_FLOATS;
             float* b_lo = b_hi + B_FLOATS;
-            const int k0 = k_begin + kb * TC_BK;
-            // core-matrix layout: chunk c (4 floats of k) at c*(ROWS*4) + (row/8)*32 + (row%8)*4
-            const int row_off = (r >> 3) * 32 + (r & 7) * 4;
 #pragma unroll
-            for (int c = 0; c < TC_BK / 4; ++c) {
-                const float4 v = load_chunk(A, g.lda, g.a_kc, g.vecA, m0 + r, g.M, k0 + 4 * c, k_end);
-                split_store(a_hi + c * (TC_BM * 4) + row_off, a_lo + c * (TC_BM * 4) + row_off, v);
-            }
+            for (int c = 0; c < NC; ++c) split_store(a_hi + c * (TC_BM * 4) + row_off, a_lo + c * (TC_BM * 4) + row_off, xa[c]);
             if (r < BN) {
 #pragma unroll
-                for (int c = 0; c < TC_BK / 4; ++c) {
-                    // B(k, n): b_kc=1 -> B[n*ldb + k]; b_kc=0 -> B[k*ldb + n]
-                    const float4 v = load_chunk(B, g.ldb, g.b_kc, g.vecB, n0 + r, g.N, k0 + 4 * c, k_end);
-                    split_store(b_hi + c * (BN * 4) + row_off, b_lo + c * (BN * 4) + row_off, v);
-                }
+                for (int c = 0; c < NC; ++c) split_store(b_hi + c * (BN * 4) + row_off, b_lo + c * (BN * 4) + row_off, xb[c]);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the MMA (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[s]);
+        };
+        issue(0, ra[0], rb[0]);
+        if (kblocks > 1) issue(1, ra[1], rb[1]);
+        for (int kb = 0; kb < kblocks; kb += 2) {
+            commit(kb, ra[0], rb[0]);
+            if (kb + 2 < kblocks) issue(kb + 2, ra[0], rb[0]);
+            if (kb + 1 < kblocks) {
+                commit(kb + 1, ra[1], rb[1]);
+                if (kb + 3 < kblocks) issue(kb + 3, ra[1], rb[1]);
+            }
         }
         // ---------------- epilogue: TMEM -> registers -> global ----------------
         mbar_wait(tmem_full, 0);
@@ -190,22 +203,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const GemmArgs g
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (m < g.M) {
+                const int nb0 = n0 + j * 32;
+                float* dst = (g.ksplit > 1) ? g.ws + ((long long)blockIdx.z * g.M + m) * g.N : C + (long long)m * g.ldc;
+                const bool fast = (nb0 + 32 <= g.N) && ((((uintptr_t)(dst + nb0)) & 15) == 0) &&
+                                  (g.ksplit > 1 || (!R && !g.accumulate));
+                if (fast) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int n = n0 + j * 32 + i;
-                    if (n >= g.N) continue;
-                    float x = __uint_as_float(v[i]);
-                    if (g.ksplit > 1) {
-                        g.ws[((long long)blockIdx.z * g.M + m) * g.N + n] = x;
-                        continue;
+                    for (int i = 0; i < 32; i += 4) {
+                        float4 o;
+                        float* of = reinterpret_cast<float*>(&o);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float x = __uint_as_float(v[i + q]);
+                            if (g.ksplit == 1) {
+                                x *= g.alpha;
+                                if (bias) x += bias[nb0 + i + q];
+                                if (g.relu) x = fmaxf(x, 0.f);
+                            }
+                            of[q] = x;
+                        }
+                        *reinterpret_cast<float4*>(dst + nb0 + i) = o;
                     }
-                    x *= g.alpha;
-                    if (bias) x += bias[n];
-                    if (g.relu) x = fmaxf(x, 0.f);
-                    if (R) x += R[(long long)m * g.ldr + n];
-                    float* cp = C + (long long)m * g.ldc + n;
-                    if (g.accumulate) x += *cp;
-                    *cp = x;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int n = nb0 + i;
+                        if (n >= g.N) continue;
+                        float x = __uint_as_float(v[i]);
+                        if (g.ksplit == 1) {
+                            x *= g.alpha;
+                            if (bias) x += bias[n];
+                            if (g.relu) x = fmaxf(x, 0.f);
+                            if (R) x += R[(long long)m * g.ldr + n];
+                            if (g.accumulate) x += dst[n];
+                        }
+                        dst[n] = x;
+                    }
                 }
             }
         }

@@ -194,10 +194,23 @@ class ActorCriticModel(nn.Module):
 
     # ------------------------------------------------------------------------------ encoders
     def encode(self, obs):
-        """CNN encoder for image observations (model.py:87-94); identity for vector observations."""
-        if self._visual:
+        """CNN encoder for image observations (model.py:87-94); identity for vector observations.
+        Without autograd (rollout, bootstrap value, enjoy) the encoder runs as this library's im2col + GEMM
+        kernels; under autograd (training minibatches) it goes through cuDNN so torch can differentiate it."""
+        if not self._visual:
+            return obs
+        if torch.is_grad_enabled() or not obs.is_cuda:
             return _conv_features(obs, self.conv1, self.conv2, self.conv3)
-        return obs
+        obs = obs.contiguous()
+        n, _, h, w = obs.shape
+        key = ("enc", n, h, w)
+        ws = self._ws_cache.get(key)
+        if ws is None:
+            ws = (torch.empty(native.conv_encoder_workspace_floats(self._cfg, n, h, w), dtype=torch.float32, device=obs.device),
+                  torch.empty((n, self._feat_dim), dtype=torch.float32, device=obs.device))
+            self._ws_cache[key] = ws
+        native.conv_encoder_forward(self._cfg, self._arena, obs, ws[0], ws[1])
+        return ws[1]
 
     # ------------------------------------------------------------------------------ native trunk
     def forward_table(self, feat, table, ep_index, win_index, mask, pe_index, sample_index=None, n=None, ws=None, out=None):

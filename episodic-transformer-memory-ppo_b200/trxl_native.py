@@ -50,6 +50,8 @@ SIGNATURES = {
     "trxl_workspace_floats": (i64, [CFGP, i32]),
     "trxl_model_forward": (i32, [CFGP, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
     "trxl_model_backward": (i32, [CFGP, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]),
+    "trxl_conv_encoder_workspace_floats": (i64, [CFGP, i32, i32, i32]),
+    "trxl_conv_encoder_forward": (i32, [CFGP, vp, vp, i32, i32, i32, vp, vp, vp]),
     "trxl_window_attention_forward": (i32, [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
     "trxl_window_attention_backward": (i32, [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32,
                                              vp, vp, vp, vp]),
@@ -190,6 +192,19 @@ def model_backward(cfg, params, grads, feat, table, slots, ep_index, win_index, 
     _check(lib.trxl_model_backward(C.byref(cfg), _p(params), _p(grads), _p(feat), _p(table), int(slots), _p(ep_index),
                                    _p(win_index), _p(mask), _p(pe_index), _p(sample_index), _p(pe_table), int(n), _p(ws),
                                    _p(out_mem), _p(dlogits), _p(dvalue), _p(dfeat), _stream()), "trxl_model_backward")
+
+
+def conv_encoder_workspace_floats(cfg, n, h, w):
+    v = load().trxl_conv_encoder_workspace_floats(C.byref(cfg), int(n), int(h), int(w))
+    if v < 0:
+        raise ValueError("no conv encoder for this config / observation too small")
+    return int(v)
+
+
+def conv_encoder_forward(cfg, params, obs, ws, feat):
+    n, _, h, w = obs.shape
+    _check(load().trxl_conv_encoder_forward(C.byref(cfg), _p(params), _p(obs), n, h, w, _p(ws), _p(feat), _stream()),
+           "trxl_conv_encoder_forward")
 
 
 def window_attention_forward(table, slots, num_blocks, block, ep_index, win_index, mask, pe_index, sample_index, pe_table, qk,

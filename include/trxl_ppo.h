@@ -104,6 +104,13 @@ int trxl_model_backward(const trxl_model_config* cfg, const float* params, float
                         const float* pe_table, int N, float* workspace, const float* out_mem, const float* dlogits,
                         const float* dvalue, float* dfeat, void* stream);
 
+/* Inference path of the CNN encoder (model.py:87-94: conv 8/4 -> ReLU -> conv 4/2 -> ReLU -> conv 3/1 -> ReLU -> flatten)
+ * as im2col + GEMM with fused bias/ReLU; used for the rollout forwards.  obs (N, C, H, W) -> feat (N, 64*oh*ow) in the
+ * reference's NCHW flatten order.  workspace >= trxl_conv_encoder_workspace_floats(cfg, N, H, W) floats. */
+int64_t trxl_conv_encoder_workspace_floats(const trxl_model_config* cfg, int N, int H, int W);
+int trxl_conv_encoder_forward(const trxl_model_config* cfg, const float* params, const float* obs, int N, int H, int W,
+                              float* workspace, float* feat, void* stream);
+
 /* ---- the hot kernel on its own ---------------------------------------------------------------- */
 /* Fused window gather + PE add + [LayerNorm] + q.K + mask + softmax(/sqrt(D)) + P.V with the K/V
  * projections folded onto the query side (MultiHeadAttention.forward transformer.py:31-86 for query
