@@ -18,29 +18,37 @@ struct WsGuard {
 };
 
 // cols[(n, oy, ox), (c, ky, kx)] = x[n, c, oy*s+ky, ox*s+kx]          (NCHW input: the observation)
+// one thread per (row, c, ky): KW contiguous inputs -> KW contiguous outputs, 32-bit index math
 __global__ void im2col_nchw_kernel(const float* __restrict__ x, float* __restrict__ cols, int N, int C, int H, int W, int KH,
                                    int KW, int S, int OH, int OW) {
-    const long long K = (long long)C * KH * KW;
-    const long long total = (long long)N * OH * OW * K;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int k = (int)(i % K);
-        const long long m = i / K;
-        const int kx = k % KW, ky = (k / KW) % KH, c = k / (KW * KH);
-        const int ox = (int)(m % OW), oy = (int)((m / OW) % OH), n = (int)(m / ((long long)OW * OH));
-        cols[i] = x[(((long long)n * C + c) * H + oy * S + ky) * W + ox * S + kx];
+    const int total = N * OH * OW * C * KH;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int ky = i % KH, c = (i / KH) % C, m = i / (KH * C);
+        const int ox = m % OW, oy = (m / OW) % OH, n = m / (OW * OH);
+        const float* src = x + (((long long)n * C + c) * H + oy * S + ky) * W + ox * S;
+        float* dst = cols + ((long long)m * C + c) * KH * KW + ky * KW;
+        for (int kx = 0; kx < KW; ++kx) dst[kx] = src[kx];
     }
 }
-// same, for a channels-last input y[(n, iy, ix), c] (the previous layer's GEMM output)
+// channels-last input y[(n, iy, ix), c] (the previous layer's GEMM output) -> cols[(n, oy, ox), (ky, kx, c)]:
+// whole channel runs move as float4 (C % 4 == 0), reads and writes both contiguous
 __global__ void im2col_nhwc_kernel(const float* __restrict__ y, float* __restrict__ cols, int N, int C, int H, int W, int KH,
                                    int KW, int S, int OH, int OW) {
-    const long long K = (long long)C * KH * KW;
-    const long long total = (long long)N * OH * OW * K;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int k = (int)(i % K);
-        const long long m = i / K;
-        const int kx = k % KW, ky = (k / KW) % KH, c = k / (KW * KH);
-        const int ox = (int)(m % OW), oy = (int)((m / OW) % OH), n = (int)(m / ((long long)OW * OH));
-        cols[i] = y[(((long long)n * H + oy * S + ky) * W + ox * S + kx) * C + c];
+    const int C4 = C >> 2;
+    const int total = N * OH * OW * KH * KW * C4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int c4 = i % C4, kx = (i / C4) % KW, ky = (i / (C4 * KW)) % KH, m = i / (C4 * KW * KH);
+        const int ox = m % OW, oy = (m / OW) % OH, n = m / (OW * OH);
+        const float4 v = *reinterpret_cast<const float4*>(y + (((long long)n * H + oy * S + ky) * W + ox * S + kx) * C + c4 * 4);
+        *reinterpret_cast<float4*>(cols + (((long long)m * KH + ky) * KW + kx) * C + c4 * 4) = v;
+    }
+}
+// w[oc][c][ky][kx] -> wp[oc][ky][kx][c]  (matches the (ky, kx, c) patch order above)
+__global__ void permute_weight_kernel(const float* __restrict__ w, float* __restrict__ wp, int OC, int C, int KH, int KW) {
+    const int total = OC * C * KH * KW;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int c = i % C, kx = (i / C) % KW, ky = (i / (C * KW)) % KH, oc = i / (C * KW * KH);
+        wp[i] = w[((oc * C + c) * KH + ky) * KW + kx];
     }
 }
 // feat[n, c*P + p] = y[(n, p), c]  -- the reference flattens NCHW (model.py:94)
@@ -68,7 +76,7 @@ long long conv_encoder_workspace_floats(int N, int C, int H, int W) {
     const long long cols3 = (long long)N * oh3 * ow3 * 576, y3 = (long long)N * oh3 * ow3 * 64;
     long long cols = cols1 > cols2 ? cols1 : cols2;
     if (cols3 > cols) cols = cols3;
-    return cols + y1 + y2 + y3 + 64 + CONV_SPLITK_FLOATS;
+    return cols + y1 + y2 + y3 + 64 + CONV_SPLITK_FLOATS + 64 * 512 + 64 * 576;
 }
 
 int conv_encoder_forward(cudaStream_t st, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
@@ -85,16 +93,22 @@ int conv_encoder_forward(cudaStream_t st, const float* w1, const float* b1, cons
     float* y1 = cols + (colsz + 3) / 4 * 4;
     float* y2 = y1 + m1 * 32;
     float* y3 = y2 + m2 * 64;
-    WsGuard guard(y3 + m3 * 64, CONV_SPLITK_FLOATS);
-    im2col_nchw_kernel<<<grid_for(m1 * k1), 256, 0, st>>>(obs, cols, N, C, H, W, 8, 8, 4, oh1, ow1);
+    float* w2p = y3 + m3 * 64;                       // conv2 / conv3 weights in (ky, kx, c) order
+    float* w3p = w2p + 64 * k2;
+    WsGuard guard(w3p + 64 * k3, CONV_SPLITK_FLOATS);
+    permute_weight_kernel<<<grid_for(64 * k2), 256, 0, st>>>(w2, w2p, 64, 32, 4, 4);
+    TRXL_CHECK_LAUNCH("permute_weight");
+    permute_weight_kernel<<<grid_for(64 * k3), 256, 0, st>>>(w3, w3p, 64, 64, 3, 3);
+    TRXL_CHECK_LAUNCH("permute_weight");
+    im2col_nchw_kernel<<<grid_for(m1 * C * 8), 256, 0, st>>>(obs, cols, N, C, H, W, 8, 8, 4, oh1, ow1);
     TRXL_CHECK_LAUNCH("im2col_nchw");
     TRXL_PROPAGATE(gemm_nt(st, (int)m1, 32, k1, cols, k1, w1, k1, y1, 32, b1, 1));
-    im2col_nhwc_kernel<<<grid_for(m2 * k2), 256, 0, st>>>(y1, cols, N, 32, oh1, ow1, 4, 4, 2, oh2, ow2);
+    im2col_nhwc_kernel<<<grid_for(m2 * k2 / 4), 256, 0, st>>>(y1, cols, N, 32, oh1, ow1, 4, 4, 2, oh2, ow2);
     TRXL_CHECK_LAUNCH("im2col_nhwc");
-    TRXL_PROPAGATE(gemm_nt(st, (int)m2, 64, k2, cols, k2, w2, k2, y2, 64, b2, 1));
-    im2col_nhwc_kernel<<<grid_for(m3 * k3), 256, 0, st>>>(y2, cols, N, 64, oh2, ow2, 3, 3, 1, oh3, ow3);
+    TRXL_PROPAGATE(gemm_nt(st, (int)m2, 64, k2, cols, k2, w2p, k2, y2, 64, b2, 1));
+    im2col_nhwc_kernel<<<grid_for(m3 * k3 / 4), 256, 0, st>>>(y2, cols, N, 64, oh2, ow2, 3, 3, 1, oh3, ow3);
     TRXL_CHECK_LAUNCH("im2col_nhwc");
-    TRXL_PROPAGATE(gemm_nt(st, (int)m3, 64, k3, cols, k3, w3, k3, y3, 64, b3, 1));
+    TRXL_PROPAGATE(gemm_nt(st, (int)m3, 64, k3, cols, k3, w3p, k3, y3, 64, b3, 1));
     nhwc_to_flat_nchw_kernel<<<grid_for(m3 * 64), 256, 0, st>>>(y3, feat, N, oh3 * ow3, 64);
     TRXL_CHECK_LAUNCH("nhwc_to_flat_nchw");
     return TRXL_OK;

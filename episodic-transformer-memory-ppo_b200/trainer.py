@@ -30,7 +30,7 @@ from model import ActorCriticModel
 from optim_native import FusedClipAdamW
 from parallel import DataParallelContext
 from utils import create_env, polynomial_decay, process_episode_info
-from worker import Worker
+from worker import Worker, make_control
 
 
 def build_mask_table(memory_length):
@@ -90,9 +90,12 @@ class PPOTrainer:
         # so the per-step image payload goes env process -> slab -> (DMA) GPU without pickling or staging copies.
         # (pass workers=[] together with trainer.device_feed = SyntheticDeviceFeed(...) to run without env processes)
         self._obs_slab = None
+        self._control = None          # shared-memory stepping arrays (own workers only)
         if workers is None:
             self._obs_slab = torch.zeros((self.num_workers,) + self.obs_shape, dtype=torch.float32).share_memory_()
-            workers = [Worker(self._env_config(w), self._obs_slab, w) for w in range(self.num_workers)]
+            if os.environ.get("TRXL_PIPE_STEPPING", "0") != "1":
+                self._control = make_control(self.num_workers, len(self.action_space_shape))
+            workers = [Worker(self._env_config(w), self._obs_slab, w, self._control) for w in range(self.num_workers)]
             rc = torch.cuda.cudart().cudaHostRegister(self._obs_slab.data_ptr(), self._obs_slab.numel() * 4, 0)
             self._slab_pinned = (int(rc) == 0) if not isinstance(rc, tuple) else (int(rc[0]) == 0)
         self.workers = workers
@@ -332,6 +335,10 @@ class PPOTrainer:
                 stream.synchronize()
                 actions = self._act_pinned.numpy()
                 te = time.perf_counter()
+                if self._control is not None:
+                    self._step_envs_shared(t, actions, episode_infos)
+                    env_time += time.perf_counter() - te
+                    continue
                 for w, worker in enumerate(self.workers):
                     worker.child.send(("step", actions[w].copy()))
                 for w, worker in enumerate(self.workers):
@@ -357,6 +364,32 @@ class PPOTrainer:
         self.timers["env"] += env_time
         self.timers["rollout"] += time.perf_counter() - t0
         return episode_infos
+
+    def _step_envs_shared(self, t, actions, episode_infos):
+        """Step every env worker through the shared-memory fast path (worker.py): publish the actions, bump
+        the command counters, wait for the acknowledgements, then apply the reference's bookkeeping
+        (trainer.py:193-218).  Finished episodes were already reset by their worker; their ``info`` arrives
+        on the pipe."""
+        c, buf, T = self._control, self.buffer, self.config["worker_steps"]
+        c["actions"].numpy()[...] = actions
+        cmd = c["cmd"].numpy()
+        cmd += 1
+        ack = c["ack"].numpy()
+        deadline = time.perf_counter() + 120.0
+        while not np.array_equal(ack, cmd):
+            if time.perf_counter() > deadline:
+                raise RuntimeError("environment workers did not answer within 120 s")
+        buf.rewards[:, t] = c["rewards"].numpy()
+        buf.dones[:, t] = c["dones"].numpy() != 0
+        finished = np.nonzero(c["has_info"].numpy())[0]
+        self._step_host += 1
+        for w in finished:
+            w = int(w)
+            episode_infos.append(self.workers[w].child.recv())
+            self._step_host[w] = 0
+            self._ep_host[w] = self._new_row()
+            if t < T - 1:
+                self._n_episodes = self._n_rows
 
     def _sample_from_device_feed(self, feed):
         """Rollout against a device-resident synthetic feed (device_feed.py): the episode schedule of the

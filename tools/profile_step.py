@@ -47,9 +47,12 @@ def main():
     ap.add_argument("--range", action="store_true", help="bracket a short slice with cudaProfilerStart/Stop for ncu")
     ap.add_argument("--minibatches", type=int, default=2)
     ap.add_argument("--rollout-steps", type=int, default=2)
+    ap.add_argument("--kineto-rollout", default=None, help="per-kernel table of ONE rollout (graphs off) to this file")
     args = ap.parse_args()
     if args.kineto:
         args.kineto = os.path.abspath(args.kineto)
+    if args.kineto_rollout:
+        args.kineto_rollout = os.path.abspath(args.kineto_rollout)
     tr, cfg = build(args.workload)
     update(tr, cfg)                     # warm-up: allocations, cuDNN heuristics, first-touch
     torch.cuda.synchronize()
@@ -62,6 +65,19 @@ def main():
         with open(args.kineto, "w") as f:
             f.write(table)
         print(table[:6000])
+    if args.kineto_rollout:
+        from torch.profiler import ProfilerActivity, profile
+        out = os.path.abspath(args.kineto_rollout) if not os.path.isabs(args.kineto_rollout) else args.kineto_rollout
+        tr.use_cuda_graphs = False
+        tr._sample_training_data()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            tr._sample_training_data()
+            torch.cuda.synchronize()
+        table = prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=100)
+        with open(out, "w") as f:
+            f.write(table)
+        print(table[:200])
     if args.range:
         tr._sample_training_data()
         tr.buffer.prepare_batch_dict()
