@@ -119,6 +119,7 @@ int trxl_layout_groups(const trxl_model_config* cfg) {
     return rc == TRXL_OK ? g : rc;
 }
 int64_t trxl_workspace_floats(const trxl_model_config* cfg, int N) { return model_workspace_floats(cfg, N); }
+int trxl_fused_forward_supported(const trxl_model_config* cfg) { return model_fused_supported(cfg); }
 
 int trxl_model_forward(const trxl_model_config* cfg, const float* params, const float* feat, const float* table, int64_t slots,
                        const int64_t* ep_index, const int64_t* win_index, const uint8_t* mask, const int64_t* pe_index,

@@ -37,13 +37,13 @@ namespace {
 constexpr float LN_EPS = 1e-5f;
 constexpr unsigned FULL = 0xffffffffu;
 
-template <int NV4>
+template <int NV4, bool FULLD>
 __device__ __forceinline__ void load_row(const float* __restrict__ src, const float* __restrict__ pe_row, int D,
                                          int lane, float4 (&x)[NV4]) {
 #pragma unroll
     for (int c = 0; c < NV4; ++c) {
         const int col = c * 128 + lane * 4;
-        if (col < D) {
+        if (FULLD || col < D) {
             x[c] = *reinterpret_cast<const float4*>(src + col);
             if (pe_row) {
                 const float4 p = *reinterpret_cast<const float4*>(pe_row + col);
@@ -103,7 +103,8 @@ __device__ __forceinline__ int packed_holder(int idx) {
 __host__ __device__ constexpr int pow2_at_least(int n) { return n <= 1 ? 1 : (n <= 2 ? 2 : (n <= 4 ? 4 : 8)); }
 
 // stage the sample's mask / window / PE index rows in shared memory; returns all_masked
-__device__ __forceinline__ bool stage_meta(const AttnArgs& a, long long row, long long* s_win, long long* s_pe,
+// (row offsets are float offsets inside the sample's episode / inside the PE table: both fit 32 bits)
+__device__ __forceinline__ bool stage_meta(const AttnArgs& a, long long row, int* s_win, int* s_pe,
                                            unsigned char* s_vis, int* s_flag) {
     const int tid = threadIdx.x;
     if (tid == 0) *s_flag = 0;
@@ -113,8 +114,8 @@ __device__ __forceinline__ bool stage_meta(const AttnArgs& a, long long row, lon
         const unsigned char m = a.mask ? a.mask[row * a.L + l] : 1;
         s_vis[l] = m;
         any |= m;
-        s_win[l] = a.win_index ? a.win_index[row * a.L + l] : (long long)l;
-        s_pe[l] = a.pe_index ? a.pe_index[row * a.L + l] : 0;
+        s_win[l] = (int)((a.win_index ? a.win_index[row * a.L + l] : (long long)l) * a.B * a.D);
+        s_pe[l] = (int)((a.pe_index ? a.pe_index[row * a.L + l] : 0) * a.D);
     }
     if (any) *s_flag = 1;
     __syncthreads();
@@ -127,20 +128,20 @@ __device__ __forceinline__ bool stage_meta(const AttnArgs& a, long long row, lon
 }
 
 // shared-memory carve shared by forward and backward:
-//   win[L] i64 | pe[L] i64 | p[HPW][Lp] f32 | acc[HPW][D] f32 | rowstat[2][Lp] f32 | misc[NW*HPW*2 + 4*HPW] f32 | vis[L] u8
+//   win[L] i32x2-padded | pe[L] i32x2-padded | p[HPW][Lp] f32 | acc[HPW][D] f32 | rowstat[2][Lp] f32 | misc[NW*HPW*2 + 4*HPW] f32 | vis[L] u8
 __host__ __device__ inline size_t attn_smem_bytes(int L, int D, int HPW, int NW) {
     const int Lp = (L + 3) & ~3;
     return (size_t)L * 16 + (size_t)HPW * Lp * 4 + (size_t)HPW * D * 4 + (size_t)2 * Lp * 4 + (size_t)(NW * HPW * 2 + 4 * HPW) * 4 + L + 16;
 }
 
-template <int NV4, int HPW, bool LN, int NW>
+template <int NV4, int HPW, bool LN, int NW, bool FULLD>
 __global__ void __launch_bounds__(NW * 32)
 window_attn_fwd_kernel(const AttnArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Lp = (a.L + 3) & ~3;
-    long long* s_win = reinterpret_cast<long long*>(smem_raw);
-    long long* s_pe = s_win + a.L;
-    float* s_p = reinterpret_cast<float*>(s_pe + a.L);           // energies, then softmax weights [HPW][Lp]
+    int* s_win = reinterpret_cast<int*>(smem_raw);
+    int* s_pe = s_win + 2 * a.L;
+    float* s_p = reinterpret_cast<float*>(s_pe + 2 * a.L);       // energies, then softmax weights [HPW][Lp]
     float* s_ctx = s_p + HPW * Lp;                               // [HPW][D]
     float* s_mu = s_ctx + HPW * a.D;                             // [Lp]   (LN)
     float* s_rstd = s_mu + Lp;                                   // [Lp]   (LN)
@@ -179,9 +180,8 @@ window_attn_fwd_kernel(const AttnArgs a) {
         }
     }
 
-    const float* tab = a.table + ((ep * a.slots) * a.B + a.blk) * (long long)a.D;
-    const long long slot_stride = (long long)a.B * a.D;
-    const float invD = 1.f / (float)a.D;
+    const float* tab = a.table + ((ep * a.slots) * a.B + a.blk) * (long long)a.D;     // row l of the window: tab + s_win[l]
+        const float invD = 1.f / (float)a.D;
     constexpr int NRED = pow2_at_least(HPW + (LN ? 2 : 0));
     const int my_idx = packed_index<NRED>(lane);
     const bool writer = (lane == packed_holder<NRED>(my_idx)) && (my_idx < HPW);
@@ -192,8 +192,8 @@ window_attn_fwd_kernel(const AttnArgs a) {
         const bool v0 = s_vis[l] != 0;
         const bool v1 = (l1 < a.L) && (s_vis[l1] != 0);
         float4 x0[NV4], x1[NV4];
-        if (v0) load_row<NV4>(tab + s_win[l] * slot_stride, a.pe ? a.pe + s_pe[l] * a.D : nullptr, a.D, lane, x0);
-        if (v1) load_row<NV4>(tab + s_win[l1] * slot_stride, a.pe ? a.pe + s_pe[l1] * a.D : nullptr, a.D, lane, x1);
+        if (v0) load_row<NV4, FULLD>(tab + s_win[l], a.pe ? a.pe + s_pe[l] : nullptr, a.D, lane, x0);
+        if (v1) load_row<NV4, FULLD>(tab + s_win[l1], a.pe ? a.pe + s_pe[l1] : nullptr, a.D, lane, x1);
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const bool vis = r ? v1 : v0;
@@ -278,8 +278,8 @@ window_attn_fwd_kernel(const AttnArgs a) {
         const bool v0 = s_vis[l] != 0;
         const bool v1 = (l1 < a.L) && (s_vis[l1] != 0);
         float4 x0[NV4], x1[NV4];
-        if (v0) load_row<NV4>(tab + s_win[l] * slot_stride, a.pe ? a.pe + s_pe[l] * a.D : nullptr, a.D, lane, x0);
-        if (v1) load_row<NV4>(tab + s_win[l1] * slot_stride, a.pe ? a.pe + s_pe[l1] * a.D : nullptr, a.D, lane, x1);
+        if (v0) load_row<NV4, FULLD>(tab + s_win[l], a.pe ? a.pe + s_pe[l] : nullptr, a.D, lane, x0);
+        if (v1) load_row<NV4, FULLD>(tab + s_win[l1], a.pe ? a.pe + s_pe[l1] : nullptr, a.D, lane, x1);
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const bool vis = r ? v1 : v0;
@@ -314,7 +314,7 @@ window_attn_fwd_kernel(const AttnArgs a) {
 #pragma unroll
                 for (int c = 0; c < NV4; ++c) {
                     const int col = c * 128 + lane * 4;
-                    if (col < a.D) {
+                    if (FULLD || col < a.D) {
                         float4* p = reinterpret_cast<float4*>(s_ctx + h * a.D + col);
                         float4 t = *p;
                         t.x += acc[h][c].x; t.y += acc[h][c].y; t.z += acc[h][c].z; t.w += acc[h][c].w;
@@ -342,14 +342,14 @@ window_attn_fwd_kernel(const AttnArgs a) {
 // for a learned positional table, scatter-add d(PE).  The memory rows themselves carry no gradient
 // (reference transformer.py:248: memories are detached inputs).  Single pass: the weights are known.
 // ---------------------------------------------------------------------------------------------
-template <int NV4, int HPW, bool LN, int NW>
+template <int NV4, int HPW, bool LN, int NW, bool FULLD>
 __global__ void __launch_bounds__(NW * 32)
 window_attn_bwd_kernel(const AttnArgs a, const AttnBwdArgs g) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Lp = (a.L + 3) & ~3;
-    long long* s_win = reinterpret_cast<long long*>(smem_raw);
-    long long* s_pe = s_win + a.L;
-    float* s_p = reinterpret_cast<float*>(s_pe + a.L);          // probs [HPW][Lp]
+    int* s_win = reinterpret_cast<int*>(smem_raw);
+    int* s_pe = s_win + 2 * a.L;
+    float* s_p = reinterpret_cast<float*>(s_pe + 2 * a.L);      // probs [HPW][Lp]
     float* s_acc = s_p + HPW * Lp;                              // [HPW][D]
     float* s_unused = s_acc + HPW * a.D;                        // rowstat region (unused here)
     float* s_stat = s_unused + 2 * Lp;                          // [NW][HPW][2]
@@ -407,9 +407,8 @@ window_attn_bwd_kernel(const AttnArgs a, const AttnBwdArgs g) {
 #pragma unroll
         for (int c = 0; c < NV4; ++c) acc[h][c] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const float* tab = a.table + ((ep * a.slots) * a.B + a.blk) * (long long)a.D;
-    const long long slot_stride = (long long)a.B * a.D;
-    const float invD = 1.f / (float)a.D;
+    const float* tab = a.table + ((ep * a.slots) * a.B + a.blk) * (long long)a.D;     // row l of the window: tab + s_win[l]
+        const float invD = 1.f / (float)a.D;
     const float inv_scale = 1.f / a.scale;
     const bool skip_all = all_masked && !need_dx;      // constant energies: no gradient reaches qk
     constexpr int NRED = pow2_at_least(HPW + (LN ? 2 : 0));
@@ -420,8 +419,8 @@ window_attn_bwd_kernel(const AttnArgs a, const AttnBwdArgs g) {
             const bool v0 = s_vis[l] != 0;
             const bool v1 = (l1 < a.L) && (s_vis[l1] != 0);
             float4 x0[NV4], x1[NV4];
-            if (v0) load_row<NV4>(tab + s_win[l] * slot_stride, a.pe ? a.pe + s_pe[l] * a.D : nullptr, a.D, lane, x0);
-            if (v1) load_row<NV4>(tab + s_win[l1] * slot_stride, a.pe ? a.pe + s_pe[l1] * a.D : nullptr, a.D, lane, x1);
+            if (v0) load_row<NV4, FULLD>(tab + s_win[l], a.pe ? a.pe + s_pe[l] : nullptr, a.D, lane, x0);
+            if (v1) load_row<NV4, FULLD>(tab + s_win[l1], a.pe ? a.pe + s_pe[l1] : nullptr, a.D, lane, x1);
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const bool vis = r ? v1 : v0;
@@ -486,7 +485,7 @@ window_attn_bwd_kernel(const AttnArgs a, const AttnBwdArgs g) {
                         dxh[c] = v;
                         if (LN) {
                             const int col = c * 128 + lane * 4;
-                            if (col < a.D) {
+                            if (FULLD || col < a.D) {
                                 const float4 xh = make_float4((x[c].x - mu) * rstd, (x[c].y - mu) * rstd,
                                                               (x[c].z - mu) * rstd, (x[c].w - mu) * rstd);
                                 t1 += v.x + v.y + v.z + v.w;
@@ -502,11 +501,11 @@ window_attn_bwd_kernel(const AttnArgs a, const AttnBwdArgs g) {
                         }
                         t1 *= invD; t2 *= invD;
                     }
-                    float* dst = g.dpe + s_pe[ll] * a.D;
+                    float* dst = g.dpe + s_pe[ll];
 #pragma unroll
                     for (int c = 0; c < NV4; ++c) {
                         const int col = c * 128 + lane * 4;
-                        if (col < a.D) {
+                        if (FULLD || col < a.D) {
                             float4 v = dxh[c];
                             if (LN) {
                                 v.x = rstd * (v.x - t1 - (x[c].x - mu) * rstd * t2);
@@ -537,7 +536,7 @@ window_attn_bwd_kernel(const AttnArgs a, const AttnBwdArgs g) {
 #pragma unroll
                 for (int c = 0; c < NV4; ++c) {
                     const int col = c * 128 + lane * 4;
-                    if (col < a.D) {
+                    if (FULLD || col < a.D) {
                         float4* p = reinterpret_cast<float4*>(s_acc + h * a.D + col);
                         float4 t = *p;
                         t.x += acc[h][c].x; t.y += acc[h][c].y; t.z += acc[h][c].z; t.w += acc[h][c].w;
@@ -568,9 +567,14 @@ template <int NV4, int HPW, bool LN, int NW>
 int launch_fwd_nw(const AttnArgs& a, cudaStream_t st) {
     dim3 grid(a.N, trxl_cdiv(a.H, HPW));
     const size_t smem = attn_smem_bytes(a.L, a.D, HPW, NW);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(window_attn_fwd_kernel<NV4, HPW, LN, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool full = (a.D == NV4 * 128);
+    if (smem > 48 * 1024) {
+        cudaFuncSetAttribute(window_attn_fwd_kernel<NV4, HPW, LN, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(window_attn_fwd_kernel<NV4, HPW, LN, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
     trxl_prof_begin(0, a.N, st);
-    window_attn_fwd_kernel<NV4, HPW, LN, NW><<<grid, NW * 32, smem, st>>>(a);
+    if (full) window_attn_fwd_kernel<NV4, HPW, LN, NW, true><<<grid, NW * 32, smem, st>>>(a);
+    else window_attn_fwd_kernel<NV4, HPW, LN, NW, false><<<grid, NW * 32, smem, st>>>(a);
     trxl_prof_end(0, st);
     TRXL_CHECK_LAUNCH("window_attn_fwd");
     return TRXL_OK;
@@ -592,9 +596,14 @@ int launch_bwd_ln(const AttnArgs& a, const AttnBwdArgs& g, cudaStream_t st) {
     constexpr int NW = 4;
     dim3 grid(a.N, trxl_cdiv(a.H, HPW));
     const size_t smem = attn_smem_bytes(a.L, a.D, HPW, NW);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(window_attn_bwd_kernel<NV4, HPW, LN, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool full = (a.D == NV4 * 128);
+    if (smem > 48 * 1024) {
+        cudaFuncSetAttribute(window_attn_bwd_kernel<NV4, HPW, LN, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(window_attn_bwd_kernel<NV4, HPW, LN, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
     trxl_prof_begin(1, a.N, st);
-    window_attn_bwd_kernel<NV4, HPW, LN, NW><<<grid, NW * 32, smem, st>>>(a, g);
+    if (full) window_attn_bwd_kernel<NV4, HPW, LN, NW, true><<<grid, NW * 32, smem, st>>>(a, g);
+    else window_attn_bwd_kernel<NV4, HPW, LN, NW, false><<<grid, NW * 32, smem, st>>>(a, g);
     trxl_prof_end(1, st);
     TRXL_CHECK_LAUNCH("window_attn_bwd");
     return TRXL_OK;

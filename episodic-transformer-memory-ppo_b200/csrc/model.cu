@@ -15,6 +15,7 @@
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "model.cuh"
+#include "rollout_fused.cuh"
 
 namespace {
 
@@ -281,11 +282,50 @@ long long model_workspace_floats(const trxl_model_config* cfg, int N) {
     return A.total;
 }
 
+static void fill_fused_args(const trxl_model_config* c, const Layout& L, RfArgs& a) {
+    a.D = c->embed_dim; a.H = c->num_heads; a.B = c->num_blocks; a.L = c->memory_length; a.hid = c->hidden_size;
+    a.feat = c->feat_dim; a.sumA = L.sumA; a.ln = c->layer_norm; a.pe_mode = c->pos_enc; a.gtrxl = c->gtrxl;
+    a.Wh = L.Wh; a.bh = L.bh; a.We = L.We; a.be = L.be; a.pos = L.pos < 0 ? 0 : L.pos;
+    a.blk_stride = c->num_blocks > 1 ? L.blk[1].Wv - L.blk[0].Wv : 0;
+    const BlockP& b = L.blk[0];
+    a.b0.Wv = b.Wv; a.b0.Wk = b.Wk; a.b0.Wq = b.Wq; a.b0.Wo = b.Wo; a.b0.bo = b.bo;
+    a.b0.g1 = RfGate{b.g1.Wr, b.g1.Ur, b.g1.Ug, b.g1.bg};
+    a.b0.g2 = RfGate{b.g2.Wr, b.g2.Ur, b.g2.Ug, b.g2.bg};
+    a.b0.n1w = b.n1w; a.b0.n1b = b.n1b; a.b0.n2w = b.n2w; a.b0.n2b = b.n2b; a.b0.nkw = b.nkw; a.b0.nkb = b.nkb;
+    a.b0.Wff = b.Wff; a.b0.bff = b.bff;
+    a.Wp = L.Wp; a.bp = L.bp; a.Wlv = L.Wlv; a.blv = L.blv; a.Wbr = L.Wbr; a.bbr = L.bbr; a.wval = L.wval; a.bval = L.bval;
+}
+
+int model_fused_supported(const trxl_model_config* c) {
+    Layout L;
+    if (build_layout(c, L) != TRXL_OK) return 0;
+    RfArgs a;
+    fill_fused_args(c, L, a);
+    return rollout_fused_supported(a) ? 1 : 0;
+}
+
+// Inference-only forward (no activations saved): the whole trunk in one launch, one CTA per sample.
+static int model_forward_fused(const trxl_model_config* c, const Layout& L, const float* P, const ModelIO& io, float* logits,
+                               float* value, float* out_mem, cudaStream_t st) {
+    RfArgs a;
+    fill_fused_args(c, L, a);
+    a.N = io.N; a.P = P; a.feat_in = io.feat; a.table = io.table; a.slots = io.slots; a.ep_index = io.ep_index;
+    a.win_index = io.win_index; a.mask = io.mask; a.pe_index = c->pos_enc == TRXL_PE_NONE ? nullptr : io.pe_index;
+    a.sample_index = io.sample_index; a.pe_table = io.pe_table; a.logits = logits; a.value = value; a.out_mem = out_mem;
+    return rollout_fused_forward(a, st);
+}
+
 int model_forward(const trxl_model_config* c, const float* P, const ModelIO& io, float* ws, float* logits, float* value,
                   float* out_mem, cudaStream_t st) {
     Layout L;
     TRXL_PROPAGATE(build_layout(c, L));
-    TRXL_CHECK_ARG(P && io.feat && io.table && ws && logits && value && out_mem, "model_forward: null pointer");
+    TRXL_CHECK_ARG(P && io.feat && io.table && logits && value && out_mem, "model_forward: null pointer");
+    if (ws == nullptr) {        // no workspace: inference-only fused path
+        TRXL_CHECK_ARG(io.N > 0, "model_forward: N must be positive");
+        TRXL_CHECK_ARG(c->pos_enc != TRXL_PE_RELATIVE || io.pe_table, "model_forward: relative PE needs pe_table");
+        TRXL_CHECK_ARG(c->pos_enc == TRXL_PE_NONE || io.pe_index, "model_forward: positional encoding needs pe_index");
+        return model_forward_fused(c, L, P, io, logits, value, out_mem, st);
+    }
     TRXL_CHECK_ARG(io.N > 0, "model_forward: N must be positive");
     TRXL_CHECK_ARG(c->pos_enc != TRXL_PE_RELATIVE || io.pe_table, "model_forward: relative PE needs pe_table");
     TRXL_CHECK_ARG(c->pos_enc == TRXL_PE_NONE || io.pe_index, "model_forward: positional encoding needs pe_index");

@@ -18,6 +18,7 @@ struct ModelIO {
 
 int model_layout(const trxl_model_config* cfg, std::vector<trxl_param_entry>& out, long long* total, int* groups);
 long long model_workspace_floats(const trxl_model_config* cfg, int N);
+int model_fused_supported(const trxl_model_config* cfg);
 int model_forward(const trxl_model_config* c, const float* P, const ModelIO& io, float* ws, float* logits, float* value,
                   float* out_mem, cudaStream_t st);
 int model_backward(const trxl_model_config* c, const float* P, float* G, const ModelIO& io, float* ws, const float* out_mem,

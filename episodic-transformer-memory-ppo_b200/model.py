@@ -120,6 +120,8 @@ class ActorCriticModel(nn.Module):
         if missing or extra:
             raise RuntimeError("parameter layout mismatch: missing %s extra %s" % (missing, extra))
         self._trunk_names = {n for n, *_ in self._layout if not n.startswith("conv")}
+        import os
+        self._fused_ok = native.fused_forward_supported(self._cfg) and os.environ.get("TRXL_NO_FUSED_ROLLOUT", "0") != "1"
         self._arena = self._grad_arena = None
         self._pe_cache = None
         self._ws_cache = {}
@@ -213,11 +215,17 @@ class ActorCriticModel(nn.Module):
         return ws[1]
 
     # ------------------------------------------------------------------------------ native trunk
-    def forward_table(self, feat, table, ep_index, win_index, mask, pe_index, sample_index=None, n=None, ws=None, out=None):
+    FUSED_MAX_BATCH = 96      # up to this many samples the one-launch per-sample trunk kernel beats the layered GEMM path
+
+    def forward_table(self, feat, table, ep_index, win_index, mask, pe_index, sample_index=None, n=None, ws=None, out=None,
+                      fused=None):
         """No-grad trunk forward reading memory windows in place from an episode table
-        (E, slots, B, D).  Returns raw (logits (N, sumA), value (N,), new_memory (N, B, D))."""
+        (E, slots, B, D).  Returns raw (logits (N, sumA), value (N,), new_memory (N, B, D)).
+        Small batches (the rollout) take the fused one-launch kernel; `fused=False` forces the layered path."""
         n = feat.shape[0] if n is None else n
-        ws = self.workspace(n) if ws is None else ws
+        if fused is None:
+            fused = self._fused_ok and n <= self.FUSED_MAX_BATCH
+        ws = None if fused else (self.workspace(n) if ws is None else ws)
         logits, value, out_mem = self._alloc_outputs(n, feat.device) if out is None else out
         native.model_forward(self._cfg, self._arena, feat, table, table.shape[1], ep_index, win_index, mask, pe_index,
                              sample_index, self._pe_table(), n, ws, logits, value, out_mem)

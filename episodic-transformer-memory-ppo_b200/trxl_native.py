@@ -48,6 +48,7 @@ SIGNATURES = {
     "trxl_layout_entry": (i32, [CFGP, i32, C.POINTER(ParamEntry)]),
     "trxl_layout_groups": (i32, [CFGP]),
     "trxl_workspace_floats": (i64, [CFGP, i32]),
+    "trxl_fused_forward_supported": (i32, [CFGP]),
     "trxl_model_forward": (i32, [CFGP, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
     "trxl_model_backward": (i32, [CFGP, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]),
     "trxl_conv_encoder_workspace_floats": (i64, [CFGP, i32, i32, i32]),
@@ -169,6 +170,10 @@ def profile_read(kind, min_samples=0):
     _check(load().trxl_profile_read(int(kind), int(min_samples), C.byref(ms), C.byref(launches), C.byref(samples)),
            "trxl_profile_read")
     return ms.value, launches.value, samples.value
+
+
+def fused_forward_supported(cfg):
+    return bool(load().trxl_fused_forward_supported(C.byref(cfg)))
 
 
 def workspace_floats(cfg, n):

@@ -77,6 +77,9 @@ int trxl_layout_groups(const trxl_model_config* cfg);
 /* ---- model forward / backward (everything after the CNN) -------------------------------------- */
 /* floats of workspace needed by trxl_model_forward/backward for N samples */
 int64_t trxl_workspace_floats(const trxl_model_config* cfg, int N);
+/* 1 if trxl_model_forward accepts workspace == NULL for this config: inference-only forward that runs the
+ * whole trunk in ONE launch (one CTA per sample, activations in shared memory) -- the rollout path. */
+int trxl_fused_forward_supported(const trxl_model_config* cfg);
 
 /* Replaces ActorCriticModel.forward from lin_hidden on (model.py:97-110) and Transformer.forward
  * (transformer.py:222-253) including the window gather (utils.py:52-75, buffer.py:90,
@@ -87,7 +90,9 @@ int64_t trxl_workspace_floats(const trxl_model_config* cfg, int N);
  *   mask        (rows, L) bool       pe_index (rows, L)      sample_index (N,) or NULL -> n
  *     (row = sample_index[n]; lets a minibatch address the flat rollout buffer without copies)
  *   pe_table    (max_episode_steps, D) for TRXL_PE_RELATIVE (host-built sinusoid), else NULL
- * Outputs: logits (N, sum A) raw, value (N,), out_mem (N, B, D) = inputs of every block. */
+ * Outputs: logits (N, sum A) raw, value (N,), out_mem (N, B, D) = inputs of every block.
+ * workspace == NULL selects the fused inference path (see trxl_fused_forward_supported); it saves no
+ * activations, so trxl_model_backward cannot follow it. */
 int trxl_model_forward(const trxl_model_config* cfg, const float* params, const float* feat, const float* table,
                        int64_t slots, const int64_t* ep_index, const int64_t* win_index, const uint8_t* mask,
                        const int64_t* pe_index, const int64_t* sample_index, const float* pe_table, int N,

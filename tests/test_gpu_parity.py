@@ -314,3 +314,31 @@ def test_tcgen05_gemm_is_used_when_enabled():
     used = native.tc_gemm_launches() - before
     assert used == (1 if os.environ.get("TRXL_TCGEN05", "0") == "1" else 0)
     assert torch.allclose(y.double(), x.double() @ w.double().t(), atol=2e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("name", golden_names("forward_"))
+def test_fused_and_layered_forward_agree_with_reference(name):
+    """Both inference paths -- the one-launch per-sample trunk kernel (rollout) and the layered GEMM path -- against
+    the reference fixture, on every configuration."""
+    g = load_golden(name)
+    case = name[len("forward_"):]
+    obs_shape = tuple(g["obs"].shape[1:])
+    model, _ = build_model(g, HEADS[case], g["mask"].shape[1], obs_shape, g["action_shape"], g["max_steps"], DEV)
+    assert model._fused_ok
+    with torch.no_grad():
+        feat = model.encode(dev(g["obs"])).clone()
+        mem, mask, idx = dev(g["memory"]), dev(g["mask"].astype(np.uint8)), dev(g["indices"])
+        outs = {}
+        for fused in (True, False):
+            lg, val, nm = model.forward_table(feat, mem, None, None, mask, idx, fused=fused)
+            torch.cuda.synchronize()
+            outs[fused] = (lg.clone(), val.clone(), nm.clone())
+    for fused, (lg, val, nm) in outs.items():
+        np.testing.assert_allclose(val.cpu().numpy(), g["value"], atol=1e-4, err_msg="fused=%s" % fused)
+        np.testing.assert_allclose(nm.cpu().numpy(), g["new_mem"], atol=1e-4, err_msg="fused=%s" % fused)
+        off = 0
+        for k, a in enumerate(g["action_shape"]):
+            z = lg[:, off:off + int(a)]
+            norm = z - z.logsumexp(-1, keepdim=True)
+            np.testing.assert_allclose(norm.cpu().numpy(), g["logits%d" % k], atol=1e-4, err_msg="fused=%s" % fused)
+            off += int(a)

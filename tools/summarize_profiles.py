@@ -86,7 +86,8 @@ def main():
             fdst.write(fsrc.read())
         print("wrote kineto table")
     for rep, title in (("attn_%s" % args.round, "fused window attention fwd/bwd, training minibatch (N=2048, L=128, D=256, H=4)"),
-                       ("sgemm_%s" % args.round, "SIMT sgemm launches: 1 rollout step (M=32) + 1 minibatch step (M=2048)")):
+                       ("sgemm_%s" % args.round, "SIMT sgemm launches: 1 rollout step (M=32) + 1 minibatch step (M=2048)"),
+                       ("tcgemm_%s" % args.round, "tcgen05 3xTF32 GEMM (opt-in), linear forward M=2048 N=256 K=256")):
         p = os.path.join(args.src, rep + ".ncu-rep")
         if os.path.exists(p):
             ncu_report(p, os.path.join(dst, "%s_ncu_%s.txt" % (args.round, rep.split("_")[0])), title)
