@@ -121,7 +121,9 @@ class ActorCriticModel(nn.Module):
             raise RuntimeError("parameter layout mismatch: missing %s extra %s" % (missing, extra))
         self._trunk_names = {n for n, *_ in self._layout if not n.startswith("conv")}
         import os
-        self._fused_ok = native.fused_forward_supported(self._cfg) and os.environ.get("TRXL_NO_FUSED_ROLLOUT", "0") != "1"
+        # the one-launch per-sample trunk kernel (csrc/rollout_fused.cu) is correct but, as measured on B200 (r1), still
+        # slower than the layered path at W=32 (latency-bound GEMV chains); opt in with TRXL_FUSED_ROLLOUT=1
+        self._fused_ok = native.fused_forward_supported(self._cfg) and os.environ.get("TRXL_FUSED_ROLLOUT", "0") == "1"
         self._arena = self._grad_arena = None
         self._pe_cache = None
         self._ws_cache = {}
@@ -215,13 +217,13 @@ class ActorCriticModel(nn.Module):
         return ws[1]
 
     # ------------------------------------------------------------------------------ native trunk
-    FUSED_MAX_BATCH = 96      # up to this many samples the one-launch per-sample trunk kernel beats the layered GEMM path
+    FUSED_MAX_BATCH = 96      # batch sizes eligible for the opt-in one-launch per-sample trunk kernel
 
     def forward_table(self, feat, table, ep_index, win_index, mask, pe_index, sample_index=None, n=None, ws=None, out=None,
                       fused=None):
         """No-grad trunk forward reading memory windows in place from an episode table
         (E, slots, B, D).  Returns raw (logits (N, sumA), value (N,), new_memory (N, B, D)).
-        Small batches (the rollout) take the fused one-launch kernel; `fused=False` forces the layered path."""
+        `fused=True` runs the one-launch per-sample kernel (inference only: it saves no activations)."""
         n = feat.shape[0] if n is None else n
         if fused is None:
             fused = self._fused_ok and n <= self.FUSED_MAX_BATCH
