@@ -40,9 +40,9 @@ sgemm_kernel(const GemmArgs g) {
 
     constexpr int A_V4 = BM * BK / 4, B_V4 = BN * BK / 4;
     constexpr int A_PER = (A_V4 + NT - 1) / NT, B_PER = (B_V4 + NT - 1) / NT;
-    float4 ra[A_PER], rb[B_PER];
+    float4 ra0[A_PER], rb0[B_PER], ra1[A_PER], rb1[B_PER];      // two register stages: tiles kt+1 and kt+2 in flight
 
-    auto load_a = [&](int k0) {
+    auto load_a = [&](int k0, float4 (&ra)[A_PER]) {
 #pragma unroll
         for (int i = 0; i < A_PER; ++i) {
             const int v = tid + i * NT;
@@ -77,7 +77,7 @@ sgemm_kernel(const GemmArgs g) {
             ra[i] = val;
         }
     };
-    auto load_b = [&](int k0) {
+    auto load_b = [&](int k0, float4 (&rb)[B_PER]) {
 #pragma unroll
         for (int i = 0; i < B_PER; ++i) {
             const int v = tid + i * NT;
@@ -112,7 +112,7 @@ sgemm_kernel(const GemmArgs g) {
             rb[i] = val;
         }
     };
-    auto store_tiles = [&](int buf) {
+    auto store_tiles = [&](int buf, const float4 (&ra)[A_PER], const float4 (&rb)[B_PER]) {
 #pragma unroll
         for (int i = 0; i < A_PER; ++i) {
             const int v = tid + i * NT;
@@ -150,16 +150,7 @@ sgemm_kernel(const GemmArgs g) {
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
     const int nk = (k_end - k_begin + BK - 1) / BK;
-    load_a(k_begin);
-    load_b(k_begin);
-    store_tiles(0);
-    __syncthreads();
-    for (int kt = 0; kt < nk; ++kt) {
-        const int buf = kt & 1;
-        if (kt + 1 < nk) {
-            load_a(k_begin + (kt + 1) * BK);
-            load_b(k_begin + (kt + 1) * BK);
-        }
+    auto compute = [&](int buf) {
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
             float a[TM], bb[TN];
@@ -172,9 +163,26 @@ sgemm_kernel(const GemmArgs g) {
 #pragma unroll
                 for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
         }
+    };
+    // software pipeline: tile kt is computed from shared memory while kt+1 and kt+2 are in flight in registers
+    load_a(k_begin, ra0); load_b(k_begin, rb0);
+    store_tiles(0, ra0, rb0);
+    if (nk > 1) { load_a(k_begin + BK, ra1); load_b(k_begin + BK, rb1); }
+    __syncthreads();
+    for (int kt = 0; kt < nk; kt += 2) {
+        // even step: shared buffer 0, tile kt+1 waits in stage 1, tile kt+2 is issued into stage 0
+        if (kt + 2 < nk) { load_a(k_begin + (kt + 2) * BK, ra0); load_b(k_begin + (kt + 2) * BK, rb0); }
+        compute(0);
         if (kt + 1 < nk) {
-            store_tiles(buf ^ 1);
+            store_tiles(1, ra1, rb1);
             __syncthreads();
+            // odd step: shared buffer 1, tile kt+2 waits in stage 0, tile kt+3 is issued into stage 1
+            if (kt + 3 < nk) { load_a(k_begin + (kt + 3) * BK, ra1); load_b(k_begin + (kt + 3) * BK, rb1); }
+            compute(1);
+            if (kt + 2 < nk) {
+                store_tiles(0, ra0, rb0);
+                __syncthreads();
+            }
         }
     }
 

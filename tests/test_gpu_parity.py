@@ -322,12 +322,12 @@ def test_tcgen05_gemm_is_used_when_enabled():
     assert torch.allclose(y.double(), x.double() @ w.double().t(), atol=2e-4, rtol=1e-4)
 
 
-@pytest.mark.parametrize("name", golden_names("forward_"))
 def native_fused_supported(model):
     import trxl_native as native
     return native.fused_forward_supported(model._cfg)
 
 
+@pytest.mark.parametrize("name", golden_names("forward_"))
 def test_fused_and_layered_forward_agree_with_reference(name):
     """Both inference paths -- the one-launch per-sample trunk kernel (rollout) and the layered GEMM path -- against
     the reference fixture, on every configuration."""
