@@ -162,9 +162,13 @@ def run_reference(args, cfg, name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals, detail = [], None
+    vals, detail, threads = [], None, None
+    many = args.steps + args.warmup > 4
     for i in range(args.warmup + args.steps):
-        v, detail = cpu_reference_sample(cfg, rollout_steps=4 if args.steps + args.warmup > 4 else 8, seed=i)
+        # the thread-count probe runs once (first step); later steps reuse its choice so K steps stay within minutes
+        v, detail = cpu_reference_sample(cfg, rollout_steps=4 if many else 8, seed=i, threads=threads,
+                                         mb_sample=256 if many else 512, reps=1 if many else 2)
+        threads = detail["threads"]
         if i >= args.warmup:
             vals.append(v)
     value = float(np.mean(vals))

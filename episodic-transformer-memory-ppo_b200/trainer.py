@@ -142,6 +142,7 @@ class PPOTrainer:
         self._ctx = None
         self.use_cuda_graphs = os.environ.get("TRXL_NO_GRAPHS", "0") != "1"
         self._graphs, self._graph_pool, self._capture_stream = {}, None, None
+        self._start_update = 0          # first update of run_training (advanced by load_checkpoint)
         self.device_feed = None         # optional device_feed.SyntheticDeviceFeed replacing the env workers (bench.py)
         self._forced_actions = None     # optional (T, W, n_branches) int64 device tensor: replay these actions (parity tests)
         self.timers = {"rollout": 0.0, "train": 0.0, "env": 0.0}
@@ -192,7 +193,8 @@ class PPOTrainer:
         if self.dp.rank == 0:
             print("Starting training on %s (%d rank%s)" % (self.device, self.dp.world_size, "" if self.dp.world_size == 1 else "s"))
         episode_infos = deque(maxlen=100)
-        for update in range(self.config["updates"]):
+        for update in range(self._start_update, self.config["updates"]):
+            self._start_update = update + 1
             lr = polynomial_decay(self.lr_schedule["initial"], self.lr_schedule["final"], self.lr_schedule["max_decay_steps"],
                                   self.lr_schedule["power"], update)
             beta = polynomial_decay(self.beta_schedule["initial"], self.beta_schedule["final"],
@@ -599,6 +601,22 @@ class PPOTrainer:
         with open("./models/" + self.run_id + ".nn", "wb") as f:
             pickle.dump((state, self.config), f)
         print("Model saved to ./models/" + self.run_id + ".nn")
+
+    def save_checkpoint(self, path):
+        """Everything needed to resume: parameters, AdamW moments/step, next update index, config.  (The
+        reference only saves ``(state_dict, config)`` at the end and cannot resume; that format is ``_save_model``.)"""
+        state = {"state_dict": {k: v.detach().cpu().clone() for k, v in self.model.state_dict().items()},
+                 "optimizer": self.optimizer.state_dict(), "next_update": self._start_update, "config": self.config}
+        with open(path, "wb") as f:
+            pickle.dump(state, f)
+
+    def load_checkpoint(self, path):
+        with open(path, "rb") as f:
+            state = pickle.load(f)
+        self.model.load_state_dict(state["state_dict"])
+        self.optimizer.load_state_dict(state["optimizer"])
+        self._start_update = int(state.get("next_update", 0))
+        return state
 
     def close(self, exit_process=True):
         """Shut down workers and the summary writer (trainer.py:364-383; the reference also exits the process)."""
