@@ -75,6 +75,51 @@ int64_t trxl_launch_count(void) { return g_trxl_launches; }
 extern long long g_trxl_tc_launches;
 int64_t trxl_tc_gemm_launches(void) { return g_trxl_tc_launches; }
 
+// ---- CUDA graph capture of a sequence of this library's launches (rollout step replay) ----
+int trxl_graph_begin(void* stream) {
+    cudaError_t e = cudaStreamBeginCapture(S(stream), cudaStreamCaptureModeRelaxed);
+    if (e != cudaSuccess) { trxl_set_error("graph_begin: %s", cudaGetErrorString(e)); return TRXL_ERR_CUDA; }
+    return TRXL_OK;
+}
+int trxl_graph_end(void* stream, void** graph_exec_out) {
+    TRXL_CHECK_ARG(graph_exec_out, "graph_end: null output");
+    *graph_exec_out = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(S(stream), &graph);
+    if (e != cudaSuccess || !graph) {
+        cudaGetLastError();
+        trxl_set_error("graph_end: capture failed: %s", cudaGetErrorString(e));
+        return TRXL_ERR_CUDA;
+    }
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { trxl_set_error("graph_end: instantiate failed: %s", cudaGetErrorString(e)); return TRXL_ERR_CUDA; }
+    *graph_exec_out = exec;
+    return TRXL_OK;
+}
+int trxl_graph_launch(void* graph_exec, void* stream) {
+    TRXL_CHECK_ARG(graph_exec, "graph_launch: null graph");
+    cudaError_t e = cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(graph_exec), S(stream));
+    if (e != cudaSuccess) { trxl_set_error("graph_launch: %s", cudaGetErrorString(e)); return TRXL_ERR_CUDA; }
+    return TRXL_OK;
+}
+int trxl_graph_destroy(void* graph_exec) {
+    if (graph_exec) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(graph_exec));
+    return TRXL_OK;
+}
+// dst[r, :row_bytes] = src[r, :row_bytes] for strided rows (buffer[:, t] = x without a torch op inside a capture)
+int trxl_copy_rows(const void* src, void* dst, int64_t rows, int64_t row_bytes, int64_t src_stride_bytes, int64_t dst_stride_bytes,
+                   void* stream) {
+    TRXL_CHECK_ARG(src && dst && rows >= 0 && row_bytes >= 0, "copy_rows: bad arguments");
+    if (rows == 0 || row_bytes == 0) return TRXL_OK;
+    cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)dst_stride_bytes, src, (size_t)src_stride_bytes, (size_t)row_bytes, (size_t)rows,
+                                      cudaMemcpyDeviceToDevice, S(stream));
+    ++g_trxl_launches;
+    if (e != cudaSuccess) { trxl_set_error("copy_rows: %s", cudaGetErrorString(e)); return TRXL_ERR_CUDA; }
+    return TRXL_OK;
+}
+
 int trxl_profile_enable(int on) {
     g_prof_on = on != 0;
     if (on) { g_prof_count[0] = 0; g_prof_count[1] = 0; }

@@ -261,34 +261,36 @@ class PPOTrainer:
             return self._device_step(t, obs_dev, step_dev, ep_dev, ctx)
         key = self._graph_key(mode)
         if self._graphs.get("key") != key:                       # table or parameter arena moved: start over
+            for old in self._graphs.get("steps", {}).values():
+                native.graph_destroy(old)
             self._graphs = {"key": key, "warm": 0, "steps": {}}
         if self._graphs["warm"] < 1:                             # first rollout for this key runs eagerly (warm-up)
             return self._device_step(t, obs_dev, step_dev, ep_dev, ctx)
         g = self._graphs["steps"].get(t)
         if g is None:
+            # Capture through the library's own graph API: the step consists only of libtrxlppo launches (no torch
+            # op, no allocation, no RNG inside), so nothing of torch's capture machinery is involved.
+            if self._capture_stream is None:
+                self._capture_stream = torch.cuda.Stream(device=self.device)
+            cs = self._capture_stream
+            cs.wait_stream(torch.cuda.current_stream())
             try:
-                if self._graph_pool is None:
-                    self._graph_pool = torch.cuda.graph_pool_handle()
-                    self._capture_stream = torch.cuda.Stream(device=self.device)
-                g = torch.cuda.CUDAGraph()
-                cs = self._capture_stream
-                cs.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(cs):
-                    g.capture_begin(pool=self._graph_pool)
-                    self._device_step(t, obs_dev, step_dev, ep_dev, ctx)
-                    g.capture_end()
+                    native.graph_begin(cs.cuda_stream)
+                    try:
+                        self._device_step(t, obs_dev, step_dev, ep_dev, ctx)
+                        g = native.graph_end(cs.cuda_stream)
+                    except Exception:
+                        native.graph_abort(cs.cuda_stream)
+                        raise
                 torch.cuda.current_stream().wait_stream(cs)
                 self._graphs["steps"][t] = g
             except Exception as e:  # noqa: BLE001 -- capture is an optimisation; the eager path is the same kernels
-                try:
-                    g.capture_end()                              # leave capture mode even if the capture is invalid
-                except Exception:  # noqa: BLE001
-                    pass
                 torch.cuda.synchronize()
                 print("[trxl] CUDA-graph capture failed (%s); continuing with eager launches" % e)
                 self.use_cuda_graphs = False
                 return self._device_step(t, obs_dev, step_dev, ep_dev, ctx)
-        g.replay()
+        native.graph_launch(g)
 
     def _graphs_finish_rollout(self, mode):
         if self.use_cuda_graphs and self._graphs.get("key") == self._graph_key(mode):
@@ -300,7 +302,8 @@ class PPOTrainer:
         sample actions, store actions / log-probs / values."""
         buf, model = self.buffer, self.model
         W, T, L, nb = self.num_workers, self.config["worker_steps"], self.memory_length, len(self.action_space_shape)
-        buf.obs[:, t] = obs_dev
+        obs_bytes = int(np.prod(self.obs_shape)) * 4
+        native.copy_rows(obs_dev.data_ptr(), buf.obs.data_ptr() + t * obs_bytes, W, obs_bytes, obs_bytes, T * obs_bytes)
         native.rollout_prepare(step_dev, ep_dev, self._mask_table_dev, self._index_table_dev,
                                ctx["flat_mask"].data_ptr() + t * L, T * L, ctx["flat_idx"].data_ptr() + t * L * 8, T * L,
                                ctx["flat_ep"].data_ptr() + t * 8, T, W, L)
@@ -312,7 +315,7 @@ class PPOTrainer:
         forced = None if self._forced_actions is None else self._forced_actions[t]
         native.sample_actions(logits, ctx["uniforms"][t], self.action_space_shape, buf.actions.data_ptr() + t * nb * 8, T * nb,
                               buf.log_probs.data_ptr() + t * nb * 4, T * nb, self._act_dev, W, forced=forced)
-        buf.values[:, t] = value
+        native.copy_rows(value.data_ptr(), buf.values.data_ptr() + t * 4, W, 4, 4, T * 4)
 
     def _sample_training_data(self):
         """Run every worker for ``worker_steps`` steps (trainer.py:145-225)."""

@@ -43,6 +43,11 @@ SIGNATURES = {
     "trxl_tc_gemm_launches": (i64, []),
     "trxl_profile_enable": (i32, [i32]),
     "trxl_profile_read": (i32, [i32, i32, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "trxl_graph_begin": (i32, [vp]),
+    "trxl_graph_end": (i32, [vp, C.POINTER(C.c_void_p)]),
+    "trxl_graph_launch": (i32, [vp, vp]),
+    "trxl_graph_destroy": (i32, [vp]),
+    "trxl_copy_rows": (i32, [vp, vp, i64, i64, i64, i64, vp]),
     "trxl_layout_num_entries": (i32, [CFGP]),
     "trxl_layout_total_floats": (i64, [CFGP]),
     "trxl_layout_entry": (i32, [CFGP, i32, C.POINTER(ParamEntry)]),
@@ -154,6 +159,36 @@ def layout(cfg):
 
 def launch_count():
     return int(load().trxl_launch_count())
+
+
+def graph_begin(stream_handle):
+    _check(load().trxl_graph_begin(stream_handle), "trxl_graph_begin")
+
+
+def graph_end(stream_handle):
+    out = C.c_void_p(None)
+    _check(load().trxl_graph_end(stream_handle, C.byref(out)), "trxl_graph_end")
+    return out.value
+
+
+def graph_abort(stream_handle):
+    out = C.c_void_p(None)
+    load().trxl_graph_end(stream_handle, C.byref(out))
+    if out.value:
+        load().trxl_graph_destroy(out.value)
+
+
+def graph_launch(graph_exec):
+    _check(load().trxl_graph_launch(graph_exec, _stream()), "trxl_graph_launch")
+
+
+def graph_destroy(graph_exec):
+    load().trxl_graph_destroy(graph_exec)
+
+
+def copy_rows(src_ptr, dst_ptr, rows, row_bytes, src_stride_bytes, dst_stride_bytes):
+    _check(load().trxl_copy_rows(src_ptr, dst_ptr, int(rows), int(row_bytes), int(src_stride_bytes), int(dst_stride_bytes), _stream()),
+           "trxl_copy_rows")
 
 
 def tc_gemm_launches():

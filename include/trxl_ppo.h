@@ -65,6 +65,16 @@ int64_t trxl_tc_gemm_launches(void);
 int trxl_profile_enable(int on);
 int trxl_profile_read(int kind, int min_samples, double* total_ms, int64_t* launches, int64_t* samples);
 
+/* Capture / replay of a sequence of this library's launches as a CUDA graph (the ~45 launches of one rollout step).
+ * `stream` must be a non-default stream for begin/end; only calls of this library may be issued in between. */
+int trxl_graph_begin(void* stream);
+int trxl_graph_end(void* stream, void** graph_exec_out);
+int trxl_graph_launch(void* graph_exec, void* stream);
+int trxl_graph_destroy(void* graph_exec);
+/* dst[r, 0:row_bytes] = src[r, 0:row_bytes] for `rows` strided rows (device to device) */
+int trxl_copy_rows(const void* src, void* dst, int64_t rows, int64_t row_bytes, int64_t src_stride_bytes, int64_t dst_stride_bytes,
+                   void* stream);
+
 /* ---- parameter arena layout ------------------------------------------------------------------ */
 /* Number of entries / total floats of the arena for a config (<0 on invalid config). */
 int trxl_layout_num_entries(const trxl_model_config* cfg);
