@@ -93,7 +93,10 @@ class PPOTrainer:
         self._control = None          # shared-memory stepping arrays (own workers only)
         if workers is None:
             self._obs_slab = torch.zeros((self.num_workers,) + self.obs_shape, dtype=torch.float32).share_memory_()
-            if os.environ.get("TRXL_PIPE_STEPPING", "0") != "1":
+            # spin-wait stepping needs a core per env process; when the box is oversubscribed (many ranks x workers)
+            # fall back to the blocking pipe protocol, where waiting processes sleep in the kernel
+            procs = self.dp.world_size * (self.num_workers + 1)
+            if os.environ.get("TRXL_PIPE_STEPPING", "0") != "1" and 1.25 * procs <= (os.cpu_count() or 1):
                 self._control = make_control(self.num_workers, len(self.action_space_shape))
             workers = [Worker(self._env_config(w), self._obs_slab, w, self._control) for w in range(self.num_workers)]
             rc = torch.cuda.cudart().cudaHostRegister(self._obs_slab.data_ptr(), self._obs_slab.numel() * 4, 0)

@@ -240,9 +240,14 @@ def test_trainer_two_updates_vs_reference(name, tmp_path, monkeypatch):
 
 
 # ------------------------------------------------------------------------------------------------ BASELINE-sized shapes
-@pytest.mark.parametrize("n,ln,pe,gtrxl", [(32, "post", "relative", False), (300, "post", "relative", False),
-                                           (32, "pre", "learned", True), (130, "pre", "relative", True)])
-def test_forward_backward_c3_dims_vs_oracle(n, ln, pe, gtrxl):
+@pytest.mark.parametrize("n,ln,pe,gtrxl,dims", [
+    (32, "post", "relative", False, (128, 256, 4, 4)), (300, "post", "relative", False, (128, 256, 4, 4)),
+    (32, "pre", "learned", True, (128, 256, 4, 4)), (130, "pre", "relative", True, (128, 256, 4, 4)),
+    (40, "post", "relative", True, (256, 384, 4, 3)),        # c4-like: L=256, D=384 (3 float4 per lane, 2 heads per pass)
+    (24, "pre", "relative", False, (512, 512, 8, 2)),        # c5-like: L=512, D=512, 8 heads
+    (20, "pre", "learned", False, (118, 384, 4, 2)),         # mortar_mayhem_grid.yaml: L=118 (not a multiple of 4)
+])
+def test_forward_backward_c3_dims_vs_oracle(n, ln, pe, gtrxl, dims):
     """c3 dimensions (L=128, D=256, H=4, B=4, lin_hidden K=3136 fed directly as a vector observation) at rollout and
     training batch sizes: exercises the skinny / split-K / tiled GEMM paths and the 128-slot window kernel against the
     CPU oracle (forward 1e-4; gradients 2e-4 of the tensor max)."""
@@ -251,7 +256,8 @@ def test_forward_backward_c3_dims_vs_oracle(n, ln, pe, gtrxl):
     from oracle import trxl_oracle as X
     from parity_util import _Space
     torch.manual_seed(n)
-    L, D, H, B, M, feat, hid = 128, 256, 4, 4, 256, 3136, 384
+    (L, D, H, B), feat, hid = dims, 3136, 384
+    M = 2 * L
     cfg = {"hidden_layer_size": hid, "value_loss_coefficient": 0.5, "max_grad_norm": 0.5,
            "transformer": {"num_blocks": B, "embed_dim": D, "num_heads": H, "memory_length": L, "positional_encoding": pe,
                            "layer_norm": ln, "gtrxl": gtrxl, "gtrxl_bias": 0.5}}
