@@ -6,6 +6,7 @@
 #include "../../include/trxl_ppo.h"
 #include "attention.cuh"
 #include "conv.cuh"
+#include "tc_conv.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "model.cuh"
@@ -205,6 +206,50 @@ int trxl_conv_encoder_forward(const trxl_model_config* cfg, const float* params,
     for (int i = 0; i < 6; ++i) TRXL_CHECK_ARG(off[i] >= 0, "conv_encoder: parameter %s missing from the layout", names[i]);
     return conv_encoder_forward(S(stream), params + off[0], params + off[1], params + off[2], params + off[3], params + off[4],
                                 params + off[5], obs, N, cfg->conv_in_channels, H, W, workspace, feat);
+}
+
+static int conv_param_offsets(const trxl_model_config* cfg, long long (&off)[6]) {
+    std::vector<trxl_param_entry> e;
+    TRXL_PROPAGATE(model_layout(cfg, e, nullptr, nullptr));
+    const char* names[6] = {"conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias", "conv3.weight", "conv3.bias"};
+    for (int i = 0; i < 6; ++i) off[i] = -1;
+    for (const auto& en : e)
+        for (int i = 0; i < 6; ++i)
+            if (strcmp(en.name, names[i]) == 0) off[i] = en.offset;
+    for (int i = 0; i < 6; ++i) TRXL_CHECK_ARG(off[i] >= 0, "conv_train: parameter %s missing from the layout", names[i]);
+    return TRXL_OK;
+}
+
+int trxl_conv_train_supported(const trxl_model_config* cfg, int H, int W) {
+    if (!cfg || cfg->conv_in_channels <= 0) return 0;
+    return tc_conv_supported(cfg->conv_in_channels, H, W);
+}
+
+int64_t trxl_conv_train_workspace_floats(const trxl_model_config* cfg, int N, int H, int W) {
+    if (!cfg || cfg->conv_in_channels <= 0 || N < 0) return -1;
+    return tc_conv_workspace_floats(N, cfg->conv_in_channels, H, W);
+}
+
+int trxl_conv_train_forward(const trxl_model_config* cfg, const float* params, const float* obs, const int64_t* sample_index, int N,
+                            int H, int W, float* workspace, float* feat, void* stream) {
+    TRXL_CHECK_ARG(cfg && cfg->conv_in_channels > 0, "conv_train: config has no convolutional encoder");
+    TRXL_CHECK_ARG(params && obs && workspace && feat, "conv_train: null pointer");
+    long long off[6];
+    TRXL_PROPAGATE(conv_param_offsets(cfg, off));
+    const float* p[6];
+    for (int i = 0; i < 6; ++i) p[i] = params + off[i];
+    return tc_conv_forward(S(stream), p, obs, (cll)sample_index, N, cfg->conv_in_channels, H, W, workspace, feat);
+}
+
+int trxl_conv_train_backward(const trxl_model_config* cfg, float* grads, int N, int H, int W, float* workspace, const float* dfeat,
+                             void* stream) {
+    TRXL_CHECK_ARG(cfg && cfg->conv_in_channels > 0, "conv_train: config has no convolutional encoder");
+    TRXL_CHECK_ARG(grads && workspace && dfeat, "conv_train: null pointer");
+    long long off[6];
+    TRXL_PROPAGATE(conv_param_offsets(cfg, off));
+    float* g[6];
+    for (int i = 0; i < 6; ++i) g[i] = grads + off[i];
+    return tc_conv_backward(S(stream), g, N, cfg->conv_in_channels, H, W, workspace, dfeat);
 }
 
 static AttnArgs make_attn(const float* table, int64_t slots, int num_blocks, int block, const int64_t* ep_index,

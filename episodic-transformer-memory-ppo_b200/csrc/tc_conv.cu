@@ -1,0 +1,626 @@
+// Training path of the CNN encoder (reference model.py:27-38,87-94 and its autograd backward) on the 5th-gen tensor
+// cores: every convolution pass is an implicit GEMM issued as tcgen05.mma.kind::tf32 with fp32-grade accuracy (3xTF32).
+//
+// Why: at the reference's c3 workload the encoder is 58 % of a PPO minibatch step on cuDNN's fp32 SIMT kernels
+// (profiles/r1_launches_c3.txt).  The fp32 parity contract (1e-4 against the CPU reference) rules out single-pass TF32,
+// so every activation / gradient / weight tensor is kept *pre-split* as hi = tf32(x), lo = tf32(x - hi) (two fp32-sized
+// planes written by the producing kernel's epilogue) and each MMA step issues hi*hi + lo*hi + hi*lo into the fp32 TMEM
+// accumulator.  Pre-splitting is what makes the producers cheap: operands are already in tensor-core format, so a tile is
+// filled with plain 16-byte cp.async copies -- no register staging, no conversion in the main loop.
+//
+// Kernels (geometry in tc_conv_geom.h; one CTA = 160 threads = 4 producer/epilogue warps + 1 MMA warp):
+//   tc_conv_gather_kernel  C[rows, BN] = gather(A)[rows, K] * W[BN, K]^T, both operands K-major in shared memory.
+//                          forward convs (bias + ReLU epilogue) and data gradients (ReLU-mask epilogue); the stride-2
+//                          data gradient runs as four parity classes.  Out-of-image taps are zero-filled by cp.async.
+//   tc_conv_wgrad_kernel   dW[K, BN] = gather(A)[rows, K]^T * dY[rows, BN]: the reduction runs over the GEMM rows, so both
+//                          operands are MN-major in shared memory (same 128-byte global runs as the forward gather);
+//                          rows are split across CTAs and the partials summed in fixed order (deterministic).
+// Pipeline per CTA: STAGES-deep ring; producers cp.async a stage, cp.async.wait_group, fence.proxy.async, arrive on the
+// stage's `full` mbarrier; the MMA lane waits, issues the stage's MMAs and tcgen05.commit's the `empty` mbarrier.
+#include "tc_conv.cuh"
+
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int BM = 128, BK = TCG_BK, THREADS = 160, STAGES = 4;
+
+struct GatherArgs {
+    TcgGather g;
+    TcgScatter s;
+    const float* a_hi; const float* a_lo;       // gathered image, pre-split
+    const long long* sample_index;              // optional: image n of the row grid reads image sample_index[n]
+    const float* b_hi; const float* b_lo;       // weights [BN][K], pre-split
+    const float* bias;                          // [BN] or null
+    int relu;
+    const float* mask;                          // optional image with the output geometry: result kept where mask > 0
+    float* out_hi; float* out_lo; float* out_plain;     // any may be null
+    long long M;
+};
+
+struct WgradArgs {
+    TcgGather g;
+    const float* a_hi; const float* a_lo;
+    const long long* sample_index;
+    const float* dy_hi; const float* dy_lo;     // [M][BN], pre-split
+    long long M;
+    int rows_per_split;                         // multiple of 32; every split is non-empty
+    float* partial;                             // [splits][K][BN]
+};
+
+__device__ __forceinline__ void stage_taps(const TcgGather& g, int* s_tapoff, int* s_dy, int* s_dx) {
+    if (threadIdx.x < g.nkb) {
+        const int kb = threadIdx.x;
+        s_dy[kb] = g.tap_dy[kb];
+        s_dx[kb] = g.tap_dx[kb];
+        s_tapoff[kb] = (g.tap_dy[kb] * g.img_w + g.tap_dx[kb]) * g.img_c + g.tap_c0[kb];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(THREADS, 1) tc_conv_gather_kernel(const __grid_constant__ GatherArgs a) {
+    extern __shared__ __align__(1024) unsigned char tcc_smem[];
+    constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    constexpr int P = STAGES - 1;                                    // stages in flight ahead of the MMA
+    uint64_t* full = reinterpret_cast<uint64_t*>(tcc_smem + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    __shared__ int s_tapoff[TCG_MAX_KB], s_dy[TCG_MAX_KB], s_dx[TCG_MAX_KB];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long m0 = (long long)blockIdx.x * BM;
+    const int nkb = a.g.nkb;
+    stage_taps(a.g, s_tapoff, s_dy, s_dx);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 4); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        mbar_init_fence();
+    }
+    if (warp == 4) tmem_alloc(tmem_slot, BN);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t smem_base = smem_u32(tcc_smem);
+
+    if (warp < 4) {
+        // ---------------- producers: one GEMM row per thread ----------------
+        const int r = threadIdx.x;
+        const long long m = m0 + r;
+        const bool row_ok = m < a.M;
+        int n = 0, ry = 0, rx = 0;
+        if (row_ok) tcg_row(a.g, m, n, ry, rx);
+        const long long img = (row_ok && a.sample_index) ? a.sample_index[n] : n;
+        const int ay = ry * a.g.rstride, ax = rx * a.g.rstride;
+        const long long base = ((img * a.g.img_h + ay) * a.g.img_w + ax) * a.g.img_c;
+        const uint32_t row_off = (uint32_t)((r >> 3) * 128 + (r & 7) * 16);     // K-major core-matrix layout, bytes
+        const int K = nkb * BK;
+        for (int it = 0; it < nkb + P; ++it) {
+            if (it < nkb) {
+                const int s = it % STAGES;
+                mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                const int sy = ay + s_dy[it], sx = ax + s_dx[it];
+                const bool ok = row_ok && sy >= 0 && sy < a.g.img_h && sx >= 0 && sx + a.g.run_px <= a.g.img_w;
+                const long long off = ok ? base + s_tapoff[it] : 0;
+                const uint32_t nbytes = ok ? 16u : 0u;
+                const uint32_t dst = smem_base + s * STAGE_BYTES + row_off;
+                const float* ah = a.a_hi + off;
+                const float* al = a.a_lo + off;
+#pragma unroll
+                for (int c = 0; c < BK / 4; ++c) {
+                    cp_async16(dst + c * (BM * 16), ah + 4 * c, nbytes);
+                    cp_async16(dst + A_BYTES + c * (BM * 16), al + 4 * c, nbytes);
+                }
+                if (r < BN) {
+                    const float* bh = a.b_hi + (long long)r * K + it * BK;
+                    const float* bl = a.b_lo + (long long)r * K + it * BK;
+                    const uint32_t dstb = smem_base + s * STAGE_BYTES + 2 * A_BYTES + row_off;
+#pragma unroll
+                    for (int c = 0; c < BK / 4; ++c) {
+                        cp_async16(dstb + c * (BN * 16), bh + 4 * c, 16u);
+                        cp_async16(dstb + B_BYTES + c * (BN * 16), bl + 4 * c, 16u);
+                    }
+                }
+            }
+            cp_async_commit();
+            if (it >= P) {
+                cp_async_wait<P>();                  // the copies of k-block it-P have landed
+                fence_async_proxy();                 // ... and are visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[(it - P) % STAGES]);
+            }
+        }
+        // ---------------- epilogue: TMEM -> registers -> bias / ReLU / mask -> pre-split NHWC stores ----------------
+        mbar_wait(tmem_full, 0);
+        fence_after_sync();
+        const long long dst = row_ok ? tcg_dst(a.s, n, ry, rx) : 0;
+#pragma unroll 1
+        for (int j = 0; j < BN / 32; ++j) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * 32), v);
+            if (!row_ok) continue;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const int col = j * 32 + i;
+                float x[4], hi[4], lo[4];
+                float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (a.mask) mk = *reinterpret_cast<const float4*>(a.mask + dst + col);
+                const float mkv[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float t = __uint_as_float(v[i + q]);
+                    if (a.bias) t += __ldg(a.bias + col + q);
+                    if (a.relu) t = fmaxf(t, 0.f);
+                    if (!(mkv[q] > 0.f)) t = 0.f;
+                    x[q] = t;
+                    split_tf32(t, hi[q], lo[q]);
+                }
+                if (a.out_hi) *reinterpret_cast<float4*>(a.out_hi + dst + col) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                if (a.out_lo) *reinterpret_cast<float4*>(a.out_lo + dst + col) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                if (a.out_plain) *reinterpret_cast<float4*>(a.out_plain + dst + col) = make_float4(x[0], x[1], x[2], x[3]);
+            }
+        }
+    } else {
+        // ---------------- MMA issuer ----------------
+        constexpr uint32_t idesc = idesc_tf32(BM, BN, false, false);
+        constexpr uint32_t A_LBO = BM * 16, B_LBO = BN * 16, SBO = 128;
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % STAGES;
+            mbar_wait(&full[s], (kb / STAGES) & 1);
+            fence_after_sync();
+            if (lane == 0) {
+                const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_BYTES;
+                const uint32_t b_hi = a_lo + A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {               // one MMA consumes K = 8 tf32 = 2 core matrices
+                    const uint64_t dah = make_desc(a_hi + k * 2 * A_LBO, A_LBO, SBO);
+                    const uint64_t dal = make_desc(a_lo + k * 2 * A_LBO, A_LBO, SBO);
+                    const uint64_t dbh = make_desc(b_hi + k * 2 * B_LBO, B_LBO, SBO);
+                    const uint64_t dbl = make_desc(b_lo + k * 2 * B_LBO, B_LBO, SBO);
+                    umma_tf32(tmem_base, dah, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_tf32(tmem_base, dal, dbh, idesc, 1u);
+                    umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+                }
+                umma_commit(&empty[s]);
+                if (kb == nkb - 1) umma_commit(tmem_full);
+            }
+            __syncwarp();
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, BN);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// grid (K tiles of 128, row splits).  Shared-memory tiles are MN-major: for a group of 8 rows (the MMA K) the tile is
+// [4-element M/N chunk][8 rows][16 bytes], chunks 128 bytes apart.
+template <int BN>
+__global__ void __launch_bounds__(THREADS, 1) tc_conv_wgrad_kernel(const __grid_constant__ WgradArgs a) {
+    extern __shared__ __align__(1024) unsigned char tcc_smem[];
+    constexpr int A_BYTES = 128 * 32 * 4, B_BYTES = BN * 32 * 4, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    constexpr int P = STAGES - 1;
+    constexpr int CPT = BN / 16;                                     // dY chunks copied per thread per stage
+    uint64_t* full = reinterpret_cast<uint64_t*>(tcc_smem + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    __shared__ int s_tapoff[TCG_MAX_KB], s_dy[TCG_MAX_KB], s_dx[TCG_MAX_KB];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kt = blockIdx.x, split = blockIdx.y;
+    const long long m_begin = (long long)split * a.rows_per_split;
+    const long long m_end = (m_begin + a.rows_per_split < a.M) ? m_begin + a.rows_per_split : a.M;
+    const int nst = (int)((m_end - m_begin + 31) / 32);
+    const int K = a.g.nkb * BK;
+    stage_taps(a.g, s_tapoff, s_dy, s_dx);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 4); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        mbar_init_fence();
+    }
+    if (warp == 4) tmem_alloc(tmem_slot, BN);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t smem_base = smem_u32(tcc_smem);
+
+    if (warp < 4) {
+        // ---------------- producers: thread = (row of the 32-row stage, one of the tile's four 32-float runs) ----------------
+        const int ml = threadIdx.x >> 2, run = threadIdx.x & 3;
+        const int kb = kt * 4 + run;
+        const bool kb_ok = kb < a.g.nkb;
+        const int tap_dy = kb_ok ? s_dy[kb] : 0, tap_dx = kb_ok ? s_dx[kb] : 0, tap_off = kb_ok ? s_tapoff[kb] : 0;
+        const uint32_t a_off = (uint32_t)(((ml >> 3) * 32 + run * 8) * 128 + (ml & 7) * 16);
+        const uint32_t b_off = (uint32_t)(((ml >> 3) * (BN / 4) + run * CPT) * 128 + (ml & 7) * 16);
+        for (int it = 0; it < nst + P; ++it) {
+            if (it < nst) {
+                const int s = it % STAGES;
+                mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                const long long m = m_begin + (long long)it * 32 + ml;
+                const bool row_ok = m < m_end;
+                int n = 0, ry = 0, rx = 0;
+                if (row_ok) tcg_row(a.g, m, n, ry, rx);
+                const long long img = (row_ok && a.sample_index) ? a.sample_index[n] : n;
+                const int ay = ry * a.g.rstride, ax = rx * a.g.rstride;
+                const int sy = ay + tap_dy, sx = ax + tap_dx;
+                const bool ok = row_ok && kb_ok && sy >= 0 && sy < a.g.img_h && sx >= 0 && sx + a.g.run_px <= a.g.img_w;
+                const long long off = ok ? ((img * a.g.img_h + ay) * a.g.img_w + ax) * a.g.img_c + tap_off : 0;
+                const uint32_t nbytes = ok ? 16u : 0u;
+                const uint32_t dsta = smem_base + s * STAGE_BYTES + a_off;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    cp_async16(dsta + j * 128, a.a_hi + off + 4 * j, nbytes);
+                    cp_async16(dsta + A_BYTES + j * 128, a.a_lo + off + 4 * j, nbytes);
+                }
+                const long long doff = row_ok ? m * BN + run * CPT * 4 : 0;
+                const uint32_t dbytes = row_ok ? 16u : 0u;
+                const uint32_t dstb = smem_base + s * STAGE_BYTES + 2 * A_BYTES + b_off;
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    cp_async16(dstb + j * 128, a.dy_hi + doff + 4 * j, dbytes);
+                    cp_async16(dstb + B_BYTES + j * 128, a.dy_lo + doff + 4 * j, dbytes);
+                }
+            }
+            cp_async_commit();
+            if (it >= P) {
+                cp_async_wait<P>();
+                fence_async_proxy();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[(it - P) % STAGES]);
+            }
+        }
+        // ---------------- epilogue: this split's partial dW tile ----------------
+        mbar_wait(tmem_full, 0);
+        fence_after_sync();
+        const int k = kt * 128 + warp * 32 + lane;
+        float* dst = a.partial + ((long long)split * K + k) * BN;
+#pragma unroll 1
+        for (int j = 0; j < BN / 32; ++j) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * 32), v);
+            if (k >= K) continue;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<float4*>(dst + j * 32 + i) = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
+                                                                           __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+        }
+    } else {
+        constexpr uint32_t idesc = idesc_tf32(128, BN, true, true);
+        constexpr uint32_t A_GROUP = 32 * 128, B_GROUP = (BN / 4) * 128, SBO = 128;
+        for (int st = 0; st < nst; ++st) {
+            const int s = st % STAGES;
+            mbar_wait(&full[s], (st / STAGES) & 1);
+            fence_after_sync();
+            if (lane == 0) {
+                const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_BYTES;
+                const uint32_t b_hi = a_lo + A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {                    // 8 rows of the stage per MMA
+                    const uint64_t dah = make_desc(a_hi + g * A_GROUP, A_GROUP, SBO);
+                    const uint64_t dal = make_desc(a_lo + g * A_GROUP, A_GROUP, SBO);
+                    const uint64_t dbh = make_desc(b_hi + g * B_GROUP, B_GROUP, SBO);
+                    const uint64_t dbl = make_desc(b_lo + g * B_GROUP, B_GROUP, SBO);
+                    umma_tf32(tmem_base, dah, dbh, idesc, (st > 0 || g > 0) ? 1u : 0u);
+                    umma_tf32(tmem_base, dal, dbh, idesc, 1u);
+                    umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+                }
+                umma_commit(&empty[s]);
+                if (st == nst - 1) umma_commit(tmem_full);
+            }
+            __syncwarp();
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, BN);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// small elementwise kernels around the GEMMs
+
+// observation rows (NCHW, selected through sample_index) -> NHWC padded to 4 channels, pre-split
+__global__ void obs_to_nhwc_split_kernel(const float* __restrict__ obs, const long long* __restrict__ sample_index, long long n,
+                                         int C, int H, int W, float* __restrict__ hi, float* __restrict__ lo) {
+    const long long total = n * H * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W), y = (int)((i / W) % H);
+        const long long img = i / ((long long)W * H);
+        const long long src = sample_index ? sample_index[img] : img;
+        float h[4], l[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float v = c < C ? obs[((src * C + c) * H + y) * W + x] : 0.f;
+            split_tf32(v, h[c], l[c]);
+        }
+        *reinterpret_cast<float4*>(hi + i * 4) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(lo + i * 4) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+}
+// kind 0: forward weights of `layer`; 1: conv3 data-gradient weights; 2: conv2 data-gradient weights of class (py, px)
+__global__ void pack_weights_kernel(const float* __restrict__ w, int kind, int layer, int py, int px, int C, int rows, int K,
+                                    float* __restrict__ hi, float* __restrict__ lo) {
+    const int total = rows * K;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int row = i / K, k = i - row * K;
+        const int idx = kind == 0 ? tcg_wfwd_index(layer, C, row, k) : (kind == 1 ? tcg_wdgrad3_index(row, k) : tcg_wdgrad2_index(py, px, row, k));
+        const float v = idx >= 0 ? w[idx] : 0.f;
+        float h, l;
+        split_tf32(v, h, l);
+        hi[i] = h;
+        lo[i] = l;
+    }
+}
+// feat[n, c*P + p] = y3[(n, p), c]                                  (the reference flattens NCHW, model.py:94)
+__global__ void nhwc_to_feat_kernel(const float* __restrict__ y, float* __restrict__ feat, long long n, int P) {
+    const long long total = n * P * 64;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(i % P), c = (int)((i / P) % 64);
+        const long long img = i / ((long long)P * 64);
+        feat[i] = y[(img * P + p) * 64 + c];
+    }
+}
+// dy3[(n, p), c] = dfeat[n, c*P + p] where the conv3 output was positive (ReLU backward), pre-split
+__global__ void dfeat_to_dy3_kernel(const float* __restrict__ dfeat, const float* __restrict__ y3_hi, long long n, int P,
+                                    float* __restrict__ hi, float* __restrict__ lo) {
+    const long long total = n * P * 64;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % 64), p = (int)((i / 64) % P);
+        const long long img = i / ((long long)P * 64);
+        const float v = y3_hi[i] > 0.f ? dfeat[(img * 64 + c) * P + p] : 0.f;
+        float h, l;
+        split_tf32(v, h, l);
+        hi[i] = h;
+        lo[i] = l;
+    }
+}
+// bias gradients: column sums of a pre-split [M][BN] matrix, two deterministic stages
+template <int BN>
+__global__ void colsum_split_partial_kernel(const float* __restrict__ hi, const float* __restrict__ lo, long long M, int rows_per_block,
+                                            float* __restrict__ partial) {
+    constexpr int LANES = 256 / BN;
+    __shared__ float s[256];
+    const int col = threadIdx.x % BN, rl = threadIdx.x / BN;
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    const long long r1 = (r0 + rows_per_block < M) ? r0 + rows_per_block : M;
+    float acc = 0.f;
+    for (long long r = r0 + rl; r < r1; r += LANES) acc += hi[r * BN + col] + lo[r * BN + col];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    if (rl == 0) {
+        float t = 0.f;
+        for (int q = 0; q < LANES; ++q) t += s[q * BN + col];
+        partial[(long long)blockIdx.x * BN + col] = t;
+    }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int blocks, int BN, float* __restrict__ out) {
+    const int col = threadIdx.x;
+    if (col >= BN) return;
+    float t = 0.f;
+    for (int b = 0; b < blocks; ++b) t += partial[(long long)b * BN + col];
+    out[col] = t;
+}
+// dW (reference layout) = sum over the row splits of the partial [K][BN] tiles
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int K, int BN, int layer, int C, float* __restrict__ dw) {
+    const int total = K * BN;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int k = i / BN, oc = i - k * BN;
+        float t = 0.f;
+        for (int s = 0; s < splits; ++s) t += partial[(long long)s * total + i];
+        const int idx = tcg_wfwd_index(layer, C, oc, k);
+        if (idx >= 0) dw[idx] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+int grid_for(long long total) {
+    long long b = (total + 255) / 256;
+    if (b > 148 * 16) b = 148 * 16;
+    return (int)(b < 1 ? 1 : b);
+}
+long long align64(long long v) { return (v + 63) / 64 * 64; }
+
+constexpr int COLSUM_BLOCKS = 592;
+
+struct Ws {
+    float *x0[2], *y1[2], *y2[2], *y3[2], *y3p, *d3[2], *d2[2], *d1[2];
+    float *wp1[2], *wp2[2], *wp3[2], *wd3[2], *wd2[2];
+    float *partial, *colpart;
+    long long partial_floats, total;
+};
+void plan_split(long long M, int ktiles, int* rows_per_split, int* splits) {
+    long long target = 296 / ktiles;
+    if (target < 1) target = 1;
+    long long rps = (M + target - 1) / target;
+    rps = (rps + 31) / 32 * 32;
+    if (rps < 32) rps = 32;
+    *rows_per_split = (int)rps;
+    *splits = (int)((M + rps - 1) / rps);
+}
+void carve(const TcgEncoder& e, long long n, float* base, Ws& w) {
+    long long off = 0;
+    auto take = [&](long long floats) { float* p = base ? base + off : nullptr; off += align64(floats); return p; };
+    const long long m1 = n * e.h1 * e.w1, m2 = n * e.h2 * e.w2, m3 = n * e.h3 * e.w3;
+    for (int i = 0; i < 2; ++i) w.x0[i] = take(n * e.H * e.W * 4);
+    for (int i = 0; i < 2; ++i) w.y1[i] = take(m1 * 32);
+    for (int i = 0; i < 2; ++i) w.y2[i] = take(m2 * 64);
+    for (int i = 0; i < 2; ++i) w.y3[i] = take(m3 * 64);
+    w.y3p = take(m3 * 64);
+    for (int i = 0; i < 2; ++i) w.d3[i] = take(m3 * 64);
+    for (int i = 0; i < 2; ++i) w.d2[i] = take(m2 * 64);
+    for (int i = 0; i < 2; ++i) w.d1[i] = take(m1 * 32);
+    for (int i = 0; i < 2; ++i) w.wp1[i] = take(32 * 256);
+    for (int i = 0; i < 2; ++i) w.wp2[i] = take(64 * 512);
+    for (int i = 0; i < 2; ++i) w.wp3[i] = take(64 * 576);
+    for (int i = 0; i < 2; ++i) w.wd3[i] = take(64 * 576);
+    for (int i = 0; i < 2; ++i) w.wd2[i] = take(4 * 32 * 256);
+    long long pf = 0;
+    const long long Ms[3] = {m1, m2, m3};
+    const int Ks[3] = {256, 512, 576}, Ns[3] = {32, 64, 64};
+    for (int l = 0; l < 3; ++l) {
+        int rps, splits;
+        plan_split(Ms[l] > 0 ? Ms[l] : 1, (Ks[l] + 127) / 128, &rps, &splits);
+        const long long f = (long long)splits * Ks[l] * Ns[l];
+        if (f > pf) pf = f;
+    }
+    w.partial_floats = pf;
+    w.partial = take(pf);
+    w.colpart = take(COLSUM_BLOCKS * 64);
+    w.total = off;
+}
+
+template <int BN>
+int launch_gather(cudaStream_t st, const GatherArgs& a) {
+    constexpr size_t smem = (size_t)STAGES * (2 * BM * BK * 4 + 2 * BN * BK * 4) + (2 * STAGES + 1) * 8 + 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc_conv_gather_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { trxl_set_error("tc_conv: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e)); return TRXL_ERR_CUDA; }
+        attr_set = true;
+    }
+    if (a.M <= 0) return TRXL_OK;
+    tc_conv_gather_kernel<BN><<<trxl_cdiv(a.M, BM), THREADS, smem, st>>>(a);
+    TRXL_CHECK_LAUNCH("tc_conv_gather");
+    return TRXL_OK;
+}
+template <int BN>
+int launch_wgrad(cudaStream_t st, WgradArgs a, int layer, int C, float* dw, const Ws& w) {
+    constexpr size_t smem = (size_t)STAGES * (2 * 128 * 32 * 4 + 2 * BN * 32 * 4) + (2 * STAGES + 1) * 8 + 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc_conv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { trxl_set_error("tc_conv: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e)); return TRXL_ERR_CUDA; }
+        attr_set = true;
+    }
+    const int K = a.g.nkb * BK, ktiles = (K + 127) / 128;
+    int splits;
+    plan_split(a.M, ktiles, &a.rows_per_split, &splits);
+    TRXL_CHECK_ARG((long long)splits * K * BN <= w.partial_floats, "tc_conv: wgrad partial buffer too small");
+    a.partial = w.partial;
+    tc_conv_wgrad_kernel<BN><<<dim3(ktiles, splits), THREADS, smem, st>>>(a);
+    TRXL_CHECK_LAUNCH("tc_conv_wgrad");
+    wgrad_reduce_kernel<<<grid_for((long long)K * BN), 256, 0, st>>>(w.partial, splits, K, BN, layer, C, dw);
+    TRXL_CHECK_LAUNCH("wgrad_reduce");
+    return TRXL_OK;
+}
+template <int BN>
+int launch_colsum(cudaStream_t st, const float* hi, const float* lo, long long M, float* colpart, float* out) {
+    int blocks = (int)((M + 255) / 256);
+    if (blocks > COLSUM_BLOCKS) blocks = COLSUM_BLOCKS;
+    if (blocks < 1) blocks = 1;
+    const int rpb = (int)((M + blocks - 1) / blocks);
+    blocks = (int)((M + rpb - 1) / rpb);
+    colsum_split_partial_kernel<BN><<<blocks, 256, 0, st>>>(hi, lo, M, rpb, colpart);
+    TRXL_CHECK_LAUNCH("colsum_split_partial");
+    colsum_final_kernel<<<1, 64, 0, st>>>(colpart, blocks, BN, out);
+    TRXL_CHECK_LAUNCH("colsum_final");
+    return TRXL_OK;
+}
+
+}  // namespace
+
+int tc_conv_supported(int C, int H, int W) {
+    TcgEncoder e;
+    return tcg_encoder(C, H, W, e) ? 1 : 0;
+}
+
+long long tc_conv_workspace_floats(int N, int C, int H, int W) {
+    TcgEncoder e;
+    if (!tcg_encoder(C, H, W, e) || N < 0) return -1;
+    Ws w;
+    carve(e, N, nullptr, w);
+    return w.total;
+}
+
+int tc_conv_forward(cudaStream_t st, const float* const* p, const float* obs, const long long* sample_index, int N, int C, int H,
+                    int W, float* ws, float* feat) {
+    TcgEncoder e;
+    TRXL_CHECK_ARG(tcg_encoder(C, H, W, e), "tc_conv: unsupported observation shape (%d, %d, %d)", C, H, W);
+    if (N == 0) return TRXL_OK;
+    Ws w;
+    carve(e, N, ws, w);
+    const long long m1 = (long long)N * e.h1 * e.w1, m2 = (long long)N * e.h2 * e.w2, m3 = (long long)N * e.h3 * e.w3;
+    // weights in tensor-core format (forward + data-gradient forms; the backward pass reuses them)
+    pack_weights_kernel<<<grid_for(32 * 256), 256, 0, st>>>(p[0], 0, 1, 0, 0, C, 32, 256, w.wp1[0], w.wp1[1]);
+    TRXL_CHECK_LAUNCH("pack_weights");
+    pack_weights_kernel<<<grid_for(64 * 512), 256, 0, st>>>(p[2], 0, 2, 0, 0, C, 64, 512, w.wp2[0], w.wp2[1]);
+    TRXL_CHECK_LAUNCH("pack_weights");
+    pack_weights_kernel<<<grid_for(64 * 576), 256, 0, st>>>(p[4], 0, 3, 0, 0, C, 64, 576, w.wp3[0], w.wp3[1]);
+    TRXL_CHECK_LAUNCH("pack_weights");
+    pack_weights_kernel<<<grid_for(64 * 576), 256, 0, st>>>(p[4], 1, 3, 0, 0, C, 64, 576, w.wd3[0], w.wd3[1]);
+    TRXL_CHECK_LAUNCH("pack_weights");
+    for (int cls = 0; cls < 4; ++cls) {
+        pack_weights_kernel<<<grid_for(32 * 256), 256, 0, st>>>(p[2], 2, 2, cls >> 1, cls & 1, C, 32, 256, w.wd2[0] + cls * 32 * 256,
+                                                                w.wd2[1] + cls * 32 * 256);
+        TRXL_CHECK_LAUNCH("pack_weights");
+    }
+    obs_to_nhwc_split_kernel<<<grid_for((long long)N * H * W), 256, 0, st>>>(obs, sample_index, N, C, H, W, w.x0[0], w.x0[1]);
+    TRXL_CHECK_LAUNCH("obs_to_nhwc_split");
+
+    GatherArgs a{};
+    tcg_plan_forward(e, 1, a.g, a.s);
+    a.a_hi = w.x0[0]; a.a_lo = w.x0[1]; a.b_hi = w.wp1[0]; a.b_lo = w.wp1[1]; a.bias = p[1]; a.relu = 1;
+    a.out_hi = w.y1[0]; a.out_lo = w.y1[1]; a.M = m1;
+    TRXL_PROPAGATE(launch_gather<32>(st, a));
+    a = GatherArgs{};
+    tcg_plan_forward(e, 2, a.g, a.s);
+    a.a_hi = w.y1[0]; a.a_lo = w.y1[1]; a.b_hi = w.wp2[0]; a.b_lo = w.wp2[1]; a.bias = p[3]; a.relu = 1;
+    a.out_hi = w.y2[0]; a.out_lo = w.y2[1]; a.M = m2;
+    TRXL_PROPAGATE(launch_gather<64>(st, a));
+    a = GatherArgs{};
+    tcg_plan_forward(e, 3, a.g, a.s);
+    a.a_hi = w.y2[0]; a.a_lo = w.y2[1]; a.b_hi = w.wp3[0]; a.b_lo = w.wp3[1]; a.bias = p[5]; a.relu = 1;
+    a.out_hi = w.y3[0]; a.out_lo = w.y3[1]; a.out_plain = w.y3p; a.M = m3;
+    TRXL_PROPAGATE(launch_gather<64>(st, a));
+    nhwc_to_feat_kernel<<<grid_for(m3 * 64), 256, 0, st>>>(w.y3p, feat, N, e.h3 * e.w3);
+    TRXL_CHECK_LAUNCH("nhwc_to_feat");
+    return TRXL_OK;
+}
+
+int tc_conv_backward(cudaStream_t st, float* const* g, int N, int C, int H, int W, float* ws, const float* dfeat) {
+    TcgEncoder e;
+    TRXL_CHECK_ARG(tcg_encoder(C, H, W, e), "tc_conv: unsupported observation shape (%d, %d, %d)", C, H, W);
+    if (N == 0) return TRXL_OK;
+    Ws w;
+    carve(e, N, ws, w);
+    const long long m1 = (long long)N * e.h1 * e.w1, m2 = (long long)N * e.h2 * e.w2, m3 = (long long)N * e.h3 * e.w3;
+    // ---- layer 3 ----
+    dfeat_to_dy3_kernel<<<grid_for(m3 * 64), 256, 0, st>>>(dfeat, w.y3[0], N, e.h3 * e.w3, w.d3[0], w.d3[1]);
+    TRXL_CHECK_LAUNCH("dfeat_to_dy3");
+    TRXL_PROPAGATE(launch_colsum<64>(st, w.d3[0], w.d3[1], m3, w.colpart, g[5]));
+    WgradArgs wa{};
+    TcgScatter unused;
+    tcg_plan_forward(e, 3, wa.g, unused);
+    wa.a_hi = w.y2[0]; wa.a_lo = w.y2[1]; wa.dy_hi = w.d3[0]; wa.dy_lo = w.d3[1]; wa.M = m3;
+    TRXL_PROPAGATE(launch_wgrad<64>(st, wa, 3, C, g[4], w));
+    GatherArgs a{};
+    tcg_plan_dgrad3(e, a.g, a.s);
+    a.a_hi = w.d3[0]; a.a_lo = w.d3[1]; a.b_hi = w.wd3[0]; a.b_lo = w.wd3[1]; a.mask = w.y2[0];
+    a.out_hi = w.d2[0]; a.out_lo = w.d2[1]; a.M = m2;
+    TRXL_PROPAGATE(launch_gather<64>(st, a));
+    // ---- layer 2 ----
+    TRXL_PROPAGATE(launch_colsum<64>(st, w.d2[0], w.d2[1], m2, w.colpart, g[3]));
+    wa = WgradArgs{};
+    tcg_plan_forward(e, 2, wa.g, unused);
+    wa.a_hi = w.y1[0]; wa.a_lo = w.y1[1]; wa.dy_hi = w.d2[0]; wa.dy_lo = w.d2[1]; wa.M = m2;
+    TRXL_PROPAGATE(launch_wgrad<64>(st, wa, 2, C, g[2], w));
+    for (int cls = 0; cls < 4; ++cls) {
+        a = GatherArgs{};
+        tcg_plan_dgrad2(e, cls >> 1, cls & 1, a.g, a.s);
+        a.a_hi = w.d2[0]; a.a_lo = w.d2[1]; a.b_hi = w.wd2[0] + cls * 32 * 256; a.b_lo = w.wd2[1] + cls * 32 * 256; a.mask = w.y1[0];
+        a.out_hi = w.d1[0]; a.out_lo = w.d1[1]; a.M = (long long)N * a.g.rh * a.g.rw;
+        TRXL_PROPAGATE(launch_gather<32>(st, a));
+    }
+    // ---- layer 1 ----
+    TRXL_PROPAGATE(launch_colsum<32>(st, w.d1[0], w.d1[1], m1, w.colpart, g[1]));
+    wa = WgradArgs{};
+    tcg_plan_forward(e, 1, wa.g, unused);
+    wa.a_hi = w.x0[0]; wa.a_lo = w.x0[1]; wa.dy_hi = w.d1[0]; wa.dy_lo = w.d1[1]; wa.M = m1;
+    TRXL_PROPAGATE(launch_wgrad<32>(st, wa, 1, C, g[0], w));
+    return TRXL_OK;
+}

@@ -1,0 +1,11 @@
+#pragma once
+#include "common.cuh"
+#include "tc_conv_geom.h"
+
+// p = {conv1.weight, conv1.bias, conv2.weight, conv2.bias, conv3.weight, conv3.bias} (reference layouts)
+int tc_conv_supported(int C, int H, int W);
+long long tc_conv_workspace_floats(int N, int C, int H, int W);
+int tc_conv_forward(cudaStream_t st, const float* const* p, const float* obs, const long long* sample_index, int N, int C, int H,
+                    int W, float* ws, float* feat);
+// g = gradient slots in the same order as p; overwritten (not accumulated).  ws must still hold the forward's state.
+int tc_conv_backward(cudaStream_t st, float* const* g, int N, int C, int H, int W, float* ws, const float* dfeat);

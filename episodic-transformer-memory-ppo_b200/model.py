@@ -9,6 +9,8 @@ base pointer, makes clip+AdamW one fused pass, and makes the multi-GPU gradient 
 all-reduce of one buffer.  Everything after the CNN encoder (lin_hidden -> embedding -> blocks ->
 heads) runs in two native calls; the three conv layers still go through cuDNN.
 """
+import os
+
 import numpy as np
 import torch
 from torch import nn
@@ -68,6 +70,25 @@ class _TrunkFunction(torch.autograd.Function):
         return (None, dfeat, None, None, None, None, None, None) + pgrads
 
 
+class _EncoderFunction(torch.autograd.Function):
+    """Autograd bridge for the tensor-core CNN encoder (csrc/tc_conv.cu) so that ``ActorCriticModel.forward`` stays
+    differentiable end to end like the reference's; the trainer's fused step calls encode_train / encode_backward."""
+
+    @staticmethod
+    def forward(ctx, model, obs, *conv_params):
+        n = obs.shape[0]
+        ctx.model, ctx.n, ctx.hw = model, n, tuple(obs.shape[-2:])
+        return model.encode_train(obs.detach().contiguous(), None, n).clone()
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        model = ctx.model
+        grads = torch.zeros_like(model._arena)
+        native.conv_train_backward(model._cfg, grads, ctx.n, ctx.hw[0], ctx.hw[1], model._enc_ws(ctx.n, *ctx.hw)[0], dfeat.contiguous())
+        pg = tuple(grads[off:off + numel].view(shape) for name, off, numel, shape in model._param_slices if name.startswith("conv"))
+        return (None, None) + pg
+
+
 class ActorCriticModel(nn.Module):
     def __init__(self, config, observation_space, action_space_shape, max_episode_length):
         super().__init__()
@@ -120,10 +141,12 @@ class ActorCriticModel(nn.Module):
         if missing or extra:
             raise RuntimeError("parameter layout mismatch: missing %s extra %s" % (missing, extra))
         self._trunk_names = {n for n, *_ in self._layout if not n.startswith("conv")}
-        import os
         # the one-launch per-sample trunk kernel (csrc/rollout_fused.cu) is correct but, as measured on B200 (r1), still
         # slower than the layered path at W=32 (latency-bound GEMV chains); opt in with TRXL_FUSED_ROLLOUT=1
         self._fused_ok = native.fused_forward_supported(self._cfg) and os.environ.get("TRXL_FUSED_ROLLOUT", "0") == "1"
+        # training-time encoder on the tcgen05 tensor cores (3xTF32 implicit GEMMs); TRXL_CUDNN_ENCODER=1 keeps cuDNN
+        self._tc_encoder = (self._visual and os.environ.get("TRXL_CUDNN_ENCODER", "0") != "1" and
+                            native.conv_train_supported(self._cfg, *self.observation_space_shape[1:]))
         self._arena = self._grad_arena = None
         self._pe_cache = None
         self._ws_cache = {}
@@ -203,7 +226,11 @@ class ActorCriticModel(nn.Module):
         kernels; under autograd (training minibatches) it goes through cuDNN so torch can differentiate it."""
         if not self._visual:
             return obs
-        if torch.is_grad_enabled() or not obs.is_cuda:
+        if not obs.is_cuda:
+            return _conv_features(obs, self.conv1, self.conv2, self.conv3)
+        if torch.is_grad_enabled():
+            if self._tc_encoder:
+                return _EncoderFunction.apply(self, obs, *[p for name, p in self.named_parameters() if name.startswith("conv")])
             return _conv_features(obs, self.conv1, self.conv2, self.conv3)
         obs = obs.contiguous()
         n, _, h, w = obs.shape
@@ -215,6 +242,30 @@ class ActorCriticModel(nn.Module):
             self._ws_cache[key] = ws
         native.conv_encoder_forward(self._cfg, self._arena, obs, ws[0], ws[1])
         return ws[1]
+
+    def _enc_ws(self, n, h, w):
+        key = ("enct", n, h, w)
+        ws = self._ws_cache.get(key)
+        if ws is None:
+            dev = self._arena.device
+            for k in [k for k in self._ws_cache if isinstance(k, tuple) and k[0] == "enct"]:
+                del self._ws_cache[k]                # one training batch size resident (the workspace holds all activations)
+            ws = (torch.empty(native.conv_train_workspace_floats(self._cfg, n, h, w), dtype=torch.float32, device=dev),
+                  torch.empty((n, self._feat_dim), dtype=torch.float32, device=dev))
+            self._ws_cache[key] = ws
+        return ws
+
+    def encode_train(self, obs, sample_index, n):
+        """Tensor-core encoder forward for a training batch: rows ``obs[sample_index]`` (or ``obs[:n]``) -> features (n, F).
+        Activations stay in the encoder workspace for ``encode_backward``."""
+        h, w = obs.shape[-2:]
+        ws, feat = self._enc_ws(n, h, w)
+        native.conv_train_forward(self._cfg, self._arena, obs, sample_index, n, ws, feat)
+        return feat
+
+    def encode_backward(self, n, h, w, dfeat):
+        """d loss / d features -> the conv slices of the gradient arena (overwritten)."""
+        native.conv_train_backward(self._cfg, self._grad_arena, n, h, w, self._enc_ws(n, h, w)[0], dfeat)
 
     # ------------------------------------------------------------------------------ native trunk
     FUSED_MAX_BATCH = 96      # batch sizes eligible for the opt-in one-launch per-sample trunk kernel

@@ -514,7 +514,7 @@ class PPOTrainer:
                 "advstats": torch.zeros(3, dtype=torch.float64, device=dev),
                 "loss_scratch": torch.empty(n // 128 * 5 + 64, dtype=torch.float32, device=dev),
                 "dfeat": torch.empty((n, model._feat_dim), dtype=torch.float32, device=dev) if model._visual else None,
-                "obs": torch.empty((n,) + self.obs_shape, dtype=torch.float32, device=dev),
+                "obs": None if (model._visual and model._tc_encoder) else torch.empty((n,) + self.obs_shape, dtype=torch.float32, device=dev),
             }
             self._train_state = {n: st}          # keep one size resident
         return st
@@ -527,8 +527,11 @@ class PPOTrainer:
             sidx = samples.sample_index
             n = sidx.shape[0]
             st = self._scratch(n)
-            native.gather_rows(flat["obs"], sidx, st["obs"])
-            obs = st["obs"]
+            if model._visual and model._tc_encoder:
+                obs = flat["obs"]                    # the encoder's first gather reads the minibatch rows in place
+            else:
+                native.gather_rows(flat["obs"], sidx, st["obs"])
+                obs = st["obs"]
             table = buf.memories
             ep_index, win_index = flat["memory_index"], flat["memory_indices"]
             mask = flat["memory_mask"].view(torch.uint8)
@@ -553,7 +556,10 @@ class PPOTrainer:
             group["lr"] = learning_rate
         self.optimizer.zero_grad()
         # encoder (cuDNN) with autograd so its backward can be driven by d loss / d features
-        if model._visual:
+        tc_enc = model._visual and model._tc_encoder
+        if tc_enc:
+            feat_g, feat = None, model.encode_train(obs, sidx, n)
+        elif model._visual:
             with torch.enable_grad():
                 feat_g = model.encode(obs)
             feat = feat_g.detach().contiguous()
@@ -570,7 +576,9 @@ class PPOTrainer:
         native.model_backward(model._cfg, model.flat_parameters(), model.flat_grads(), feat, table, table.shape[1], ep_index,
                               win_index, mask, pe_index, sidx, model._pe_table(), n, st["ws"], out_mem, st["dlogits"],
                               st["dvalue"], st["dfeat"])
-        if feat_g is not None:
+        if tc_enc:
+            model.encode_backward(n, obs.shape[-2], obs.shape[-1], st["dfeat"])
+        elif feat_g is not None:
             feat_g.backward(st["dfeat"])           # accumulates into the conv slices of the gradient arena
         if self.dp.world_size > 1:
             self.dp.all_reduce_(model.flat_grads())     # ONE collective per optimiser step: the flat gradient arena

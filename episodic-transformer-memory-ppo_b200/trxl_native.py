@@ -58,6 +58,10 @@ SIGNATURES = {
     "trxl_model_backward": (i32, [CFGP, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]),
     "trxl_conv_encoder_workspace_floats": (i64, [CFGP, i32, i32, i32]),
     "trxl_conv_encoder_forward": (i32, [CFGP, vp, vp, i32, i32, i32, vp, vp, vp]),
+    "trxl_conv_train_supported": (i32, [CFGP, i32, i32]),
+    "trxl_conv_train_workspace_floats": (i64, [CFGP, i32, i32, i32]),
+    "trxl_conv_train_forward": (i32, [CFGP, vp, vp, vp, i32, i32, i32, vp, vp, vp]),
+    "trxl_conv_train_backward": (i32, [CFGP, vp, i32, i32, i32, vp, vp, vp]),
     "trxl_window_attention_forward": (i32, [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
     "trxl_window_attention_backward": (i32, [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32,
                                              vp, vp, vp, vp]),
@@ -245,6 +249,28 @@ def conv_encoder_forward(cfg, params, obs, ws, feat):
     n, _, h, w = obs.shape
     _check(load().trxl_conv_encoder_forward(C.byref(cfg), _p(params), _p(obs), n, h, w, _p(ws), _p(feat), _stream()),
            "trxl_conv_encoder_forward")
+
+
+def conv_train_supported(cfg, h, w):
+    return bool(load().trxl_conv_train_supported(C.byref(cfg), int(h), int(w)))
+
+
+def conv_train_workspace_floats(cfg, n, h, w):
+    v = load().trxl_conv_train_workspace_floats(C.byref(cfg), int(n), int(h), int(w))
+    if v < 0:
+        raise ValueError("the tensor-core encoder does not cover this observation shape")
+    return int(v)
+
+
+def conv_train_forward(cfg, params, obs, sample_index, n, ws, feat):
+    h, w = obs.shape[-2:]
+    _check(load().trxl_conv_train_forward(C.byref(cfg), _p(params), _p(obs), _p(sample_index), int(n), int(h), int(w), _p(ws),
+                                          _p(feat), _stream()), "trxl_conv_train_forward")
+
+
+def conv_train_backward(cfg, grads, n, h, w, ws, dfeat):
+    _check(load().trxl_conv_train_backward(C.byref(cfg), _p(grads), int(n), int(h), int(w), _p(ws), _p(dfeat), _stream()),
+           "trxl_conv_train_backward")
 
 
 def window_attention_forward(table, slots, num_blocks, block, ep_index, win_index, mask, pe_index, sample_index, pe_table, qk,

@@ -126,6 +126,19 @@ int64_t trxl_conv_encoder_workspace_floats(const trxl_model_config* cfg, int N, 
 int trxl_conv_encoder_forward(const trxl_model_config* cfg, const float* params, const float* obs, int N, int H, int W,
                               float* workspace, float* feat, void* stream);
 
+/* Training path of the CNN encoder on the tcgen05 tensor cores (3xTF32 implicit GEMMs, csrc/tc_conv.cu): replaces the
+ * reference's conv forward (model.py:87-94) and the autograd backward of the three convolutions (trainer.py:310) for
+ * observations with <= 4 channels.  forward: obs rows (NCHW; row i of the batch is obs[sample_index[i]], or obs[i] when
+ * sample_index is NULL) -> feat (N, 64*oh*ow) in the reference's flatten order; the workspace keeps the activations.
+ * backward: dfeat (N, 64*oh*ow) -> the six conv gradient slices of `grads` (overwritten), using the same workspace.
+ * trxl_conv_train_supported returns 1 when the shape is covered. */
+int trxl_conv_train_supported(const trxl_model_config* cfg, int H, int W);
+int64_t trxl_conv_train_workspace_floats(const trxl_model_config* cfg, int N, int H, int W);
+int trxl_conv_train_forward(const trxl_model_config* cfg, const float* params, const float* obs, const int64_t* sample_index,
+                            int N, int H, int W, float* workspace, float* feat, void* stream);
+int trxl_conv_train_backward(const trxl_model_config* cfg, float* grads, int N, int H, int W, float* workspace,
+                             const float* dfeat, void* stream);
+
 /* ---- the hot kernel on its own ---------------------------------------------------------------- */
 /* Fused window gather + PE add + [LayerNorm] + q.K + mask + softmax(/sqrt(D)) + P.V with the K/V
  * projections folded onto the query side (MultiHeadAttention.forward transformer.py:31-86 for query
