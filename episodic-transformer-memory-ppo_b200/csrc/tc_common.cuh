@@ -42,14 +42,18 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 // [16,30) leading byte offset>>4, [32,46) stride byte offset>>4, [46,48) version = 1, [61,64) layout type = 0.
 //   K-major : core matrix = 8 rows x 16 bytes (4 tf32 along K); LBO = distance between the two K halves of one MMA,
 //             SBO = distance between 8-row groups
-//   MN-major: core matrix = 8 K-rows x 16 bytes (4 tf32 along M/N); SBO = distance between 4-element M/N groups,
-//             LBO = distance between 8-deep K groups (one tf32 MMA has K = 8: a single group)
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// MN-major TF32 operands exist in one layout only, SWIZZLE_128B_BASE32B (layout type 1; cutlass sm100_common.inl:92):
+//   atom = 4 K-rows x 128 bytes (32 tf32 along M/N), the 32-byte chunks of K-row r stored at chunk position c ^ (r & 3)
+//   (Swizzle<2,5,2> on the byte address: the tile base must be 512-byte aligned); LBO = distance between 32-element M/N
+//   groups, SBO = distance between 4-deep K atoms (one tf32 MMA has K = 8: two atoms).
+constexpr uint32_t LAYOUT_NONE = 0, LAYOUT_SW128_BASE32B = 1;
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = LAYOUT_NONE) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(layout & 7) << 61;
     return d;
 }
 // instruction descriptor (cute UMMA::InstrDescriptor): D = F32 (1<<4), A/B = TF32 (2<<7, 2<<10), bit 15/16 = A/B MN-major,

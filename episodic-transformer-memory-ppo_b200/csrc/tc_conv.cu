@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_gather_kernel(const __grid
     extern __shared__ __align__(1024) unsigned char tcc_smem[];
     constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     constexpr int P = STAGES - 1;                                    // stages in flight ahead of the MMA
-    uint64_t* full = reinterpret_cast<uint64_t*>(tcc_smem + STAGES * STAGE_BYTES);
+    unsigned char* tiles = tcc_smem + ((1024u - (smem_u32(tcc_smem) & 1023u)) & 1023u);      // swizzled layouts need an aligned base
+    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_gather_kernel(const __grid
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t smem_base = smem_u32(tcc_smem);
+    const uint32_t smem_base = smem_u32(tiles);
 
     if (warp < 4) {
         // ---------------- producers: one GEMM row per thread ----------------
@@ -197,15 +198,17 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_gather_kernel(const __grid
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// grid (K tiles of 128, row splits).  Shared-memory tiles are MN-major: for a group of 8 rows (the MMA K) the tile is
-// [4-element M/N chunk][8 rows][16 bytes], chunks 128 bytes apart.
+// grid (K tiles of 128, row splits).  Shared-memory tiles are MN-major in the SWIZZLE_128B_BASE32B layout (the only one
+// TF32 has for MN-major): [32-element M/N group][row / 4][row % 4][128 bytes], 32-byte chunks XOR-swizzled with row % 4.
+// One 128-byte global run (32 consecutive k of one row, or 32 consecutive channels of one dY row) is one shared row.
 template <int BN>
 __global__ void __launch_bounds__(THREADS, 1) tc_conv_wgrad_kernel(const __grid_constant__ WgradArgs a) {
     extern __shared__ __align__(1024) unsigned char tcc_smem[];
     constexpr int A_BYTES = 128 * 32 * 4, B_BYTES = BN * 32 * 4, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     constexpr int P = STAGES - 1;
     constexpr int CPT = BN / 16;                                     // dY chunks copied per thread per stage
-    uint64_t* full = reinterpret_cast<uint64_t*>(tcc_smem + STAGES * STAGE_BYTES);
+    unsigned char* tiles = tcc_smem + ((1024u - (smem_u32(tcc_smem) & 1023u)) & 1023u);      // swizzled layouts need an aligned base
+    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_wgrad_kernel(const __grid_
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t smem_base = smem_u32(tcc_smem);
+    const uint32_t smem_base = smem_u32(tiles);
 
     if (warp < 4) {
         // ---------------- producers: thread = (row of the 32-row stage, one of the tile's four 32-float runs) ----------------
@@ -236,8 +239,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_wgrad_kernel(const __grid_
         const int kb = kt * 4 + run;
         const bool kb_ok = kb < a.g.nkb;
         const int tap_dy = kb_ok ? s_dy[kb] : 0, tap_dx = kb_ok ? s_dx[kb] : 0, tap_off = kb_ok ? s_tapoff[kb] : 0;
-        const uint32_t a_off = (uint32_t)(((ml >> 3) * 32 + run * 8) * 128 + (ml & 7) * 16);
-        const uint32_t b_off = (uint32_t)(((ml >> 3) * (BN / 4) + run * CPT) * 128 + (ml & 7) * 16);
+        const uint32_t row_off = (uint32_t)((ml >> 2) * 512 + (ml & 3) * 128);      // K atom (4 rows) and row inside it
+        const uint32_t sw = (uint32_t)(ml & 3);                                     // chunk swizzle of this row
+        const uint32_t a_off = (uint32_t)(run * 4096) + row_off;
         for (int it = 0; it < nst + P; ++it) {
             if (it < nst) {
                 const int s = it % STAGES;
@@ -255,16 +259,19 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_wgrad_kernel(const __grid_
                 const uint32_t dsta = smem_base + s * STAGE_BYTES + a_off;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    cp_async16(dsta + j * 128, a.a_hi + off + 4 * j, nbytes);
-                    cp_async16(dsta + A_BYTES + j * 128, a.a_lo + off + 4 * j, nbytes);
+                    const uint32_t o = (((uint32_t)(j >> 1) ^ sw) * 32) + (j & 1) * 16;
+                    cp_async16(dsta + o, a.a_hi + off + 4 * j, nbytes);
+                    cp_async16(dsta + A_BYTES + o, a.a_lo + off + 4 * j, nbytes);
                 }
                 const long long doff = row_ok ? m * BN + run * CPT * 4 : 0;
                 const uint32_t dbytes = row_ok ? 16u : 0u;
-                const uint32_t dstb = smem_base + s * STAGE_BYTES + 2 * A_BYTES + b_off;
+                const uint32_t dstb = smem_base + s * STAGE_BYTES + 2 * A_BYTES + row_off;
 #pragma unroll
                 for (int j = 0; j < CPT; ++j) {
-                    cp_async16(dstb + j * 128, a.dy_hi + doff + 4 * j, dbytes);
-                    cp_async16(dstb + B_BYTES + j * 128, a.dy_lo + doff + 4 * j, dbytes);
+                    const uint32_t q = (uint32_t)(run * CPT + j);              // 16-byte piece of the dY row
+                    const uint32_t o = (q >> 3) * 4096 + ((((q & 7) >> 1) ^ sw) * 32) + (q & 1) * 16;
+                    cp_async16(dstb + o, a.dy_hi + doff + 4 * j, dbytes);
+                    cp_async16(dstb + B_BYTES + o, a.dy_lo + doff + 4 * j, dbytes);
                 }
             }
             cp_async_commit();
@@ -292,7 +299,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_wgrad_kernel(const __grid_
         }
     } else {
         constexpr uint32_t idesc = idesc_tf32(128, BN, true, true);
-        constexpr uint32_t A_GROUP = 32 * 128, B_GROUP = (BN / 4) * 128, SBO = 128;
+        constexpr uint32_t LBO = 4096, SBO = 512, STEP = 1024;     // M/N group stride, K atom stride, 8 rows per MMA
         for (int st = 0; st < nst; ++st) {
             const int s = st % STAGES;
             mbar_wait(&full[s], (st / STAGES) & 1);
@@ -302,10 +309,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_wgrad_kernel(const __grid_
                 const uint32_t b_hi = a_lo + A_BYTES, b_lo = b_hi + B_BYTES;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {                    // 8 rows of the stage per MMA
-                    const uint64_t dah = make_desc(a_hi + g * A_GROUP, A_GROUP, SBO);
-                    const uint64_t dal = make_desc(a_lo + g * A_GROUP, A_GROUP, SBO);
-                    const uint64_t dbh = make_desc(b_hi + g * B_GROUP, B_GROUP, SBO);
-                    const uint64_t dbl = make_desc(b_lo + g * B_GROUP, B_GROUP, SBO);
+                    const uint64_t dah = make_desc(a_hi + g * STEP, LBO, SBO, LAYOUT_SW128_BASE32B);
+                    const uint64_t dal = make_desc(a_lo + g * STEP, LBO, SBO, LAYOUT_SW128_BASE32B);
+                    const uint64_t dbh = make_desc(b_hi + g * STEP, LBO, SBO, LAYOUT_SW128_BASE32B);
+                    const uint64_t dbl = make_desc(b_lo + g * STEP, LBO, SBO, LAYOUT_SW128_BASE32B);
                     umma_tf32(tmem_base, dah, dbh, idesc, (st > 0 || g > 0) ? 1u : 0u);
                     umma_tf32(tmem_base, dal, dbh, idesc, 1u);
                     umma_tf32(tmem_base, dah, dbl, idesc, 1u);
@@ -476,7 +483,7 @@ void carve(const TcgEncoder& e, long long n, float* base, Ws& w) {
 
 template <int BN>
 int launch_gather(cudaStream_t st, const GatherArgs& a) {
-    constexpr size_t smem = (size_t)STAGES * (2 * BM * BK * 4 + 2 * BN * BK * 4) + (2 * STAGES + 1) * 8 + 16;
+    constexpr size_t smem = (size_t)STAGES * (2 * BM * BK * 4 + 2 * BN * BK * 4) + (2 * STAGES + 1) * 8 + 16 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tc_conv_gather_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -490,7 +497,7 @@ int launch_gather(cudaStream_t st, const GatherArgs& a) {
 }
 template <int BN>
 int launch_wgrad(cudaStream_t st, WgradArgs a, int layer, int C, float* dw, const Ws& w) {
-    constexpr size_t smem = (size_t)STAGES * (2 * 128 * 32 * 4 + 2 * BN * 32 * 4) + (2 * STAGES + 1) * 8 + 16;
+    constexpr size_t smem = (size_t)STAGES * (2 * 128 * 32 * 4 + 2 * BN * 32 * 4) + (2 * STAGES + 1) * 8 + 16 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tc_conv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
