@@ -25,7 +25,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int BM = 128, BK = TCG_BK, THREADS = 160, STAGES = 4;
+constexpr int BM = 128, BK = TCG_BK, THREADS = 160, STAGES = 2;        // 2 stages x <= 48 KB: two CTAs per SM
 
 struct GatherArgs {
     TcgGather g;
@@ -61,7 +61,7 @@ __device__ __forceinline__ void stage_taps(const TcgGather& g, int* s_tapoff, in
 
 // ------------------------------------------------------------------------------------------------------------------
 template <int BN>
-__global__ void __launch_bounds__(THREADS, 1) tc_conv_gather_kernel(const __grid_constant__ GatherArgs a) {
+__global__ void __launch_bounds__(THREADS, 2) tc_conv_gather_kernel(const __grid_constant__ GatherArgs a) {
     extern __shared__ __align__(1024) unsigned char tcc_smem[];
     constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     constexpr int P = STAGES - 1;                                    // stages in flight ahead of the MMA
@@ -71,11 +71,29 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_gather_kernel(const __grid
     uint64_t* tmem_full = empty + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
     __shared__ int s_tapoff[TCG_MAX_KB], s_dy[TCG_MAX_KB], s_dx[TCG_MAX_KB];
+    __shared__ long long s_rowbase[BM], s_rowdst[BM];       // float offsets of a row's anchor pixel / output pixel (-1: past M)
+    __shared__ int s_rowyx[BM];                             // anchor pixel (y << 16 | x)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long m0 = (long long)blockIdx.x * BM;
     const int nkb = a.g.nkb;
     stage_taps(a.g, s_tapoff, s_dy, s_dx);
+    if (threadIdx.x < BM) {
+        const long long m = m0 + threadIdx.x;
+        long long base = -1, dst = -1;
+        int ay = 0, ax = 0;
+        if (m < a.M) {
+            int n, ry, rx;
+            tcg_row(a.g, m, n, ry, rx);
+            const long long img = a.sample_index ? a.sample_index[n] : n;
+            ay = ry * a.g.rstride; ax = rx * a.g.rstride;
+            base = ((img * a.g.img_h + ay) * a.g.img_w + ax) * a.g.img_c;
+            dst = tcg_dst(a.s, n, ry, rx);
+        }
+        s_rowbase[threadIdx.x] = base;
+        s_rowdst[threadIdx.x] = dst;
+        s_rowyx[threadIdx.x] = (ay << 16) | ax;
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 4); mbar_init(&empty[s], 1); }
         mbar_init(tmem_full, 1);
@@ -89,42 +107,39 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_gather_kernel(const __grid
     const uint32_t smem_base = smem_u32(tiles);
 
     if (warp < 4) {
-        // ---------------- producers: one GEMM row per thread ----------------
-        const int r = threadIdx.x;
-        const long long m = m0 + r;
-        const bool row_ok = m < a.M;
-        int n = 0, ry = 0, rx = 0;
-        if (row_ok) tcg_row(a.g, m, n, ry, rx);
-        const long long img = (row_ok && a.sample_index) ? a.sample_index[n] : n;
-        const int ay = ry * a.g.rstride, ax = rx * a.g.rstride;
-        const long long base = ((img * a.g.img_h + ay) * a.g.img_w + ax) * a.g.img_c;
-        const uint32_t row_off = (uint32_t)((r >> 3) * 128 + (r & 7) * 16);     // K-major core-matrix layout, bytes
+        // ---------------- producers ----------------
+        // Eight consecutive lanes copy the eight 16-byte pieces of one row's 128-byte run (fully coalesced global reads);
+        // thread t owns piece t & 7 of rows (t >> 3) + 16 i.  Shared tiles are K-major SWIZZLE_128B: row r at
+        // (r / 8) * 1024 + (r % 8) * 128, piece c at position c ^ (r % 8), so the eight lanes of a row hit distinct banks.
+        const int piece = threadIdx.x & 7, r0 = threadIdx.x >> 3;
+        long long rbase[8];
+        int ryx[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { rbase[i] = s_rowbase[r0 + 16 * i]; ryx[i] = s_rowyx[r0 + 16 * i]; }
+        const uint32_t dst0 = (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128 + ((piece ^ (r0 & 7)) * 16));
         const int K = nkb * BK;
         for (int it = 0; it < nkb + P; ++it) {
             if (it < nkb) {
                 const int s = it % STAGES;
                 mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
-                const int sy = ay + s_dy[it], sx = ax + s_dx[it];
-                const bool ok = row_ok && sy >= 0 && sy < a.g.img_h && sx >= 0 && sx + a.g.run_px <= a.g.img_w;
-                const long long off = ok ? base + s_tapoff[it] : 0;
-                const uint32_t nbytes = ok ? 16u : 0u;
-                const uint32_t dst = smem_base + s * STAGE_BYTES + row_off;
-                const float* ah = a.a_hi + off;
-                const float* al = a.a_lo + off;
+                const int tdy = s_dy[it], tdx = s_dx[it];
+                const long long toff = s_tapoff[it] + piece * 4;
+                const uint32_t dst = smem_base + s * STAGE_BYTES + dst0;
 #pragma unroll
-                for (int c = 0; c < BK / 4; ++c) {
-                    cp_async16(dst + c * (BM * 16), ah + 4 * c, nbytes);
-                    cp_async16(dst + A_BYTES + c * (BM * 16), al + 4 * c, nbytes);
+                for (int i = 0; i < 8; ++i) {
+                    const int sy = (ryx[i] >> 16) + tdy, sx = (ryx[i] & 0xffff) + tdx;
+                    const bool ok = rbase[i] >= 0 && sy >= 0 && sy < a.g.img_h && sx >= 0 && sx + a.g.run_px <= a.g.img_w;
+                    const long long off = ok ? rbase[i] + toff : 0;
+                    const uint32_t nbytes = ok ? 16u : 0u;
+                    cp_async16(dst + i * 2048, a.a_hi + off, nbytes);
+                    cp_async16(dst + A_BYTES + i * 2048, a.a_lo + off, nbytes);
                 }
-                if (r < BN) {
-                    const float* bh = a.b_hi + (long long)r * K + it * BK;
-                    const float* bl = a.b_lo + (long long)r * K + it * BK;
-                    const uint32_t dstb = smem_base + s * STAGE_BYTES + 2 * A_BYTES + row_off;
+                const long long boff = (long long)r0 * K + it * BK + piece * 4;
+                const uint32_t dstb = smem_base + s * STAGE_BYTES + 2 * A_BYTES + dst0;
 #pragma unroll
-                    for (int c = 0; c < BK / 4; ++c) {
-                        cp_async16(dstb + c * (BN * 16), bh + 4 * c, 16u);
-                        cp_async16(dstb + B_BYTES + c * (BN * 16), bl + 4 * c, 16u);
-                    }
+                for (int i = 0; i < BN / 16; ++i) {
+                    cp_async16(dstb + i * 2048, a.b_hi + boff + (long long)i * 16 * K, 16u);
+                    cp_async16(dstb + B_BYTES + i * 2048, a.b_lo + boff + (long long)i * 16 * K, 16u);
                 }
             }
             cp_async_commit();
@@ -138,7 +153,8 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_gather_kernel(const __grid
         // ---------------- epilogue: TMEM -> registers -> bias / ReLU / mask -> pre-split NHWC stores ----------------
         mbar_wait(tmem_full, 0);
         fence_after_sync();
-        const long long dst = row_ok ? tcg_dst(a.s, n, ry, rx) : 0;
+        const long long dst = s_rowdst[threadIdx.x];
+        const bool row_ok = dst >= 0;
 #pragma unroll 1
         for (int j = 0; j < BN / 32; ++j) {
             uint32_t v[32];
@@ -168,7 +184,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_gather_kernel(const __grid
     } else {
         // ---------------- MMA issuer ----------------
         constexpr uint32_t idesc = idesc_tf32(BM, BN, false, false);
-        constexpr uint32_t A_LBO = BM * 16, B_LBO = BN * 16, SBO = 128;
+        constexpr uint32_t SBO = 1024;
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % STAGES;
             mbar_wait(&full[s], (kb / STAGES) & 1);
@@ -177,11 +193,11 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_gather_kernel(const __grid
                 const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_BYTES;
                 const uint32_t b_hi = a_lo + A_BYTES, b_lo = b_hi + B_BYTES;
 #pragma unroll
-                for (int k = 0; k < BK / 8; ++k) {               // one MMA consumes K = 8 tf32 = 2 core matrices
-                    const uint64_t dah = make_desc(a_hi + k * 2 * A_LBO, A_LBO, SBO);
-                    const uint64_t dal = make_desc(a_lo + k * 2 * A_LBO, A_LBO, SBO);
-                    const uint64_t dbh = make_desc(b_hi + k * 2 * B_LBO, B_LBO, SBO);
-                    const uint64_t dbl = make_desc(b_lo + k * 2 * B_LBO, B_LBO, SBO);
+                for (int k = 0; k < BK / 8; ++k) {               // one MMA consumes K = 8 tf32 = 32 bytes of the 128-byte span
+                    const uint64_t dah = make_desc(a_hi + k * 32, 16, SBO, LAYOUT_SW128);
+                    const uint64_t dal = make_desc(a_lo + k * 32, 16, SBO, LAYOUT_SW128);
+                    const uint64_t dbh = make_desc(b_hi + k * 32, 16, SBO, LAYOUT_SW128);
+                    const uint64_t dbl = make_desc(b_lo + k * 32, 16, SBO, LAYOUT_SW128);
                     umma_tf32(tmem_base, dah, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                     umma_tf32(tmem_base, dal, dbh, idesc, 1u);
                     umma_tf32(tmem_base, dah, dbl, idesc, 1u);
@@ -202,11 +218,10 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_gather_kernel(const __grid
 // TF32 has for MN-major): [32-element M/N group][row / 4][row % 4][128 bytes], 32-byte chunks XOR-swizzled with row % 4.
 // One 128-byte global run (32 consecutive k of one row, or 32 consecutive channels of one dY row) is one shared row.
 template <int BN>
-__global__ void __launch_bounds__(THREADS, 1) tc_conv_wgrad_kernel(const __grid_constant__ WgradArgs a) {
+__global__ void __launch_bounds__(THREADS, 2) tc_conv_wgrad_kernel(const __grid_constant__ WgradArgs a) {
     extern __shared__ __align__(1024) unsigned char tcc_smem[];
     constexpr int A_BYTES = 128 * 32 * 4, B_BYTES = BN * 32 * 4, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     constexpr int P = STAGES - 1;
-    constexpr int CPT = BN / 16;                                     // dY chunks copied per thread per stage
     unsigned char* tiles = tcc_smem + ((1024u - (smem_u32(tcc_smem) & 1023u)) & 1023u);      // swizzled layouts need an aligned base
     uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
     uint64_t* empty = full + STAGES;
@@ -234,44 +249,60 @@ __global__ void __launch_bounds__(THREADS, 1) tc_conv_wgrad_kernel(const __grid_
     const uint32_t smem_base = smem_u32(tiles);
 
     if (warp < 4) {
-        // ---------------- producers: thread = (row of the 32-row stage, one of the tile's four 32-float runs) ----------------
-        const int ml = threadIdx.x >> 2, run = threadIdx.x & 3;
-        const int kb = kt * 4 + run;
-        const bool kb_ok = kb < a.g.nkb;
-        const int tap_dy = kb_ok ? s_dy[kb] : 0, tap_dx = kb_ok ? s_dx[kb] : 0, tap_off = kb_ok ? s_tapoff[kb] : 0;
-        const uint32_t row_off = (uint32_t)((ml >> 2) * 512 + (ml & 3) * 128);      // K atom (4 rows) and row inside it
-        const uint32_t sw = (uint32_t)(ml & 3);                                     // chunk swizzle of this row
-        const uint32_t a_off = (uint32_t)(run * 4096) + row_off;
+        // ---------------- producers ----------------
+        // Eight consecutive lanes copy one 128-byte run (a row's 32 consecutive k, or 32 channels of its dY row); thread t owns
+        // piece t & 7 of rows ml0 = t >> 3 and ml0 + 16 of every 32-row stage, for all four runs of the K tile.
+        const int piece = threadIdx.x & 7, ml0 = threadIdx.x >> 3;
+        int tdy[4], tdx[4], toff[4];
+        bool kb_ok[4];
+#pragma unroll
+        for (int run = 0; run < 4; ++run) {
+            const int kb = kt * 4 + run;
+            kb_ok[run] = kb < a.g.nkb;
+            tdy[run] = kb_ok[run] ? s_dy[kb] : 0; tdx[run] = kb_ok[run] ? s_dx[kb] : 0; toff[run] = kb_ok[run] ? s_tapoff[kb] : 0;
+        }
+        // row iterators (advance 32 rows per stage without divisions)
+        long long rm[2];
+        int rn[2], rry[2], rrx[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            rm[h] = m_begin + ml0 + 16 * h;
+            tcg_row(a.g, rm[h], rn[h], rry[h], rrx[h]);
+        }
+        const uint32_t sw = (uint32_t)(ml0 & 3);
+        const uint32_t off0 = (uint32_t)((ml0 >> 2) * 512 + (ml0 & 3) * 128 + (((uint32_t)(piece >> 1) ^ sw) * 32) + (piece & 1) * 16);
         for (int it = 0; it < nst + P; ++it) {
             if (it < nst) {
                 const int s = it % STAGES;
                 mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
-                const long long m = m_begin + (long long)it * 32 + ml;
-                const bool row_ok = m < m_end;
-                int n = 0, ry = 0, rx = 0;
-                if (row_ok) tcg_row(a.g, m, n, ry, rx);
-                const long long img = (row_ok && a.sample_index) ? a.sample_index[n] : n;
-                const int ay = ry * a.g.rstride, ax = rx * a.g.rstride;
-                const int sy = ay + tap_dy, sx = ax + tap_dx;
-                const bool ok = row_ok && kb_ok && sy >= 0 && sy < a.g.img_h && sx >= 0 && sx + a.g.run_px <= a.g.img_w;
-                const long long off = ok ? ((img * a.g.img_h + ay) * a.g.img_w + ax) * a.g.img_c + tap_off : 0;
-                const uint32_t nbytes = ok ? 16u : 0u;
-                const uint32_t dsta = smem_base + s * STAGE_BYTES + a_off;
+                const uint32_t dsta = smem_base + s * STAGE_BYTES + off0;
+                const uint32_t dstb = dsta + 2 * A_BYTES;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t o = (((uint32_t)(j >> 1) ^ sw) * 32) + (j & 1) * 16;
-                    cp_async16(dsta + o, a.a_hi + off + 4 * j, nbytes);
-                    cp_async16(dsta + A_BYTES + o, a.a_lo + off + 4 * j, nbytes);
-                }
-                const long long doff = row_ok ? m * BN + run * CPT * 4 : 0;
-                const uint32_t dbytes = row_ok ? 16u : 0u;
-                const uint32_t dstb = smem_base + s * STAGE_BYTES + 2 * A_BYTES + row_off;
+                for (int h = 0; h < 2; ++h) {
+                    const bool row_ok = rm[h] < m_end;
+                    const long long img = (row_ok && a.sample_index) ? a.sample_index[rn[h]] : rn[h];
+                    const int ay = rry[h] * a.g.rstride, ax = rrx[h] * a.g.rstride;
+                    const long long base = ((img * a.g.img_h + ay) * a.g.img_w + ax) * a.g.img_c + piece * 4;
 #pragma unroll
-                for (int j = 0; j < CPT; ++j) {
-                    const uint32_t q = (uint32_t)(run * CPT + j);              // 16-byte piece of the dY row
-                    const uint32_t o = (q >> 3) * 4096 + ((((q & 7) >> 1) ^ sw) * 32) + (q & 1) * 16;
-                    cp_async16(dstb + o, a.dy_hi + doff + 4 * j, dbytes);
-                    cp_async16(dstb + B_BYTES + o, a.dy_lo + doff + 4 * j, dbytes);
+                    for (int run = 0; run < 4; ++run) {
+                        const int sy = ay + tdy[run], sx = ax + tdx[run];
+                        const bool ok = row_ok && kb_ok[run] && sy >= 0 && sy < a.g.img_h && sx >= 0 && sx + a.g.run_px <= a.g.img_w;
+                        const long long off = ok ? base + toff[run] : 0;
+                        const uint32_t nbytes = ok ? 16u : 0u;
+                        cp_async16(dsta + h * 2048 + run * 4096, a.a_hi + off, nbytes);
+                        cp_async16(dsta + A_BYTES + h * 2048 + run * 4096, a.a_lo + off, nbytes);
+                    }
+                    const long long doff = row_ok ? rm[h] * BN + piece * 4 : 0;
+                    const uint32_t dbytes = row_ok ? 16u : 0u;
+#pragma unroll
+                    for (int grp = 0; grp < BN / 32; ++grp) {
+                        cp_async16(dstb + h * 2048 + grp * 4096, a.dy_hi + doff + grp * 32, dbytes);
+                        cp_async16(dstb + B_BYTES + h * 2048 + grp * 4096, a.dy_lo + doff + grp * 32, dbytes);
+                    }
+                    rm[h] += 32;
+                    rrx[h] += 32;
+                    while (rrx[h] >= a.g.rw) { rrx[h] -= a.g.rw; ++rry[h]; }
+                    while (rry[h] >= a.g.rh) { rry[h] -= a.g.rh; ++rn[h]; }
                 }
             }
             cp_async_commit();
@@ -446,6 +477,7 @@ void plan_split(long long M, int ktiles, int* rows_per_split, int* splits) {
     long long rps = (M + target - 1) / target;
     rps = (rps + 31) / 32 * 32;
     if (rps < 32) rps = 32;
+    if (rps > 1024) rps = 1024;      // bounds the TMEM accumulation chain (the tensor core accumulates with truncation)
     *rows_per_split = (int)rps;
     *splits = (int)((M + rps - 1) / rps);
 }

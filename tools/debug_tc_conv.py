@@ -76,6 +76,13 @@ def main():
     rep("dy3", d3[0] + d3[1], nhwc(zs[2].grad))
     rep("dy2", d2[0] + d2[1], nhwc(zs[1].grad))
     rep("dy1", d1[0] + d1[1], nhwc(zs[0].grad))
+    e1 = np.abs((d1[0] + d1[1]) - nhwc(zs[0].grad)).reshape(n, h1, w1, 32).max(axis=3)
+    bad = np.argwhere(e1 > 1e-3)
+    print("dy1 bad pixels: %d of %d; by class (py,px): %s" % (len(bad), e1.size, {(py, px): int((e1[:, py::2, px::2] > 1e-3).sum())
+                                                                                   for py in (0, 1) for px in (0, 1)}))
+    print("   bad by iy", (e1 > 1e-3).sum(axis=(0, 2)), "\n   bad by ix", (e1 > 1e-3).sum(axis=(0, 1)))
+    print("   bad images (first 20)", np.unique(bad[:, 0])[:20], "count", len(np.unique(bad[:, 0])))
+    print("   first bad", bad[:12].tolist())
     got = [t.grad.cpu().numpy() for c in (model.conv1, model.conv2, model.conv3) for t in (c.weight, c.bias)]
     ref = [t.grad.numpy() for c in convs for t in (c.weight, c.bias)]
     for name, a, b in zip("dw1 db1 dw2 db2 dw3 db3".split(), got, ref):
