@@ -26,6 +26,10 @@ namespace {
 using namespace tc;
 
 constexpr int BM = 128, BK = TCG_BK, THREADS = 160, STAGES = 2;        // 2 stages x <= 48 KB: two CTAs per SM
+// The tensor core adds into the TMEM accumulator with truncation, so the rounding error grows with the length of the
+// accumulation chain.  Three accumulators keep it at fp32-SIMT level: hi*hi products alternate between two of them (halving
+// the chain that carries the magnitude), the ~2^-11 smaller cross terms go to the third, and the epilogue adds them (RN).
+__host__ __device__ constexpr int tmem_cols(int bn) { return bn == 32 ? 128 : 256; }
 
 struct GatherArgs {
     TcgGather g;
@@ -57,6 +61,17 @@ __device__ __forceinline__ void stage_taps(const TcgGather& g, int* s_tapoff, in
         s_dx[kb] = g.tap_dx[kb];
         s_tapoff[kb] = (g.tap_dy[kb] * g.img_w + g.tap_dx[kb]) * g.img_c + g.tap_c0[kb];
     }
+}
+
+// v = (hi*hi even steps + hi*hi odd steps) + cross terms, for 32 accumulator columns of this warp's 32 lanes
+template <int BN>
+__device__ __forceinline__ void load_accumulators(uint32_t taddr, uint32_t (&v)[32]) {
+    uint32_t u[32], x[32];
+    tmem_ld32(taddr, v);
+    tmem_ld32(taddr + BN, u);
+    tmem_ld32(taddr + 2 * BN, x);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint((__uint_as_float(v[i]) + __uint_as_float(u[i])) + __uint_as_float(x[i]));
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -99,7 +114,7 @@ __global__ void __launch_bounds__(THREADS, 2) tc_conv_gather_kernel(const __grid
         mbar_init(tmem_full, 1);
         mbar_init_fence();
     }
-    if (warp == 4) tmem_alloc(tmem_slot, BN);
+    if (warp == 4) tmem_alloc(tmem_slot, tmem_cols(BN));
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -158,7 +173,7 @@ __global__ void __launch_bounds__(THREADS, 2) tc_conv_gather_kernel(const __grid
 #pragma unroll 1
         for (int j = 0; j < BN / 32; ++j) {
             uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * 32), v);
+            load_accumulators<BN>(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * 32), v);
             if (!row_ok) continue;
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
@@ -198,9 +213,10 @@ __global__ void __launch_bounds__(THREADS, 2) tc_conv_gather_kernel(const __grid
                     const uint64_t dal = make_desc(a_lo + k * 32, 16, SBO, LAYOUT_SW128);
                     const uint64_t dbh = make_desc(b_hi + k * 32, 16, SBO, LAYOUT_SW128);
                     const uint64_t dbl = make_desc(b_lo + k * 32, 16, SBO, LAYOUT_SW128);
-                    umma_tf32(tmem_base, dah, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                    umma_tf32(tmem_base, dal, dbh, idesc, 1u);
-                    umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+                    const int step = kb * (BK / 8) + k;
+                    umma_tf32(tmem_base + (uint32_t)((step & 1) * BN), dah, dbh, idesc, step >= 2 ? 1u : 0u);
+                    umma_tf32(tmem_base + 2 * BN, dal, dbh, idesc, step > 0 ? 1u : 0u);
+                    umma_tf32(tmem_base + 2 * BN, dah, dbl, idesc, 1u);
                 }
                 umma_commit(&empty[s]);
                 if (kb == nkb - 1) umma_commit(tmem_full);
@@ -210,7 +226,7 @@ __global__ void __launch_bounds__(THREADS, 2) tc_conv_gather_kernel(const __grid
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, BN);
+    if (warp == 4) tmem_dealloc(tmem_base, tmem_cols(BN));
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -241,7 +257,7 @@ __global__ void __launch_bounds__(THREADS, 2) tc_conv_wgrad_kernel(const __grid_
         mbar_init(tmem_full, 1);
         mbar_init_fence();
     }
-    if (warp == 4) tmem_alloc(tmem_slot, BN);
+    if (warp == 4) tmem_alloc(tmem_slot, tmem_cols(BN));
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -321,7 +337,7 @@ __global__ void __launch_bounds__(THREADS, 2) tc_conv_wgrad_kernel(const __grid_
 #pragma unroll 1
         for (int j = 0; j < BN / 32; ++j) {
             uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * 32), v);
+            load_accumulators<BN>(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * 32), v);
             if (k >= K) continue;
 #pragma unroll
             for (int i = 0; i < 32; i += 4)
@@ -344,9 +360,10 @@ __global__ void __launch_bounds__(THREADS, 2) tc_conv_wgrad_kernel(const __grid_
                     const uint64_t dal = make_desc(a_lo + g * STEP, LBO, SBO, LAYOUT_SW128_BASE32B);
                     const uint64_t dbh = make_desc(b_hi + g * STEP, LBO, SBO, LAYOUT_SW128_BASE32B);
                     const uint64_t dbl = make_desc(b_lo + g * STEP, LBO, SBO, LAYOUT_SW128_BASE32B);
-                    umma_tf32(tmem_base, dah, dbh, idesc, (st > 0 || g > 0) ? 1u : 0u);
-                    umma_tf32(tmem_base, dal, dbh, idesc, 1u);
-                    umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+                    const int step = st * 4 + g;
+                    umma_tf32(tmem_base + (uint32_t)((step & 1) * BN), dah, dbh, idesc, step >= 2 ? 1u : 0u);
+                    umma_tf32(tmem_base + 2 * BN, dal, dbh, idesc, step > 0 ? 1u : 0u);
+                    umma_tf32(tmem_base + 2 * BN, dah, dbl, idesc, 1u);
                 }
                 umma_commit(&empty[s]);
                 if (st == nst - 1) umma_commit(tmem_full);
@@ -356,7 +373,7 @@ __global__ void __launch_bounds__(THREADS, 2) tc_conv_wgrad_kernel(const __grid_
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, BN);
+    if (warp == 4) tmem_dealloc(tmem_base, tmem_cols(BN));
 }
 
 // ------------------------------------------------------------------------------------------------------------------
