@@ -230,15 +230,26 @@ int64_t trxl_conv_train_workspace_floats(const trxl_model_config* cfg, int N, in
     return tc_conv_workspace_floats(N, cfg->conv_in_channels, H, W);
 }
 
+int trxl_conv_train_pack_weights(const trxl_model_config* cfg, const float* params, int N, int H, int W, float* workspace,
+                                 void* stream) {
+    TRXL_CHECK_ARG(cfg && cfg->conv_in_channels > 0, "conv_train: config has no convolutional encoder");
+    TRXL_CHECK_ARG(params && workspace, "conv_train: null pointer");
+    long long off[6];
+    TRXL_PROPAGATE(conv_param_offsets(cfg, off));
+    const float* p[6];
+    for (int i = 0; i < 6; ++i) p[i] = params + off[i];
+    return tc_conv_pack_weights(S(stream), p, N, cfg->conv_in_channels, H, W, workspace);
+}
+
 int trxl_conv_train_forward(const trxl_model_config* cfg, const float* params, const float* obs, const int64_t* sample_index, int N,
-                            int H, int W, float* workspace, float* feat, void* stream) {
+                            int H, int W, float* workspace, float* feat, int repack_weights, void* stream) {
     TRXL_CHECK_ARG(cfg && cfg->conv_in_channels > 0, "conv_train: config has no convolutional encoder");
     TRXL_CHECK_ARG(params && obs && workspace && feat, "conv_train: null pointer");
     long long off[6];
     TRXL_PROPAGATE(conv_param_offsets(cfg, off));
     const float* p[6];
     for (int i = 0; i < 6; ++i) p[i] = params + off[i];
-    return tc_conv_forward(S(stream), p, obs, (cll)sample_index, N, cfg->conv_in_channels, H, W, workspace, feat);
+    return tc_conv_forward(S(stream), p, obs, (cll)sample_index, N, cfg->conv_in_channels, H, W, workspace, feat, repack_weights);
 }
 
 int trxl_conv_train_backward(const trxl_model_config* cfg, float* grads, int N, int H, int W, float* workspace, const float* dfeat,

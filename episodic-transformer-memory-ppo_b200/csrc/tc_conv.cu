@@ -593,14 +593,11 @@ long long tc_conv_workspace_floats(int N, int C, int H, int W) {
     return w.total;
 }
 
-int tc_conv_forward(cudaStream_t st, const float* const* p, const float* obs, const long long* sample_index, int N, int C, int H,
-                    int W, float* ws, float* feat) {
+int tc_conv_pack_weights(cudaStream_t st, const float* const* p, int N, int C, int H, int W, float* ws) {
     TcgEncoder e;
     TRXL_CHECK_ARG(tcg_encoder(C, H, W, e), "tc_conv: unsupported observation shape (%d, %d, %d)", C, H, W);
-    if (N == 0) return TRXL_OK;
     Ws w;
     carve(e, N, ws, w);
-    const long long m1 = (long long)N * e.h1 * e.w1, m2 = (long long)N * e.h2 * e.w2, m3 = (long long)N * e.h3 * e.w3;
     // weights in tensor-core format (forward + data-gradient forms; the backward pass reuses them)
     pack_weights_kernel<<<grid_for(32 * 256), 256, 0, st>>>(p[0], 0, 1, 0, 0, C, 32, 256, w.wp1[0], w.wp1[1]);
     TRXL_CHECK_LAUNCH("pack_weights");
@@ -615,6 +612,18 @@ int tc_conv_forward(cudaStream_t st, const float* const* p, const float* obs, co
                                                                 w.wd2[1] + cls * 32 * 256);
         TRXL_CHECK_LAUNCH("pack_weights");
     }
+    return TRXL_OK;
+}
+
+int tc_conv_forward(cudaStream_t st, const float* const* p, const float* obs, const long long* sample_index, int N, int C, int H,
+                    int W, float* ws, float* feat, int repack) {
+    TcgEncoder e;
+    TRXL_CHECK_ARG(tcg_encoder(C, H, W, e), "tc_conv: unsupported observation shape (%d, %d, %d)", C, H, W);
+    if (N == 0) return TRXL_OK;
+    Ws w;
+    carve(e, N, ws, w);
+    const long long m1 = (long long)N * e.h1 * e.w1, m2 = (long long)N * e.h2 * e.w2, m3 = (long long)N * e.h3 * e.w3;
+    if (repack) TRXL_PROPAGATE(tc_conv_pack_weights(st, p, N, C, H, W, ws));
     obs_to_nhwc_split_kernel<<<grid_for((long long)N * H * W), 256, 0, st>>>(obs, sample_index, N, C, H, W, w.x0[0], w.x0[1]);
     TRXL_CHECK_LAUNCH("obs_to_nhwc_split");
 

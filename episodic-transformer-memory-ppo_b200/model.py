@@ -220,10 +220,11 @@ class ActorCriticModel(nn.Module):
                 torch.empty((n, t.num_blocks, t.embed_dim), device=device))
 
     # ------------------------------------------------------------------------------ encoders
-    def encode(self, obs):
+    def encode(self, obs, weights_packed=False):
         """CNN encoder for image observations (model.py:87-94); identity for vector observations.
-        Without autograd (rollout, bootstrap value, enjoy) the encoder runs as this library's im2col + GEMM
-        kernels; under autograd (training minibatches) it goes through cuDNN so torch can differentiate it."""
+        On the GPU the three convolutions run as tcgen05 implicit GEMMs (csrc/tc_conv.cu) for observations with up to
+        4 channels, otherwise as im2col + SIMT GEMM without autograd and cuDNN under autograd.  ``weights_packed=True``
+        (rollout steps after the first: the weights are frozen) skips the conversion of the weights to tensor-core format."""
         if not self._visual:
             return obs
         if not obs.is_cuda:
@@ -234,6 +235,11 @@ class ActorCriticModel(nn.Module):
             return _conv_features(obs, self.conv1, self.conv2, self.conv3)
         obs = obs.contiguous()
         n, _, h, w = obs.shape
+        if self._tc_encoder:
+            fresh = ("enci", n, h, w) not in self._ws_cache
+            ws = self._inference_enc_ws(n, h, w)
+            native.conv_train_forward(self._cfg, self._arena, obs, None, n, ws[0], ws[1], repack=fresh or not weights_packed)
+            return ws[1]
         key = ("enc", n, h, w)
         ws = self._ws_cache.get(key)
         if ws is None:
@@ -242,6 +248,21 @@ class ActorCriticModel(nn.Module):
             self._ws_cache[key] = ws
         native.conv_encoder_forward(self._cfg, self._arena, obs, ws[0], ws[1])
         return ws[1]
+
+    def _inference_enc_ws(self, n, h, w):
+        key = ("enci", n, h, w)
+        ws = self._ws_cache.get(key)
+        if ws is None:
+            dev = self._arena.device
+            ws = (torch.empty(native.conv_train_workspace_floats(self._cfg, n, h, w), dtype=torch.float32, device=dev),
+                  torch.empty((n, self._feat_dim), dtype=torch.float32, device=dev))
+            self._ws_cache[key] = ws
+        return ws
+
+    def pack_encoder_weights(self, n, h, w):
+        """Convert the conv weights to tensor-core format for the no-grad encoder of batch size n (the rollout calls this
+        once per rollout and then runs ``encode(..., weights_packed=True)`` while the weights are frozen)."""
+        native.conv_train_pack_weights(self._cfg, self._arena, n, h, w, self._inference_enc_ws(n, h, w)[0])
 
     def _enc_ws(self, n, h, w):
         key = ("enct", n, h, w)

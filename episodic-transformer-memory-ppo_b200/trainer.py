@@ -252,6 +252,11 @@ class PPOTrainer:
                 "ep_sched": torch.zeros((T + 1, W), dtype=torch.long, device=self.device),
             }
         self._ctx["uniforms"].uniform_()
+        # the weights are frozen during a rollout: convert them to tensor-core format once, outside the per-step graphs
+        self._ctx["enc_packed"] = False
+        if self.model._visual and self.model._tc_encoder:
+            self.model.pack_encoder_weights(self.num_workers, *self.obs_shape[1:])
+            self._ctx["enc_packed"] = True
         return self._ctx
 
     # -- CUDA graphs: the ~60 small launches of one rollout step are captured once per step index and replayed,
@@ -310,7 +315,7 @@ class PPOTrainer:
         native.rollout_prepare(step_dev, ep_dev, self._mask_table_dev, self._index_table_dev,
                                ctx["flat_mask"].data_ptr() + t * L, T * L, ctx["flat_idx"].data_ptr() + t * L * 8, T * L,
                                ctx["flat_ep"].data_ptr() + t * 8, T, W, L)
-        feat = model.encode(obs_dev)
+        feat = model.encode(obs_dev, weights_packed=ctx["enc_packed"])
         logits, value, new_mem = model.forward_table(feat, self._table, ctx["flat_ep"], ctx["flat_idx"], ctx["flat_mask"],
                                                      ctx["flat_idx"], sample_index=self._rollout_rows[t], n=W, ws=ctx["ws"],
                                                      out=ctx["outs"])

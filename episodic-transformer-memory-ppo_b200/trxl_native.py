@@ -60,7 +60,8 @@ SIGNATURES = {
     "trxl_conv_encoder_forward": (i32, [CFGP, vp, vp, i32, i32, i32, vp, vp, vp]),
     "trxl_conv_train_supported": (i32, [CFGP, i32, i32]),
     "trxl_conv_train_workspace_floats": (i64, [CFGP, i32, i32, i32]),
-    "trxl_conv_train_forward": (i32, [CFGP, vp, vp, vp, i32, i32, i32, vp, vp, vp]),
+    "trxl_conv_train_pack_weights": (i32, [CFGP, vp, i32, i32, i32, vp, vp]),
+    "trxl_conv_train_forward": (i32, [CFGP, vp, vp, vp, i32, i32, i32, vp, vp, i32, vp]),
     "trxl_conv_train_backward": (i32, [CFGP, vp, i32, i32, i32, vp, vp, vp]),
     "trxl_window_attention_forward": (i32, [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
     "trxl_window_attention_backward": (i32, [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32,
@@ -262,10 +263,15 @@ def conv_train_workspace_floats(cfg, n, h, w):
     return int(v)
 
 
-def conv_train_forward(cfg, params, obs, sample_index, n, ws, feat):
+def conv_train_pack_weights(cfg, params, n, h, w, ws):
+    _check(load().trxl_conv_train_pack_weights(C.byref(cfg), _p(params), int(n), int(h), int(w), _p(ws), _stream()),
+           "trxl_conv_train_pack_weights")
+
+
+def conv_train_forward(cfg, params, obs, sample_index, n, ws, feat, repack=True):
     h, w = obs.shape[-2:]
     _check(load().trxl_conv_train_forward(C.byref(cfg), _p(params), _p(obs), _p(sample_index), int(n), int(h), int(w), _p(ws),
-                                          _p(feat), _stream()), "trxl_conv_train_forward")
+                                          _p(feat), 1 if repack else 0, _stream()), "trxl_conv_train_forward")
 
 
 def conv_train_backward(cfg, grads, n, h, w, ws, dfeat):

@@ -131,11 +131,15 @@ int trxl_conv_encoder_forward(const trxl_model_config* cfg, const float* params,
  * observations with <= 4 channels.  forward: obs rows (NCHW; row i of the batch is obs[sample_index[i]], or obs[i] when
  * sample_index is NULL) -> feat (N, 64*oh*ow) in the reference's flatten order; the workspace keeps the activations.
  * backward: dfeat (N, 64*oh*ow) -> the six conv gradient slices of `grads` (overwritten), using the same workspace.
+ * The weights are converted to tensor-core format (pre-split TF32 planes) into the workspace by pack_weights, or by a
+ * forward with repack_weights = 1; rollout forwards (weights frozen) pack once and pass 0.
  * trxl_conv_train_supported returns 1 when the shape is covered. */
 int trxl_conv_train_supported(const trxl_model_config* cfg, int H, int W);
 int64_t trxl_conv_train_workspace_floats(const trxl_model_config* cfg, int N, int H, int W);
+int trxl_conv_train_pack_weights(const trxl_model_config* cfg, const float* params, int N, int H, int W, float* workspace,
+                                 void* stream);
 int trxl_conv_train_forward(const trxl_model_config* cfg, const float* params, const float* obs, const int64_t* sample_index,
-                            int N, int H, int W, float* workspace, float* feat, void* stream);
+                            int N, int H, int W, float* workspace, float* feat, int repack_weights, void* stream);
 int trxl_conv_train_backward(const trxl_model_config* cfg, float* grads, int N, int H, int W, float* workspace,
                              const float* dfeat, void* stream);
 
