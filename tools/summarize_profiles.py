@@ -21,6 +21,7 @@ METRICS = [
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "launch__occupancy_limit_shared_mem",
 ]
 
 
@@ -79,6 +80,12 @@ def main():
     p = os.path.join(args.src, "launches_c3.csv")
     if os.path.exists(p):
         launch_list(p, os.path.join(dst, "%s_launches_c3.txt" % args.round))
+    p = os.path.join(args.src, "rollout_kernels.txt")
+    if os.path.exists(p):
+        with open(p) as fsrc, open(os.path.join(dst, "%s_kineto_rollout_c3.txt" % args.round), "w") as fdst:
+            fdst.write("# torch.profiler (CUPTI) over ONE rollout (512 steps x 32 workers, CUDA graphs off) of the c3 workload, device feed\n")
+            fdst.write(fsrc.read())
+        print("wrote rollout kineto table")
     p = os.path.join(args.src, "kernels_c3.txt")
     if os.path.exists(p):
         with open(p) as fsrc, open(os.path.join(dst, "%s_kineto_update_c3.txt" % args.round), "w") as fdst:
@@ -87,7 +94,9 @@ def main():
         print("wrote kineto table")
     for rep, title in (("attn_%s" % args.round, "fused window attention fwd/bwd, training minibatch (N=2048, L=128, D=256, H=4)"),
                        ("sgemm_%s" % args.round, "SIMT sgemm launches: 1 rollout step (M=32) + 1 minibatch step (M=2048)"),
-                       ("tcgemm_%s" % args.round, "tcgen05 3xTF32 GEMM (opt-in), linear forward M=2048 N=256 K=256")):
+                       ("tcgemm_%s" % args.round, "tcgen05 3xTF32 GEMM (opt-in), linear forward M=2048 N=256 K=256"),
+                       ("tcconv_%s" % args.round, "tcgen05 3xTF32 implicit-GEMM CNN encoder, one training minibatch (N=2048, 4x84x84): conv1/2/3 "
+                                                  "forward, wgrad3, dgrad3, wgrad2, dgrad2 x4 parity classes, wgrad1 (launch order)")):
         p = os.path.join(args.src, rep + ".ncu-rep")
         if os.path.exists(p):
             ncu_report(p, os.path.join(dst, "%s_ncu_%s.txt" % (args.round, rep.split("_")[0])), title)
