@@ -235,8 +235,9 @@ __global__ void __cluster_dims__(RF_CL, 1, 1) __launch_bounds__(RF_THREADS, 1) r
     float* s_red = s_hd + ((2 * hid + 3) & ~3);       // [2 * RF_WARPS + 4]
     float* s_part = s_red + 2 * RF_WARPS + 4;         // [RF_PART]
     int* s_win = reinterpret_cast<int*>(s_part + RF_PART);   // [L]
-    int* s_pe = s_win + L;                            // [L]
-    int* s_vis = s_pe + L;                            // [L]
+    int* s_pe = s_win + Lp;                           // [L]
+    int* s_vis = s_pe + Lp;                           // [L]
+    float* s_cache = reinterpret_cast<float*>(s_vis + Lp);   // [L][D] window rows (+PE) of the head in flight, if it fits
     __shared__ int s_any;
 
     Cl c;
@@ -325,34 +326,43 @@ __global__ void __cluster_dims__(RF_CL, 1, 1) __launch_bounds__(RF_THREADS, 1) r
                 const int col = cc * 128 + lane * 4;
                 qv[cc] = (cc < NC && col < D) ? *reinterpret_cast<const float4*>(s_qk + col) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            // ---- pass 1: energies (two window rows in flight per warp) ----
-            for (int l0 = warp * 2; l0 < L; l0 += RF_WARPS * 2) {
-                float4 x[2][4];
-                bool vis[2];
+            // ---- pass 1: energies (four window rows in flight per warp) ----
+            for (int l0 = warp * 4; l0 < L; l0 += RF_WARPS * 4) {
+                float4 x[4][4];
+                bool vis[4];
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
+                for (int u = 0; u < 4; ++u) {
                     const int l = l0 + u;
                     vis[u] = (l < L) && s_vis[l];
 #pragma unroll
                     for (int cc = 0; cc < 4; ++cc) {
                         const int col = cc * 128 + lane * 4;
                         x[u][cc] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (vis[u] && cc < NC && col < D) {
-                            x[u][cc] = ldg4(tab + s_win[l] + col);
-                            if (pe) {
-                                const float4 p4 = ldg4(pe + s_pe[l] + col);
+                        if (vis[u] && cc < NC && col < D) x[u][cc] = ldg4(tab + s_win[l] + col);
+                    }
+                }
+                if (pe) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) {
+                            const int col = cc * 128 + lane * 4;
+                            if (vis[u] && cc < NC && col < D) {
+                                const float4 p4 = ldg4(pe + s_pe[l0 + u] + col);
                                 x[u][cc].x += p4.x; x[u][cc].y += p4.y; x[u][cc].z += p4.z; x[u][cc].w += p4.w;
                             }
                         }
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
+                for (int u = 0; u < 4; ++u) {
                     if (!vis[u]) continue;                      // warp-uniform
                     const int l = l0 + u;
                     float d = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
                     for (int cc = 0; cc < 4; ++cc) {
+                        const int col = cc * 128 + lane * 4;
+                        if (a.cache_window && cc < NC && col < D) *reinterpret_cast<float4*>(s_cache + l * D + col) = x[u][cc];
                         d += dot4f(qv[cc], x[u][cc]);
                         s1 += x[u][cc].x + x[u][cc].y + x[u][cc].z + x[u][cc].w;
                         s2 += dot4f(x[u][cc], x[u][cc]);
@@ -405,10 +415,14 @@ __global__ void __cluster_dims__(RF_CL, 1, 1) __launch_bounds__(RF_THREADS, 1) r
                             const int col = cc * 128 + lane * 4;
                             x[u][cc] = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (vis[u] && cc < NC && col < D) {
-                                x[u][cc] = ldg4(tab + s_win[l] + col);
-                                if (pe) {
-                                    const float4 p4 = ldg4(pe + s_pe[l] + col);
-                                    x[u][cc].x += p4.x; x[u][cc].y += p4.y; x[u][cc].z += p4.z; x[u][cc].w += p4.w;
+                                if (a.cache_window) {
+                                    x[u][cc] = *reinterpret_cast<const float4*>(s_cache + l * D + col);
+                                } else {
+                                    x[u][cc] = ldg4(tab + s_win[l] + col);
+                                    if (pe) {
+                                        const float4 p4 = ldg4(pe + s_pe[l] + col);
+                                        x[u][cc].x += p4.x; x[u][cc].y += p4.y; x[u][cc].z += p4.z; x[u][cc].w += p4.w;
+                                    }
                                 }
                             }
                         }
@@ -508,15 +522,19 @@ __global__ void __cluster_dims__(RF_CL, 1, 1) __launch_bounds__(RF_THREADS, 1) r
 
 }  // namespace
 
-size_t rollout_fused_smem_bytes(const RfArgs& a) {
+static size_t base_smem_bytes(const RfArgs& a) {
     const int Lp = (a.L + 3) & ~3;
     const size_t floats = ((a.feat + 3) & ~3) + 10 * (size_t)a.D + 3 * (size_t)Lp + ((2 * (size_t)a.hid + 3) & ~3) + 2 * RF_WARPS + 4 + RF_PART;
-    return floats * 4 + (size_t)3 * a.L * 4 + 64;
+    return floats * 4 + (size_t)3 * Lp * 4 + 64;
+}
+static bool window_fits(const RfArgs& a) { return base_smem_bytes(a) + (size_t)a.L * a.D * 4 <= 200 * 1024; }
+size_t rollout_fused_smem_bytes(const RfArgs& a) {
+    return base_smem_bytes(a) + (window_fits(a) ? (size_t)a.L * a.D * 4 : 0);
 }
 
 bool rollout_fused_supported(const RfArgs& a) {
     return a.D % 4 == 0 && a.D >= 8 && a.D <= 512 && RF_WARPS * a.D <= RF_PART && a.H >= 1 && a.D % a.H == 0 && a.hid % 4 == 0 &&
-           rollout_fused_smem_bytes(a) <= 200 * 1024;
+           base_smem_bytes(a) <= 200 * 1024;
 }
 
 int rollout_fused_forward(const RfArgs& a, cudaStream_t st) {
@@ -529,7 +547,9 @@ int rollout_fused_forward(const RfArgs& a, cudaStream_t st) {
         if (e != cudaSuccess) { trxl_set_error("rollout_fused: cannot reserve %zu bytes of shared memory", smem); return TRXL_ERR_CUDA; }
         attr_smem = smem;
     }
-    rollout_fused_kernel<<<a.N * RF_CL, RF_THREADS, smem, st>>>(a);
+    RfArgs b = a;
+    b.cache_window = window_fits(a) ? 1 : 0;
+    rollout_fused_kernel<<<a.N * RF_CL, RF_THREADS, smem, st>>>(b);
     TRXL_CHECK_LAUNCH("rollout_fused");
     return TRXL_OK;
 }

@@ -25,6 +25,7 @@ struct RfArgs {
     float* logits = nullptr;
     float* value = nullptr;
     float* out_mem = nullptr;
+    int cache_window = 0;      // set by the launcher: the head's window (L x D floats) is kept in shared memory between the two passes
 };
 
 size_t rollout_fused_smem_bytes(const RfArgs& a);

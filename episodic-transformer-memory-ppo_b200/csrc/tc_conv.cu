@@ -25,7 +25,9 @@ namespace {
 
 using namespace tc;
 
-constexpr int BM = 128, BK = TCG_BK, THREADS = 160, STAGES = 2;        // 2 stages x <= 48 KB: two CTAs per SM
+constexpr int BM = 128, BK = TCG_BK, THREADS = 160;
+// STAGES = 2 (<= 48 KB per stage): two CTAs per SM for the training-sized grids; STAGES = 4: one CTA per SM with three
+// k-blocks in flight for rollout-sized grids (fewer CTAs than SMs, pure latency)
 // The tensor core adds into the TMEM accumulator with truncation, so the rounding error grows with the length of the
 // accumulation chain.  Three accumulators keep it at fp32-SIMT level: hi*hi products alternate between two of them (halving
 // the chain that carries the magnitude), the ~2^-11 smaller cross terms go to the third, and the epilogue adds them (RN).
@@ -75,8 +77,8 @@ __device__ __forceinline__ void load_accumulators(uint32_t taddr, uint32_t (&v)[
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-template <int BN>
-__global__ void __launch_bounds__(THREADS, 2) tc_conv_gather_kernel(const __grid_constant__ GatherArgs a) {
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(THREADS, STAGES == 2 ? 2 : 1) tc_conv_gather_kernel(const __grid_constant__ GatherArgs a) {
     extern __shared__ __align__(1024) unsigned char tcc_smem[];
     constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     constexpr int P = STAGES - 1;                                    // stages in flight ahead of the MMA
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(THREADS, 2) tc_conv_gather_kernel(const __grid
 // grid (K tiles of 128, row splits).  Shared-memory tiles are MN-major in the SWIZZLE_128B_BASE32B layout (the only one
 // TF32 has for MN-major): [32-element M/N group][row / 4][row % 4][128 bytes], 32-byte chunks XOR-swizzled with row % 4.
 // One 128-byte global run (32 consecutive k of one row, or 32 consecutive channels of one dY row) is one shared row.
-template <int BN>
+template <int BN, int STAGES>
 __global__ void __launch_bounds__(THREADS, 2) tc_conv_wgrad_kernel(const __grid_constant__ WgradArgs a) {
     extern __shared__ __align__(1024) unsigned char tcc_smem[];
     constexpr int A_BYTES = 128 * 32 * 4, B_BYTES = BN * 32 * 4, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
@@ -530,26 +532,31 @@ void carve(const TcgEncoder& e, long long n, float* base, Ws& w) {
     w.total = off;
 }
 
-template <int BN>
-int launch_gather(cudaStream_t st, const GatherArgs& a) {
+template <int BN, int STAGES>
+int launch_gather_stages(cudaStream_t st, const GatherArgs& a) {
     constexpr size_t smem = (size_t)STAGES * (2 * BM * BK * 4 + 2 * BN * BK * 4) + (2 * STAGES + 1) * 8 + 16 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_conv_gather_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(tc_conv_gather_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { trxl_set_error("tc_conv: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e)); return TRXL_ERR_CUDA; }
         attr_set = true;
     }
-    if (a.M <= 0) return TRXL_OK;
-    tc_conv_gather_kernel<BN><<<trxl_cdiv(a.M, BM), THREADS, smem, st>>>(a);
+    tc_conv_gather_kernel<BN, STAGES><<<trxl_cdiv(a.M, BM), THREADS, smem, st>>>(a);
     TRXL_CHECK_LAUNCH("tc_conv_gather");
     return TRXL_OK;
 }
 template <int BN>
+int launch_gather(cudaStream_t st, const GatherArgs& a) {
+    if (a.M <= 0) return TRXL_OK;
+    return trxl_cdiv(a.M, BM) <= 148 ? launch_gather_stages<BN, 4>(st, a) : launch_gather_stages<BN, 2>(st, a);
+}
+template <int BN>
 int launch_wgrad(cudaStream_t st, WgradArgs a, int layer, int C, float* dw, const Ws& w) {
+    constexpr int STAGES = 2;
     constexpr size_t smem = (size_t)STAGES * (2 * 128 * 32 * 4 + 2 * BN * 32 * 4) + (2 * STAGES + 1) * 8 + 16 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_conv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(tc_conv_wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { trxl_set_error("tc_conv: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e)); return TRXL_ERR_CUDA; }
         attr_set = true;
     }
@@ -558,7 +565,7 @@ int launch_wgrad(cudaStream_t st, WgradArgs a, int layer, int C, float* dw, cons
     plan_split(a.M, ktiles, &a.rows_per_split, &splits);
     TRXL_CHECK_ARG((long long)splits * K * BN <= w.partial_floats, "tc_conv: wgrad partial buffer too small");
     a.partial = w.partial;
-    tc_conv_wgrad_kernel<BN><<<dim3(ktiles, splits), THREADS, smem, st>>>(a);
+    tc_conv_wgrad_kernel<BN, STAGES><<<dim3(ktiles, splits), THREADS, smem, st>>>(a);
     TRXL_CHECK_LAUNCH("tc_conv_wgrad");
     wgrad_reduce_kernel<<<grid_for((long long)K * BN), 256, 0, st>>>(w.partial, splits, K, BN, layer, C, dw);
     TRXL_CHECK_LAUNCH("wgrad_reduce");
