@@ -141,9 +141,9 @@ class ActorCriticModel(nn.Module):
         if missing or extra:
             raise RuntimeError("parameter layout mismatch: missing %s extra %s" % (missing, extra))
         self._trunk_names = {n for n, *_ in self._layout if not n.startswith("conv")}
-        # the one-launch per-sample trunk kernel (csrc/rollout_fused.cu) is correct but, as measured on B200 (r1), still
-        # slower than the layered path at W=32 (latency-bound GEMV chains); opt in with TRXL_FUSED_ROLLOUT=1
-        self._fused_ok = native.fused_forward_supported(self._cfg) and os.environ.get("TRXL_FUSED_ROLLOUT", "0") == "1"
+        # rollout-sized forwards (n <= FUSED_MAX_BATCH, no grad) run the one-launch cluster kernel (csrc/rollout_fused.cu): a
+        # 4-CTA cluster per sample instead of ~45 latency-bound launches; TRXL_FUSED_ROLLOUT=0 keeps the layered path
+        self._fused_ok = native.fused_forward_supported(self._cfg) and os.environ.get("TRXL_FUSED_ROLLOUT", "1") != "0"
         # training-time encoder on the tcgen05 tensor cores (3xTF32 implicit GEMMs); TRXL_CUDNN_ENCODER=1 keeps cuDNN
         self._tc_encoder = (self._visual and os.environ.get("TRXL_CUDNN_ENCODER", "0") != "1" and
                             native.conv_train_supported(self._cfg, *self.observation_space_shape[1:]))
@@ -289,7 +289,7 @@ class ActorCriticModel(nn.Module):
         native.conv_train_backward(self._cfg, self._grad_arena, n, h, w, self._enc_ws(n, h, w)[0], dfeat)
 
     # ------------------------------------------------------------------------------ native trunk
-    FUSED_MAX_BATCH = 96      # batch sizes eligible for the opt-in one-launch per-sample trunk kernel
+    FUSED_MAX_BATCH = 96      # batch sizes that take the one-launch cluster-per-sample trunk kernel
 
     def forward_table(self, feat, table, ep_index, win_index, mask, pe_index, sample_index=None, n=None, ws=None, out=None,
                       fused=None):
