@@ -15,8 +15,9 @@
 //   tc_conv_wgrad_kernel   dW[K, BN] = gather(A)[rows, K]^T * dY[rows, BN]: the reduction runs over the GEMM rows, so both
 //                          operands are MN-major in shared memory (same 128-byte global runs as the forward gather);
 //                          rows are split across CTAs and the partials summed in fixed order (deterministic).
-// Pipeline per CTA: STAGES-deep ring; producers cp.async a stage, cp.async.wait_group, fence.proxy.async, arrive on the
-// stage's `full` mbarrier; the MMA lane waits, issues the stage's MMAs and tcgen05.commit's the `empty` mbarrier.
+// Pipeline per CTA: STAGES-deep ring; producers cp.async a stage and attach `cp.async.mbarrier.arrive.noinc` to the stage's
+// `full` mbarrier (no producer ever waits for its own copies, so all stages stay in flight); the MMA warp waits on `full`,
+// runs fence.proxy.async, issues the stage's MMAs and tcgen05.commit's the `empty` mbarrier.
 #include "tc_conv.cuh"
 
 #include "tc_common.cuh"
@@ -81,7 +82,6 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(THREADS, STAGES == 2 ? 2 : 1) tc_conv_gather_kernel(const __grid_constant__ GatherArgs a) {
     extern __shared__ __align__(1024) unsigned char tcc_smem[];
     constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    constexpr int P = STAGES - 1;                                    // stages in flight ahead of the MMA
     unsigned char* tiles = tcc_smem + ((1024u - (smem_u32(tcc_smem) & 1023u)) & 1023u);      // swizzled layouts need an aligned base
     uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
     uint64_t* empty = full + STAGES;
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(THREADS, STAGES == 2 ? 2 : 1) tc_conv_gather_k
         s_rowyx[threadIdx.x] = (ay << 16) | ax;
     }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 4); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
         mbar_init(tmem_full, 1);
         mbar_init_fence();
     }
@@ -135,8 +135,8 @@ __global__ void __launch_bounds__(THREADS, STAGES == 2 ? 2 : 1) tc_conv_gather_k
         for (int i = 0; i < 8; ++i) { rbase[i] = s_rowbase[r0 + 16 * i]; ryx[i] = s_rowyx[r0 + 16 * i]; }
         const uint32_t dst0 = (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128 + ((piece ^ (r0 & 7)) * 16));
         const int K = nkb * BK;
-        for (int it = 0; it < nkb + P; ++it) {
-            if (it < nkb) {
+        for (int it = 0; it < nkb; ++it) {
+            {
                 const int s = it % STAGES;
                 mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
                 const int tdy = s_dy[it], tdx = s_dx[it];
@@ -158,13 +158,7 @@ __global__ void __launch_bounds__(THREADS, STAGES == 2 ? 2 : 1) tc_conv_gather_k
                     cp_async16(dstb + i * 2048, a.b_hi + boff + (long long)i * 16 * K, 16u);
                     cp_async16(dstb + B_BYTES + i * 2048, a.b_lo + boff + (long long)i * 16 * K, 16u);
                 }
-            }
-            cp_async_commit();
-            if (it >= P) {
-                cp_async_wait<P>();                  // the copies of k-block it-P have landed
-                fence_async_proxy();                 // ... and are visible to the tensor core (async proxy)
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full[(it - P) % STAGES]);
+                cp_async_arrive(&full[s]);           // fires when this thread's copies of the stage have landed; nobody waits
             }
         }
         // ---------------- epilogue: TMEM -> registers -> bias / ReLU / mask -> pre-split NHWC stores ----------------
@@ -205,6 +199,7 @@ __global__ void __launch_bounds__(THREADS, STAGES == 2 ? 2 : 1) tc_conv_gather_k
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % STAGES;
             mbar_wait(&full[s], (kb / STAGES) & 1);
+            fence_async_proxy();                     // the landed copies (generic proxy) -> visible to the MMAs this warp issues
             fence_after_sync();
             if (lane == 0) {
                 const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_BYTES;
@@ -239,7 +234,6 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(THREADS, 2) tc_conv_wgrad_kernel(const __grid_constant__ WgradArgs a) {
     extern __shared__ __align__(1024) unsigned char tcc_smem[];
     constexpr int A_BYTES = 128 * 32 * 4, B_BYTES = BN * 32 * 4, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    constexpr int P = STAGES - 1;
     unsigned char* tiles = tcc_smem + ((1024u - (smem_u32(tcc_smem) & 1023u)) & 1023u);      // swizzled layouts need an aligned base
     uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
     uint64_t* empty = full + STAGES;
@@ -255,7 +249,7 @@ __global__ void __launch_bounds__(THREADS, 2) tc_conv_wgrad_kernel(const __grid_
     const int K = a.g.nkb * BK;
     stage_taps(a.g, s_tapoff, s_dy, s_dx);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 4); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
         mbar_init(tmem_full, 1);
         mbar_init_fence();
     }
@@ -289,8 +283,8 @@ __global__ void __launch_bounds__(THREADS, 2) tc_conv_wgrad_kernel(const __grid_
         }
         const uint32_t sw = (uint32_t)(ml0 & 3);
         const uint32_t off0 = (uint32_t)((ml0 >> 2) * 512 + (ml0 & 3) * 128 + (((uint32_t)(piece >> 1) ^ sw) * 32) + (piece & 1) * 16);
-        for (int it = 0; it < nst + P; ++it) {
-            if (it < nst) {
+        for (int it = 0; it < nst; ++it) {
+            {
                 const int s = it % STAGES;
                 mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
                 const uint32_t dsta = smem_base + s * STAGE_BYTES + off0;
@@ -322,13 +316,7 @@ __global__ void __launch_bounds__(THREADS, 2) tc_conv_wgrad_kernel(const __grid_
                     while (rrx[h] >= a.g.rw) { rrx[h] -= a.g.rw; ++rry[h]; }
                     while (rry[h] >= a.g.rh) { rry[h] -= a.g.rh; ++rn[h]; }
                 }
-            }
-            cp_async_commit();
-            if (it >= P) {
-                cp_async_wait<P>();
-                fence_async_proxy();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full[(it - P) % STAGES]);
+                cp_async_arrive(&full[s]);
             }
         }
         // ---------------- epilogue: this split's partial dW tile ----------------
@@ -352,6 +340,7 @@ __global__ void __launch_bounds__(THREADS, 2) tc_conv_wgrad_kernel(const __grid_
         for (int st = 0; st < nst; ++st) {
             const int s = st % STAGES;
             mbar_wait(&full[s], (st / STAGES) & 1);
+            fence_async_proxy();
             fence_after_sync();
             if (lane == 0) {
                 const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_BYTES;
