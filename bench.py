@@ -231,7 +231,9 @@ def run_b200(args, cfg, name):
         obs_bytes = int(np.prod(env_cfg["obs_shape"])) * 4
         e2e = {"value": world * W * T * n_e2e / float(dt), "unit": UNIT,
                "h2d_bytes_per_step": T * (W * obs_bytes + 2 * W * 8), "d2h_bytes_per_step": T * W * 8 + 40 * 4 * 32,
-               "updates_timed": n_e2e, "env_transport": "1 process per env, pipes (worker.py)",
+               "updates_timed": n_e2e,
+               "env_transport": ("1 process per env; observations through a shared pinned slab, actions/acks through shared-memory "
+                                 "stepping (worker.py)" if tr._control is not None else "1 process per env, pipes (worker.py)"),
                "env_wait_s_per_update": tr.timers["env"] / n_e2e, "rollout_s_per_update": tr.timers["rollout"] / n_e2e,
                "train_s_per_update": tr.timers["train"] / n_e2e}
         tr.close(exit_process=False)
