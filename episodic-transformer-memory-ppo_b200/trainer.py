@@ -93,11 +93,12 @@ class PPOTrainer:
         self._control = None          # shared-memory stepping arrays (own workers only)
         if workers is None:
             self._obs_slab = torch.zeros((self.num_workers,) + self.obs_shape, dtype=torch.float32).share_memory_()
-            # spin-wait stepping needs a core per env process; when the box is oversubscribed (many ranks x workers)
-            # fall back to the blocking pipe protocol, where waiting processes sleep in the kernel
             procs = self.dp.world_size * (self.num_workers + 1)
-            if os.environ.get("TRXL_PIPE_STEPPING", "0") != "1" and 1.25 * procs <= (os.cpu_count() or 1):
-                self._control = make_control(self.num_workers, len(self.action_space_shape))
+            if os.environ.get("TRXL_PIPE_STEPPING", "0") != "1":
+                # spinning workers answer fastest but need an idle physical core each (measured on the 128-thread B200 host:
+                # 2 ranks x 32 spinning workers tripled the env wait); otherwise workers block on a semaphore between steps
+                spin = os.environ.get("TRXL_SPIN_STEPPING", "1" if 4 * procs <= (os.cpu_count() or 1) + 8 else "0") == "1"
+                self._control = make_control(self.num_workers, len(self.action_space_shape), blocking=not spin)
             workers = [Worker(self._env_config(w), self._obs_slab, w, self._control) for w in range(self.num_workers)]
             rc = torch.cuda.cudart().cudaHostRegister(self._obs_slab.data_ptr(), self._obs_slab.numel() * 4, 0)
             self._slab_pinned = (int(rc) == 0) if not isinstance(rc, tuple) else (int(rc[0]) == 0)
@@ -387,6 +388,9 @@ class PPOTrainer:
         c["actions"].numpy()[...] = actions
         cmd = c["cmd"].numpy()
         cmd += 1
+        if c.get("sems"):
+            for sem in c["sems"]:
+                sem.release()
         ack = c["ack"].numpy()
         deadline = time.perf_counter() + 120.0
         while not np.array_equal(ack, cmd):

@@ -32,10 +32,15 @@ class WorkerException(Exception):
         raise self.ee
 
 
-def make_control(n_workers, n_branches):
-    """Shared arrays of the stepping fast path (torch tensors in shared memory, inherited by fork)."""
+def make_control(n_workers, n_branches, blocking=False):
+    """Shared arrays of the stepping fast path (torch tensors in shared memory, inherited by fork).
+    ``blocking=True`` adds one semaphore per worker: workers then sleep in the kernel between steps instead of
+    spinning on their command counter (needed as soon as env processes outnumber idle cores: spinning siblings slow
+    the envs that are actually stepping)."""
     import torch
-    return {"actions": torch.zeros((n_workers, n_branches), dtype=torch.int64).share_memory_(),
+    sems = [multiprocessing.get_context("fork").Semaphore(0) for _ in range(n_workers)] if blocking else None
+    return {"sems": sems,
+            "actions": torch.zeros((n_workers, n_branches), dtype=torch.int64).share_memory_(),
             "rewards": torch.zeros(n_workers, dtype=torch.float32).share_memory_(),
             "dones": torch.zeros(n_workers, dtype=torch.uint8).share_memory_(),
             "has_info": torch.zeros(n_workers, dtype=torch.uint8).share_memory_(),
@@ -72,9 +77,26 @@ def worker_process(remote, config, obs_slab=None, index=0, control=None):
         c_done, c_info = control["dones"].numpy(), control["has_info"].numpy()
         c_cmd, c_ack = control["cmd"].numpy(), control["ack"].numpy()
         last, idle = int(c_cmd[index]), 0
+        sem = control["sems"][index] if control.get("sems") else None
     while True:
         try:
-            if control is not None:
+            if control is not None and sem is not None:
+                # blocking variant: sleep on the semaphore; the pipe (control messages) is polled every 20 ms
+                if sem.acquire(timeout=0.02):
+                    seq = int(c_cmd[index])
+                    obs, reward, done, info = env.step(c_act.copy())
+                    if info:
+                        remote.send(info)
+                        obs = env.reset()
+                    if slot is not None:
+                        slot[...] = obs
+                    c_rew[index], c_done[index], c_info[index] = reward, 1 if done else 0, 1 if info else 0
+                    last = seq
+                    c_ack[index] = seq
+                    continue
+                if not remote.poll(0):
+                    continue
+            elif control is not None:
                 # spin on the command counter; fall back to the pipe for control messages; back off when idle
                 seq = int(c_cmd[index])
                 if seq != last:

@@ -219,3 +219,45 @@ def test_two_rank_gradient_allreduce_matches_single_rank(tmp_path):
                         "127.0.0.1", "--master-port", "29611", str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
+
+
+@pytest.mark.parametrize("blocking", [False, True])
+def test_shared_memory_stepping_modes(blocking):
+    """The rollout's env transport (worker.py): spinning and semaphore-blocking workers speak the same protocol --
+    actions in, (reward, done) out through shared arrays, observation into the shared slab, auto-reset + info on the pipe."""
+    import time
+    from worker import Worker, make_control
+    n, obs_shape = 3, (3, 8, 8)
+    slab = torch.zeros((n,) + obs_shape, dtype=torch.float32).share_memory_()
+    control = make_control(n, 1, blocking=blocking)
+    cfg = {"type": "Synthetic", "obs_shape": list(obs_shape), "n_actions": 4, "max_episode_steps": 5, "min_episode_steps": 2, "seed": 0}
+    workers = [Worker(dict(cfg, seed=w), slab, w, control) for w in range(n)]
+    try:
+        for w in workers:
+            w.child.send(("reset", None))
+        for w in workers:
+            assert w.child.recv() is None            # the observation went to the slab
+        first = slab.clone()
+        assert float(first.abs().sum()) > 0
+        infos = 0
+        for step in range(12):
+            control["actions"].numpy()[...] = step % 4
+            control["cmd"].numpy()[...] += 1
+            if control["sems"]:
+                for sem in control["sems"]:
+                    sem.release()
+            deadline = time.time() + 20
+            while not np.array_equal(control["ack"].numpy(), control["cmd"].numpy()):
+                assert time.time() < deadline, "workers did not acknowledge"
+            for w in np.nonzero(control["has_info"].numpy())[0]:
+                assert control["dones"].numpy()[w] == 1
+                assert isinstance(workers[int(w)].child.recv(), dict)
+                infos += 1
+        assert infos >= n                            # max_episode_steps = 5: every env finished at least once in 12 steps
+        assert not torch.equal(first, slab)
+    finally:
+        for w in workers:
+            w.child.send(("close", None))
+        for w in workers:
+            w.child.recv()
+            w.process.join(5)
