@@ -95,6 +95,8 @@ def main():
     for rep, title in (("attn_%s" % args.round, "fused window attention fwd/bwd, training minibatch (N=2048, L=128, D=256, H=4)"),
                        ("sgemm_%s" % args.round, "SIMT sgemm launches: 1 rollout step (M=32) + 1 minibatch step (M=2048)"),
                        ("tcgemm_%s" % args.round, "tcgen05 3xTF32 GEMM (opt-in), linear forward M=2048 N=256 K=256"),
+                       ("rollout_%s" % args.round, "one rollout step (W=32): tcgen05 conv1/2/3 forward + the cluster-per-sample fused trunk kernel "
+                                                   "(captured before the producers became fully asynchronous; two steps)"),
                        ("tcconv_%s" % args.round, "tcgen05 3xTF32 implicit-GEMM CNN encoder, one training minibatch (N=2048, 4x84x84): conv1/2/3 "
                                                   "forward, wgrad3, dgrad3, wgrad2, dgrad2 x4 parity classes, wgrad1 (launch order)")):
         p = os.path.join(args.src, rep + ".ncu-rep")
