@@ -338,17 +338,23 @@ class PPOTrainer:
         ctx = self._rollout_ctx()
         stream = torch.cuda.current_stream()
         env_time = 0.0
+        trace = [0.0, 0.0, 0.0] if os.environ.get("TRXL_E2E_TRACE") == "1" else None     # enqueue, device wait, env
         with torch.no_grad():
             for t in range(T):
                 # observations: host -> (pinned) -> device; cursors of every worker's live episode
+                ta = time.perf_counter()
                 self._upload_obs()
                 self._step_dev.copy_(self._step_host, non_blocking=True)
                 self._ep_dev.copy_(self._ep_host, non_blocking=True)
                 self._step_via_graph("workers", t, self._obs_dev, self._step_dev, self._ep_dev, ctx)
                 self._act_pinned.copy_(self._act_dev, non_blocking=True)
+                tb = time.perf_counter()
                 stream.synchronize()
                 actions = self._act_pinned.numpy()
                 te = time.perf_counter()
+                if trace is not None:
+                    trace[0] += tb - ta
+                    trace[1] += te - tb
                 if self._control is not None:
                     self._step_envs_shared(t, actions, episode_infos)
                     env_time += time.perf_counter() - te
@@ -372,6 +378,9 @@ class PPOTrainer:
                         self.obs[w] = obs
                 env_time += time.perf_counter() - te
         self._graphs_finish_rollout("workers")
+        if trace is not None:
+            print("[trxl] rollout trace per step: enqueue %.0f us, device wait %.0f us, env %.0f us" %
+                  (1e6 * trace[0] / T, 1e6 * trace[1] / T, 1e6 * env_time / T), flush=True)
         last_value = self.get_last_value()
         buf.calc_advantages(last_value, cfg["gamma"], cfg["lamda"])
         buf.memories = self._table[:self._n_episodes]
