@@ -91,6 +91,10 @@ class PPOTrainer:
         # (pass workers=[] together with trainer.device_feed = SyntheticDeviceFeed(...) to run without env processes)
         self._obs_slab = None
         self._control = None          # shared-memory stepping arrays (own workers only)
+        self._obs_on_device = False   # set when _step_envs_shared has already uploaded the new observations
+        g = max(1, self.num_workers // 4)
+        self._upload_chunks = ([(lo, min(self.num_workers, lo + g)) for lo in range(0, self.num_workers, g)]
+                               if os.environ.get("TRXL_CHUNKED_UPLOAD", "1") == "1" else [])
         if workers is None:
             self._obs_slab = torch.zeros((self.num_workers,) + self.obs_shape, dtype=torch.float32).share_memory_()
             procs = self.dp.world_size * (self.num_workers + 1)
@@ -232,6 +236,9 @@ class PPOTrainer:
     def _upload_obs(self):
         """Current observations of all workers -> device.  Shared pinned slab: one DMA; otherwise stage
         through a pinned buffer."""
+        if self._obs_on_device:                       # already copied group by group while the envs were stepping
+            self._obs_on_device = False
+            return
         if self._obs_slab is not None and self._slab_pinned:
             self._obs_dev.copy_(self._obs_slab, non_blocking=True)
         else:
@@ -402,9 +409,23 @@ class PPOTrainer:
                 sem.release()
         ack = c["ack"].numpy()
         deadline = time.perf_counter() + 120.0
-        while not np.array_equal(ack, cmd):
+        # While the slower workers are still stepping, the observations of the groups that have already answered go to the
+        # device (the stream is idle: the step that read obs_dev has been synchronised), so most of the host->device copy
+        # hides behind the env wait instead of sitting in front of the next GPU step.
+        chunks = self._upload_chunks
+        pending = list(range(len(chunks))) if (chunks and self._slab_pinned) else []
+        while True:
+            done = ack == cmd
+            for k in pending[:]:
+                lo, hi = chunks[k]
+                if done[lo:hi].all():
+                    self._obs_dev[lo:hi].copy_(self._obs_slab[lo:hi], non_blocking=True)
+                    pending.remove(k)
+            if done.all():
+                break
             if time.perf_counter() > deadline:
                 raise RuntimeError("environment workers did not answer within 120 s")
+        self._obs_on_device = bool(chunks and self._slab_pinned)
         buf.rewards[:, t] = c["rewards"].numpy()
         buf.dones[:, t] = c["dones"].numpy() != 0
         finished = np.nonzero(c["has_info"].numpy())[0]
