@@ -94,7 +94,7 @@ class PPOTrainer:
         self._obs_on_device = False   # set when _step_envs_shared has already uploaded the new observations
         g = max(1, self.num_workers // 4)
         self._upload_chunks = ([(lo, min(self.num_workers, lo + g)) for lo in range(0, self.num_workers, g)]
-                               if os.environ.get("TRXL_CHUNKED_UPLOAD", "1") == "1" else [])
+                               if os.environ.get("TRXL_CHUNKED_UPLOAD", "0") == "1" else [])
         if workers is None:
             self._obs_slab = torch.zeros((self.num_workers,) + self.obs_shape, dtype=torch.float32).share_memory_()
             procs = self.dp.world_size * (self.num_workers + 1)
@@ -409,9 +409,9 @@ class PPOTrainer:
                 sem.release()
         ack = c["ack"].numpy()
         deadline = time.perf_counter() + 120.0
-        # While the slower workers are still stepping, the observations of the groups that have already answered go to the
-        # device (the stream is idle: the step that read obs_dev has been synchronised), so most of the host->device copy
-        # hides behind the env wait instead of sitting in front of the next GPU step.
+        # Opt-in (TRXL_CHUNKED_UPLOAD=1): while the slower workers are still stepping, the observations of the groups that have
+        # already answered go to the device (the stream is idle: the step that read obs_dev has been synchronised).  Measured on
+        # the B200 host it only moves time from the device wait into the env wait (0.87 ms/step either way), so it is off.
         chunks = self._upload_chunks
         pending = list(range(len(chunks))) if (chunks and self._slab_pinned) else []
         while True:
