@@ -7,7 +7,9 @@ Storage is B200-first: every parameter is a view into ONE flat fp32 arena (and i
 into a twin arena), laid out by libtrxlppo (``trxl_layout_*``).  That gives the native trunk a single
 base pointer, makes clip+AdamW one fused pass, and makes the multi-GPU gradient exchange a single
 all-reduce of one buffer.  Everything after the CNN encoder (lin_hidden -> embedding -> blocks ->
-heads) runs in two native calls; the three conv layers still go through cuDNN.
+heads) runs in two native calls (one cluster-per-sample launch at rollout batch sizes); the three conv layers run as
+tcgen05 3xTF32 implicit GEMMs, forward and backward (csrc/tc_conv.cu), with cuDNN / im2col+SIMT GEMM kept for more than 4
+input channels.
 """
 import os
 
