@@ -30,7 +30,7 @@ from model import ActorCriticModel
 from optim_native import FusedClipAdamW
 from parallel import DataParallelContext
 from utils import create_env, polynomial_decay, process_episode_info
-from worker import Worker, make_control
+from worker import Worker, make_control, physical_cpus
 
 
 def build_mask_table(memory_length):
@@ -103,7 +103,13 @@ class PPOTrainer:
                 # 2 ranks x 32 spinning workers tripled the env wait); otherwise workers block on a semaphore between steps
                 spin = os.environ.get("TRXL_SPIN_STEPPING", "1" if 4 * procs <= (os.cpu_count() or 1) + 8 else "0") == "1"
                 self._control = make_control(self.num_workers, len(self.action_space_shape), blocking=not spin)
-            workers = [Worker(self._env_config(w), self._obs_slab, w, self._control) for w in range(self.num_workers)]
+            # one physical core per env worker when the box has enough of them (TRXL_PIN_WORKERS=0 leaves placement to the OS)
+            cores = physical_cpus() if os.environ.get("TRXL_PIN_WORKERS", "1") == "1" else []
+            if len(cores) < procs:
+                cores = []
+            first = 1 + self.dp.rank * (self.num_workers + 1)          # core `first - 1` is left to this rank's main thread
+            workers = [Worker(self._env_config(w), self._obs_slab, w, self._control,
+                              cpu=cores[(first + w) % len(cores)] if cores else None) for w in range(self.num_workers)]
             rc = torch.cuda.cudart().cudaHostRegister(self._obs_slab.data_ptr(), self._obs_slab.numel() * 4, 0)
             self._slab_pinned = (int(rc) == 0) if not isinstance(rc, tuple) else (int(rc[0]) == 0)
         self.workers = workers

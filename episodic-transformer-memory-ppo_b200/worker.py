@@ -48,9 +48,36 @@ def make_control(n_workers, n_branches, blocking=False):
             "ack": torch.zeros(n_workers, dtype=torch.int64).share_memory_()}
 
 
-def worker_process(remote, config, obs_slab=None, index=0, control=None):
+def physical_cpus():
+    """One logical CPU per physical core among the CPUs this process may run on (Linux topology files; falls back to the
+    plain affinity list).  Used to give every spinning env worker a core of its own: two busy-waiting hyper-thread
+    siblings slow each other and whichever of them is actually stepping its environment."""
+    import os
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return []
+    cores, seen = [], set()
+    for cpu in allowed:
+        try:
+            with open("/sys/devices/system/cpu/cpu%d/topology/thread_siblings_list" % cpu) as f:
+                sib = f.read().strip()
+        except OSError:
+            sib = str(cpu)
+        if sib not in seen:
+            seen.add(sib)
+            cores.append(cpu)
+    return cores
+
+
+def worker_process(remote, config, obs_slab=None, index=0, control=None, cpu=None):
     import os
     os.environ.setdefault("OMP_NUM_THREADS", "1")
+    if cpu is not None:
+        try:
+            os.sched_setaffinity(0, {int(cpu)})
+        except (AttributeError, OSError):
+            pass
     from utils import create_env
     try:
         env = create_env(config)
@@ -134,8 +161,8 @@ class Worker:
     child: multiprocessing.connection.Connection
     process: multiprocessing.Process
 
-    def __init__(self, env_config, obs_slab=None, index=0, control=None):
+    def __init__(self, env_config, obs_slab=None, index=0, control=None, cpu=None):
         ctx = multiprocessing.get_context("fork")
         self.child, parent = ctx.Pipe()
-        self.process = ctx.Process(target=worker_process, args=(parent, env_config, obs_slab, index, control), daemon=True)
+        self.process = ctx.Process(target=worker_process, args=(parent, env_config, obs_slab, index, control, cpu), daemon=True)
         self.process.start()
