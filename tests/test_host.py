@@ -114,6 +114,23 @@ def test_invalid_configs_are_rejected():
     assert native.workspace_floats(ok, 8) > 0
 
 
+def test_tensor_core_encoder_shape_gate_and_workspace():
+    """Host-side part of the tcgen05 encoder API: which observation shapes it covers, and that the workspace grows with
+    the batch (the kernels themselves need a GPU; their geometry is pinned in test_tc_conv_geometry.py)."""
+    import trxl_native as native
+    visual = native.make_config(32, 4, 1, 4, 16, 3136, "post", "relative", False, 8, (2,), conv_in_channels=3)
+    assert native.conv_train_supported(visual, 84, 84)
+    assert not native.conv_train_supported(visual, 30, 84)                          # too small for the 8/4, 4/2, 3/1 stack
+    many = native.make_config(32, 4, 1, 4, 16, 3136, "post", "relative", False, 8, (2,), conv_in_channels=6)
+    assert not native.conv_train_supported(many, 84, 84)                            # > 4 channels: cuDNN / im2col path
+    vector = native.make_config(32, 4, 1, 4, 16, 3, "post", "relative", False, 8, (2,))
+    assert not native.conv_train_supported(vector, 84, 84)
+    small, big = native.conv_train_workspace_floats(visual, 32, 84, 84), native.conv_train_workspace_floats(visual, 2048, 84, 84)
+    assert 0 < small < big and big * 4 < 4 << 30                                    # c3 minibatch: activations + gradients < 4 GB
+    with pytest.raises(ValueError):
+        native.conv_train_workspace_floats(many, 32, 84, 84)
+
+
 def test_utils_and_yaml(tmp_path):
     from utils import polynomial_decay, process_episode_info
     from yaml_parser import YamlParser
