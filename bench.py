@@ -293,7 +293,7 @@ def run_b200(args, cfg, name):
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": fwd_ms / max(1, fwd_n), "launches_timed": fwd_n,
-                "traffic": None,
+                "traffic": ncu_traffic_bytes("window_attn_fwd_kernel"), "traffic_source": "profiles/r1_ncu_attn.txt (ncu --set full, dram read + write per launch)",
                 "bwd_kernel": {"avg_launch_ms": bwd_ms / max(1, bwd_n), "launches_timed": bwd_n,
                                "achieved": (bytes_per_launch / (bwd_ms / max(1, bwd_n) * 1e-3) / 1e9) if bwd_n else None},
                 "share_of_step": (fwd_ms + bwd_ms) / ms if ms else None}
@@ -315,6 +315,27 @@ def run_b200(args, cfg, name):
 def _s(schedule):
     return {"initial": schedule["initial"], "final": schedule["final"], "max_decay_steps": schedule["max_decay_steps"],
             "power": schedule["power"]}
+
+
+def ncu_traffic_bytes(kernel, profile=os.path.join(ROOT, "profiles", "r1_ncu_attn.txt")):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the first launch of `kernel` in a committed ncu summary (bytes), or None."""
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        lines = open(profile).read().splitlines()
+    except OSError:
+        return None
+    total, inside, found = 0.0, False, 0
+    for ln in lines:
+        if ln.startswith("["):
+            if inside and found:
+                break
+            inside = kernel in ln
+            continue
+        parts = ln.split()
+        if inside and len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and parts[2] in scale:
+            total += float(parts[1].replace(",", "")) * scale[parts[2]]
+            found += 1
+    return total if found == 2 else None
 
 
 def main():
