@@ -121,6 +121,17 @@ int trxl_copy_rows(const void* src, void* dst, int64_t rows, int64_t row_bytes, 
     return TRXL_OK;
 }
 
+int trxl_copy_async(const void* src, void* dst, int64_t bytes, void* stream) {
+    TRXL_CHECK_ARG(src && dst && bytes >= 0, "copy_async: bad arguments");
+    if (bytes == 0) return TRXL_OK;
+    // cudaMemcpyDefault: the direction comes from unified addressing, so pinned (or cudaHostRegister'ed) host buffers and
+    // device buffers can be mixed; capturable into a CUDA graph as a memcpy node
+    cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, S(stream));
+    ++g_trxl_launches;
+    if (e != cudaSuccess) { trxl_set_error("copy_async: %s", cudaGetErrorString(e)); return TRXL_ERR_CUDA; }
+    return TRXL_OK;
+}
+
 int trxl_profile_enable(int on) {
     g_prof_on = on != 0;
     if (on) { g_prof_count[0] = 0; g_prof_count[1] = 0; }
@@ -345,6 +356,26 @@ int trxl_rollout_prepare(const int64_t* step, const int64_t* ep, const uint8_t* 
     TRXL_CHECK_ARG(step && mask_table && index_table && mask_out && idx_out, "rollout_prepare: null pointer");
     return ppo_rollout_prepare(S(stream), (cll)step, (cll)ep, mask_table, (cll)index_table, mask_out, mask_stride,
                                (long long*)idx_out, idx_stride, (long long*)ep_out, ep_stride, W, L);
+}
+
+int trxl_rollout_fetch(const float* obs_src, int64_t obs_floats, const int64_t* step_src, const int64_t* ep_src, float* obs_dev,
+                       float* obs_store, int64_t store_stride_floats, int64_t* step_dev, int64_t* ep_dev, int n, void* stream) {
+    TRXL_CHECK_ARG(obs_src && step_src && ep_src && obs_dev && obs_store && step_dev && ep_dev, "rollout_fetch: null pointer");
+    return ppo_rollout_fetch(S(stream), obs_src, obs_floats, (cll)step_src, (cll)ep_src, obs_dev, obs_store, store_stride_floats,
+                             (long long*)step_dev, (long long*)ep_dev, n);
+}
+
+int trxl_host_device_pointer(const void* host_ptr, void** device_ptr_out) {
+    TRXL_CHECK_ARG(host_ptr && device_ptr_out, "host_device_pointer: null pointer");
+    void* d = nullptr;
+    cudaError_t e = cudaHostGetDevicePointer(&d, const_cast<void*>(host_ptr), 0);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        trxl_set_error("host_device_pointer: %s (is the buffer pinned or cudaHostRegister'ed?)", cudaGetErrorString(e));
+        return TRXL_ERR_CUDA;
+    }
+    *device_ptr_out = d;
+    return TRXL_OK;
 }
 
 int trxl_memory_scatter(float* table, const int64_t* ep, const int64_t* step, const float* new_mem, int W, int64_t slots,

@@ -93,6 +93,57 @@ __global__ void rollout_prepare_kernel(const long long* __restrict__ step, const
     if (threadIdx.x == 0 && ep_out) ep_out[w * ep_stride] = ep[w];
 }
 
+// Fetch one rollout step's inputs in ONE kernel: observations (n, obs_floats) and the episode cursors (n,) from `*_src`
+// -- which may be pinned / cudaHostRegister'ed HOST memory read in place over PCIe (zero-copy; no copy-engine node, no
+// engine switch inside the captured step) -- into device staging buffers, and the observations also into their strided rows
+// of the rollout buffer (reference trainer.py:163).  Every thread keeps 4 independent 16-byte loads in flight.
+__global__ void rollout_fetch_kernel(const float4* __restrict__ obs_src, long long obs_vec4, const long long* __restrict__ step_src,
+                                     const long long* __restrict__ ep_src, float4* __restrict__ obs_dev, float4* __restrict__ obs_store,
+                                     long long store_stride_vec4, long long* __restrict__ step_dev, long long* __restrict__ ep_dev, int n) {
+    const long long total = (long long)n * obs_vec4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        step_dev[i] = step_src[i];
+        ep_dev[i] = ep_src[i];
+    }
+    for (; i < total; i += 4 * stride) {
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long j = i + k * stride;
+            if (j < total) v[k] = obs_src[j];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long j = i + k * stride;
+            if (j < total) {
+                obs_dev[j] = v[k];
+                const long long w = j / obs_vec4;
+                obs_store[w * store_stride_vec4 + (j - w * obs_vec4)] = v[k];
+            }
+        }
+    }
+}
+
+// scalar variant for observation sizes that are not a multiple of 4 floats (small vector observations)
+__global__ void rollout_fetch_scalar_kernel(const float* __restrict__ obs_src, long long obs_floats, const long long* __restrict__ step_src,
+                                            const long long* __restrict__ ep_src, float* __restrict__ obs_dev, float* __restrict__ obs_store,
+                                            long long store_stride, long long* __restrict__ step_dev, long long* __restrict__ ep_dev, int n) {
+    const long long total = (long long)n * obs_floats;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        step_dev[i] = step_src[i];
+        ep_dev[i] = ep_src[i];
+    }
+    for (; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const float v = obs_src[i];
+        obs_dev[i] = v;
+        const long long w = i / obs_floats;
+        obs_store[w * store_stride + (i - w * obs_floats)] = v;
+    }
+}
+
 // ------------------------------------------------------------------------------------ action sampling
 // Inverse-CDF sampling from softmax(logits) per branch with caller-provided uniforms (torch RNG).
 __global__ void sample_actions_kernel(const float* __restrict__ logits, int sumA, const float* __restrict__ u,
@@ -338,6 +389,31 @@ int ppo_rollout_prepare(cudaStream_t st, const long long* step, const long long*
     rollout_prepare_kernel<<<W, 64, 0, st>>>(step, ep, mask_table, index_table, mask_out, mask_stride, idx_out, idx_stride,
                                             ep_out, ep_stride, L);
     TRXL_CHECK_LAUNCH("rollout_prepare");
+    return TRXL_OK;
+}
+
+int ppo_rollout_fetch(cudaStream_t st, const float* obs_src, long long obs_floats, const long long* step_src, const long long* ep_src,
+                      float* obs_dev, float* obs_store, long long store_stride_floats, long long* step_dev, long long* ep_dev, int n) {
+    if (n == 0) return TRXL_OK;
+    const bool vec = obs_floats % 4 == 0 && store_stride_floats % 4 == 0 && ((uintptr_t)obs_src % 16 == 0) &&
+                     ((uintptr_t)obs_dev % 16 == 0) && ((uintptr_t)obs_store % 16 == 0);
+    if (!vec) {
+        int sblocks = trxl_cdiv((long long)n * obs_floats, 256);
+        if (sblocks > 148 * 4) sblocks = 148 * 4;
+        if (sblocks < trxl_cdiv(n, 256)) sblocks = trxl_cdiv(n, 256);
+        rollout_fetch_scalar_kernel<<<sblocks, 256, 0, st>>>(obs_src, obs_floats, step_src, ep_src, obs_dev, obs_store,
+                                                            store_stride_floats, step_dev, ep_dev, n);
+        TRXL_CHECK_LAUNCH("rollout_fetch");
+        return TRXL_OK;
+    }
+    const long long vec4 = obs_floats / 4, total = vec4 * n;
+    int blocks = trxl_cdiv(total, 256 * 4);
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks < 1) blocks = 1;
+    rollout_fetch_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(obs_src), vec4, step_src, ep_src,
+                                                reinterpret_cast<float4*>(obs_dev), reinterpret_cast<float4*>(obs_store),
+                                                store_stride_floats / 4, step_dev, ep_dev, n);
+    TRXL_CHECK_LAUNCH("rollout_fetch");
     return TRXL_OK;
 }
 

@@ -42,6 +42,8 @@ int ppo_memory_scatter(cudaStream_t st, float* table, const long long* ep, const
 int ppo_rollout_prepare(cudaStream_t st, const long long* step, const long long* ep, const unsigned char* mask_table,
                         const long long* index_table, unsigned char* mask_out, long long mask_stride, long long* idx_out,
                         long long idx_stride, long long* ep_out, long long ep_stride, int W, int L);
+int ppo_rollout_fetch(cudaStream_t st, const float* obs_src, long long obs_floats, const long long* step_src, const long long* ep_src,
+                      float* obs_dev, float* obs_store, long long store_stride_floats, long long* step_dev, long long* ep_dev, int n);
 int ppo_sample_actions(cudaStream_t st, const float* logits, int sumA, const float* u, const long long* forced,
                        const BranchSpec& bs, long long* act_out,
                        long long act_stride, float* logp_out, long long logp_stride, long long* act_compact, int W);

@@ -23,10 +23,28 @@ def init_transformer_memory(trxl_conf, max_episode_steps, device):
         build_window_index_table(max_episode_steps, trxl_conf["memory_length"]).to(device)
 
 
-def run_episode(model, env, config, device, render=False, generator=None):
+def load_model(path, env, device):
+    """Load the reference's checkpoint format -- a pickled ``(state_dict, config)`` tuple (reference enjoy.py:47-57,
+    written by trainer._save_model) -- into an ActorCriticModel on ``device``.  Returns (model, config)."""
+    with open(path, "rb") as f:
+        state_dict, config = pickle.load(f)
+    model = ActorCriticModel(config, env.observation_space, (env.action_space.n,), env.max_episode_steps)
+    model.load_state_dict(state_dict)
+    model.to(device).eval()
+    return model, config
+
+
+def run_episode(model, env, config=None, device=None, render=False, record=False):
+    """Step one episode (reference enjoy.py:60-84).  ``model`` is an ActorCriticModel or the path of a saved
+    ``(state_dict, config)`` pickle.  Returns ``(info, rewards)``; with ``record=True`` a dict that also holds every
+    step's observation, value and normalised logits (used by the parity tests)."""
+    device = torch.device("cuda") if device is None else torch.device(device)
+    if isinstance(model, (str, os.PathLike)):
+        model, config = load_model(model, env, device)
     trxl = config["transformer"]
     memory, mask_table, index_table = init_transformer_memory(trxl, env.max_episode_steps, device)
     L, t, done, info, rewards = trxl["memory_length"], 0, False, None, []
+    trace = {"obs": [], "values": [], "logits": [], "actions": []}
     obs = env.reset()
     with torch.no_grad():
         while not done:
@@ -36,12 +54,20 @@ def run_episode(model, env, config, device, render=False, generator=None):
             mask = mask_table[max(0, min(t, L - 1))].unsqueeze(0)
             if render:
                 env.render()
-            policy, _value, new_memory = model(obs_t, window, mask, idx)
+            policy, value, new_memory = model(obs_t, window, mask, idx)
             memory[:, t] = new_memory
             action = [int(branch.sample().item()) for branch in policy]
+            if record:
+                trace["obs"].append(np.asarray(obs, dtype=np.float32).copy())
+                trace["values"].append(float(value[0]))
+                trace["logits"].append(policy[0].logits[0].cpu().numpy())
+                trace["actions"].append(action)
             obs, reward, done, info = env.step(action)
             rewards.append(reward)
             t += 1
+    if record:
+        trace.update(info=info, rewards=rewards, length=t)
+        return trace
     return info, rewards
 
 
@@ -51,11 +77,9 @@ def main(argv=None):
     args = ap.parse_args(argv)
     device = torch.device("cuda")          # the engine has no CPU path
     with open(args.model, "rb") as f:
-        state_dict, config = pickle.load(f)
+        _, config = pickle.load(f)
     env = create_env(config["environment"], render=True)
-    model = ActorCriticModel(config, env.observation_space, (env.action_space.n,), env.max_episode_steps)
-    model.load_state_dict(state_dict)
-    model.to(device).eval()
+    model, config = load_model(args.model, env, device)
     info, _ = run_episode(model, env, config, device, render=True)
     print("Episode length: " + str(info["length"]))
     print("Episode reward: " + str(info["reward"]))

@@ -161,7 +161,10 @@ class ActorCriticModel(nn.Module):
         named = dict(self.named_parameters())
         device = next(iter(named.values())).device
         arena = torch.zeros(self._arena_floats, dtype=torch.float32, device=device)
-        grads = torch.zeros_like(arena)
+        # the gradient arena carries an 8-float tail: the loss statistics of the step ride along in the single
+        # all-reduce of a multi-GPU optimiser step (parallel.py)
+        grads_full = torch.zeros(self._arena_floats + self.GRAD_TAIL, dtype=torch.float32, device=device)
+        grads = grads_full[:self._arena_floats]
         self._param_slices = []
         with torch.no_grad():
             for name, off, shape, _group in self._layout:
@@ -171,7 +174,7 @@ class ActorCriticModel(nn.Module):
                 p.data = arena[off:off + numel].view(shape)
                 p.grad = grads[off:off + numel].view(shape)
                 self._param_slices.append((name, off, numel, shape))
-        self._arena, self._grad_arena = arena, grads
+        self._arena, self._grad_arena, self._grad_full = arena, grads, grads_full
         self._pe_cache = None
         self._ws_cache = {}
         self._chunks = None
@@ -186,6 +189,15 @@ class ActorCriticModel(nn.Module):
 
     def flat_grads(self):
         return self._grad_arena
+
+    GRAD_TAIL = 8
+
+    def flat_grads_with_tail(self):
+        """Gradient arena + its 8-float tail (``stats_tail``) as one contiguous buffer: what a multi-GPU step all-reduces."""
+        return self._grad_full
+
+    def stats_tail(self):
+        return self._grad_full[self._arena_floats:self._arena_floats + 6]
 
     def grad_chunks(self, chunk=8192):
         """(nchunks, 3) int64 {start, length, group} table for the fused norm/clip kernel."""
@@ -222,11 +234,13 @@ class ActorCriticModel(nn.Module):
                 torch.empty((n, t.num_blocks, t.embed_dim), device=device))
 
     # ------------------------------------------------------------------------------ encoders
-    def encode(self, obs, weights_packed=False):
+    def encode(self, obs, weights_packed=False, slot=0):
         """CNN encoder for image observations (model.py:87-94); identity for vector observations.
         On the GPU the three convolutions run as tcgen05 implicit GEMMs (csrc/tc_conv.cu) for observations with up to
         4 channels, otherwise as im2col + SIMT GEMM without autograd and cuDNN under autograd.  ``weights_packed=True``
-        (rollout steps after the first: the weights are frozen) skips the conversion of the weights to tensor-core format."""
+        (rollout steps after the first: the weights are frozen) skips the conversion of the weights to tensor-core format.
+        ``slot`` selects one of several independent no-grad workspaces, so that worker groups of the rollout can run the
+        encoder concurrently on different streams."""
         if not self._visual:
             return obs
         if not obs.is_cuda:
@@ -238,11 +252,11 @@ class ActorCriticModel(nn.Module):
         obs = obs.contiguous()
         n, _, h, w = obs.shape
         if self._tc_encoder:
-            fresh = ("enci", n, h, w) not in self._ws_cache
-            ws = self._inference_enc_ws(n, h, w)
+            fresh = ("enci", n, h, w, slot) not in self._ws_cache
+            ws = self._inference_enc_ws(n, h, w, slot)
             native.conv_train_forward(self._cfg, self._arena, obs, None, n, ws[0], ws[1], repack=fresh or not weights_packed)
             return ws[1]
-        key = ("enc", n, h, w)
+        key = ("enc", n, h, w, slot)
         ws = self._ws_cache.get(key)
         if ws is None:
             ws = (torch.empty(native.conv_encoder_workspace_floats(self._cfg, n, h, w), dtype=torch.float32, device=obs.device),
@@ -251,8 +265,8 @@ class ActorCriticModel(nn.Module):
         native.conv_encoder_forward(self._cfg, self._arena, obs, ws[0], ws[1])
         return ws[1]
 
-    def _inference_enc_ws(self, n, h, w):
-        key = ("enci", n, h, w)
+    def _inference_enc_ws(self, n, h, w, slot=0):
+        key = ("enci", n, h, w, slot)
         ws = self._ws_cache.get(key)
         if ws is None:
             dev = self._arena.device
@@ -261,10 +275,10 @@ class ActorCriticModel(nn.Module):
             self._ws_cache[key] = ws
         return ws
 
-    def pack_encoder_weights(self, n, h, w):
+    def pack_encoder_weights(self, n, h, w, slot=0):
         """Convert the conv weights to tensor-core format for the no-grad encoder of batch size n (the rollout calls this
         once per rollout and then runs ``encode(..., weights_packed=True)`` while the weights are frozen)."""
-        native.conv_train_pack_weights(self._cfg, self._arena, n, h, w, self._inference_enc_ws(n, h, w)[0])
+        native.conv_train_pack_weights(self._cfg, self._arena, n, h, w, self._inference_enc_ws(n, h, w, slot)[0])
 
     def _enc_ws(self, n, h, w):
         key = ("enct", n, h, w)

@@ -33,6 +33,58 @@ from utils import create_env, polynomial_decay, process_episode_info
 from worker import Worker, make_control, physical_cpus
 
 
+def save_model_file(model, config, path):
+    """Write the reference's checkpoint format: ``pickle.dump((state_dict, config))`` with CPU tensors and the
+    reference's state_dict keys/shapes (reference trainer.py:356-362; read by enjoy.py:47-57)."""
+    state = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    with open(path, "wb") as f:
+        pickle.dump((state, config), f)
+
+
+def effective_cpus():
+    """CPUs this process tree may actually burn: the affinity mask capped by the cgroup CPU quota (cpu.max /
+    cfs_quota_us).  Busy-waiting env workers beyond this number get the whole container throttled by CFS."""
+    try:
+        n = float(len(os.sched_getaffinity(0)))
+    except AttributeError:
+        n = float(os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, float(quota) / float(period))
+    except (OSError, ValueError):
+        try:
+            quota = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            period = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota > 0:
+                n = min(n, quota / period)
+        except (OSError, ValueError):
+            pass
+    return n
+
+
+class _WorkerGroup:
+    """A contiguous slice [lo, hi) of the env workers that steps as a unit: its own CUDA stream, staging buffers,
+    per-step CUDA graphs and completion event, so one group's forward runs while another group's environments step."""
+    GPU, ENV, DONE = 0, 1, 2
+
+    def __init__(self, index, lo, hi, trainer):
+        dev, nb = trainer.device, len(trainer.action_space_shape)
+        self.index, self.lo, self.hi, self.n = index, lo, hi, hi - lo
+        self.stream = torch.cuda.Stream(device=dev)
+        self.event = torch.cuda.Event()
+        self.obs_dev = torch.zeros((self.n,) + trainer.obs_shape, dtype=torch.float32, device=dev)
+        self.act_dev = torch.zeros((self.n, nb), dtype=torch.long, device=dev)
+        self.act_pinned = torch.zeros((self.n, nb), dtype=torch.long).pin_memory()
+        self.act_host_dptr = native.host_device_pointer(self.act_pinned.data_ptr())     # kernels write the actions here
+        self.step_dev = torch.zeros(self.n, dtype=torch.long, device=dev)
+        self.ep_dev = torch.zeros(self.n, dtype=torch.long, device=dev)
+        self.rows = None            # (T, n) int64: flat buffer rows of this group's workers at each step
+        self.ws = self.outs = None
+        self.graphs = {}
+        self.t, self.phase = 0, self.DONE
+
+
 def build_mask_table(memory_length):
     """(L, L) strictly-lower-triangular float table (trainer.py:78); row min(step, L-1) is a sample's mask."""
     return torch.tril(torch.ones((memory_length, memory_length)), diagonal=-1)
@@ -91,17 +143,18 @@ class PPOTrainer:
         # (pass workers=[] together with trainer.device_feed = SyntheticDeviceFeed(...) to run without env processes)
         self._obs_slab = None
         self._control = None          # shared-memory stepping arrays (own workers only)
-        self._obs_on_device = False   # set when _step_envs_shared has already uploaded the new observations
-        g = max(1, self.num_workers // 4)
-        self._upload_chunks = ([(lo, min(self.num_workers, lo + g)) for lo in range(0, self.num_workers, g)]
-                               if os.environ.get("TRXL_CHUNKED_UPLOAD", "0") == "1" else [])
         if workers is None:
             self._obs_slab = torch.zeros((self.num_workers,) + self.obs_shape, dtype=torch.float32).share_memory_()
             procs = self.dp.world_size * (self.num_workers + 1)
             if os.environ.get("TRXL_PIPE_STEPPING", "0") != "1":
-                # spinning workers answer fastest but need an idle physical core each (measured on the 128-thread B200 host:
-                # 2 ranks x 32 spinning workers tripled the env wait); otherwise workers block on a semaphore between steps
-                spin = os.environ.get("TRXL_SPIN_STEPPING", "1" if 4 * procs <= (os.cpu_count() or 1) + 8 else "0") == "1"
+                # Spinning workers answer fastest but every one of them burns a CPU all the time: they are only used when
+                # all env processes of all ranks (+ the trainers) fit the CPUs this container may use (affinity capped by
+                # the cgroup quota -- measured on the B200 host: 33 spinners under a 16-CPU quota get CFS-throttled), and
+                # only on x86 (the handshake publishes with plain stores and relies on total store order).  Otherwise the
+                # workers sleep on a semaphore between steps.
+                import platform
+                can_spin = procs + 1 <= effective_cpus() and platform.machine() in ("x86_64", "AMD64")
+                spin = os.environ.get("TRXL_SPIN_STEPPING", "1" if can_spin else "0") == "1"
                 self._control = make_control(self.num_workers, len(self.action_space_shape), blocking=not spin)
             # one physical core per env worker when the box has enough of them (TRXL_PIN_WORKERS=0 leaves placement to the OS)
             cores = physical_cpus() if os.environ.get("TRXL_PIN_WORKERS", "1") == "1" else []
@@ -154,14 +207,44 @@ class PPOTrainer:
         self._mask_last = torch.zeros((W, L), dtype=torch.uint8, device=dev)
         self._train_state = {}
         self._ctx = None
+        # worker groups: with shared-memory stepping the workers are split into groups that alternate between the GPU (forward +
+        # sampling on the group's own stream) and the environments, so env stepping overlaps the other group's device work
+        n_groups = int(os.environ.get("TRXL_ROLLOUT_GROUPS", "2" if (self._control is not None and W >= 8) else "1"))
+        n_groups = max(1, min(n_groups, W))
+        bounds = [round(i * W / n_groups) for i in range(n_groups + 1)]
+        self._groups = [_WorkerGroup(i, bounds[i], bounds[i + 1], self) for i in range(n_groups) if bounds[i + 1] > bounds[i]]
+        self._whole = self._groups[0] if len(self._groups) == 1 else _WorkerGroup(len(self._groups), 0, W, self)
+        for grp in self._groups + [self._whole]:
+            grp.rows = self._rollout_rows[:, grp.lo:grp.hi].contiguous()
         self.use_cuda_graphs = os.environ.get("TRXL_NO_GRAPHS", "0") != "1"
-        self._graphs, self._graph_pool, self._capture_stream = {}, None, None
+        self._capture_stream = None
+        self._mapped = {}
         self._start_update = 0          # first update of run_training (advanced by load_checkpoint)
         self.device_feed = None         # optional device_feed.SyntheticDeviceFeed replacing the env workers (bench.py)
-        self._forced_actions = None     # optional (T, W, n_branches) int64 device tensor: replay these actions (parity tests)
+        self._forced_buf = None         # persistent (T, W, n_branches) int64 device buffer behind ``_forced_actions``
+        self._forced_on = False
+        self._graph_warm_rollouts = 1   # rollouts run eagerly before the per-step graphs are captured (lazy initialisation)
         self.timers = {"rollout": 0.0, "train": 0.0, "env": 0.0}
 
     # ------------------------------------------------------------------------------------------ setup helpers
+    @property
+    def _forced_actions(self):
+        """Optional (T, W, n_branches) int64 device tensor of actions to replay instead of sampling (parity tests).
+        Assigning copies into a persistent buffer, so CUDA graphs captured with forced actions stay valid when the
+        next update's actions are assigned."""
+        return self._forced_buf if self._forced_on else None
+
+    @_forced_actions.setter
+    def _forced_actions(self, value):
+        if value is None:
+            self._forced_on = False
+            return
+        value = value.to(self.device, torch.long)
+        if self._forced_buf is None or self._forced_buf.shape != value.shape:
+            self._forced_buf = torch.empty_like(value).contiguous()
+        self._forced_buf.copy_(value)
+        self._forced_on = True
+
     def _env_config(self, worker):
         cfg = dict(self.config["environment"])
         if cfg.get("type") == "Synthetic":
@@ -173,10 +256,15 @@ class PPOTrainer:
         return W + max(8, (W * T) // max(1, self.max_episode_length // 2))
 
     def _alloc_table(self, capacity):
+        """(Re)allocate the episode table.  Growing it mid-rollout is rare (the capacity doubles and persists): worker groups
+        may have steps in flight on their own streams, so the move is fenced by device-wide synchronisation."""
+        if self._table is not None:
+            torch.cuda.synchronize(self.device)
         new = torch.zeros((capacity, self.max_episode_length, self.num_blocks, self.embed_dim), dtype=torch.float32,
                           device=self.device)
         if self._table is not None:
             new[:self._table.shape[0]].copy_(self._table)
+            torch.cuda.synchronize(self.device)
         self._table, self._table_cap = new, capacity
 
     @property
@@ -239,17 +327,14 @@ class PPOTrainer:
             s[0], s[1], s[3], s[2], torch.mean(self.buffer.values).item(), torch.mean(self.buffer.advantages).item()))
 
     # ------------------------------------------------------------------------------------------ rollout
-    def _upload_obs(self):
-        """Current observations of all workers -> device.  Shared pinned slab: one DMA; otherwise stage
-        through a pinned buffer."""
-        if self._obs_on_device:                       # already copied group by group while the envs were stepping
-            self._obs_on_device = False
-            return
+    def _stage_host_obs(self, lo=0, hi=None):
+        """Host observations of workers [lo, hi) -> a pinned buffer the GPU can DMA from.  The shared slab is itself
+        registered as pinned memory (nothing to do); otherwise (pipe transport) stage through ``_obs_pinned``."""
+        hi = self.num_workers if hi is None else hi
         if self._obs_slab is not None and self._slab_pinned:
-            self._obs_dev.copy_(self._obs_slab, non_blocking=True)
-        else:
-            self._obs_pinned.copy_(torch.from_numpy(self.obs))
-            self._obs_dev.copy_(self._obs_pinned, non_blocking=True)
+            return self._obs_slab
+        self._obs_pinned[lo:hi].copy_(torch.from_numpy(self.obs[lo:hi]))
+        return self._obs_pinned
 
     def _rollout_ctx(self):
         """Persistent per-trainer rollout buffers (their addresses are baked into the captured CUDA
@@ -260,84 +345,127 @@ class PPOTrainer:
             self._ctx = {
                 "flat_mask": buf.memory_mask.view(torch.uint8).view(W * T, L), "flat_idx": buf.memory_indices.view(W * T, L),
                 "flat_ep": buf.memory_index.view(W * T), "inner": self.num_blocks * self.embed_dim,
-                "uniforms": torch.empty((T, W, nb), device=self.device), "ws": self.model.workspace(W),
-                "outs": self.model._alloc_outputs(W, self.device),
+                "uniforms": torch.empty((T, W, nb), device=self.device),
                 "step_sched": torch.zeros((T + 1, W), dtype=torch.long, device=self.device),
                 "ep_sched": torch.zeros((T + 1, W), dtype=torch.long, device=self.device),
             }
         self._ctx["uniforms"].uniform_()
-        # the weights are frozen during a rollout: convert them to tensor-core format once, outside the per-step graphs
-        self._ctx["enc_packed"] = False
-        if self.model._visual and self.model._tc_encoder:
-            self.model.pack_encoder_weights(self.num_workers, *self.obs_shape[1:])
-            self._ctx["enc_packed"] = True
         return self._ctx
 
-    # -- CUDA graphs: the ~60 small launches of one rollout step are captured once per step index and replayed,
-    #    which removes the host launch overhead that otherwise dominates a W=32 forward.
-    def _graph_key(self, mode):
-        return (mode, self._table.data_ptr(), self.model.flat_parameters().data_ptr())
+    def _prepare_group(self, grp):
+        """Per-rollout device preparation of a worker group: activation workspace / output buffers (once), and -- the
+        weights are frozen during a rollout -- conversion of the conv weights to tensor-core format once, outside the
+        per-step graphs.  Every group has its own encoder workspace slot: groups run concurrently on their own streams."""
+        if grp.outs is None:
+            grp.outs = self.model._alloc_outputs(grp.n, self.device)
+            grp.ws = None if (self.model._fused_ok and grp.n <= self.model.FUSED_MAX_BATCH) else \
+                torch.empty(self.model._ws_floats(grp.n), dtype=torch.float32, device=self.device)
+        grp.enc_packed = False
+        if self.model._visual and self.model._tc_encoder:
+            self.model.pack_encoder_weights(grp.n, *self.obs_shape[1:], slot=grp.index)
+            grp.enc_packed = True
 
-    def _step_via_graph(self, mode, t, obs_dev, step_dev, ep_dev, ctx):
-        if not self.use_cuda_graphs or self._forced_actions is not None:
-            return self._device_step(t, obs_dev, step_dev, ep_dev, ctx)
+    # -- CUDA graphs: the copies and ~10 launches of one rollout step of a worker group are captured once per step index and
+    #    replayed, which removes the host launch overhead that otherwise dominates a W=32 forward.
+    def _graph_key(self, mode):
+        forced = self._forced_buf.data_ptr() if self._forced_on else 0
+        return (mode, self._table.data_ptr(), self.model.flat_parameters().data_ptr(), forced)
+
+    def _step_via_graph(self, mode, grp, t, src):
+        """Enqueue step t of worker group ``grp`` on the current stream, as a CUDA-graph replay when possible."""
+        if not self.use_cuda_graphs:
+            return self._device_step(grp, t, src)
         key = self._graph_key(mode)
-        if self._graphs.get("key") != key:                       # table or parameter arena moved: start over
-            for old in self._graphs.get("steps", {}).values():
+        state = grp.graphs
+        if state.get("key") != key:                               # table or parameter arena moved: start over
+            for old in state.get("steps", {}).values():
                 native.graph_destroy(old)
-            self._graphs = {"key": key, "warm": 0, "steps": {}}
-        if self._graphs["warm"] < 1:                             # first rollout for this key runs eagerly (warm-up)
-            return self._device_step(t, obs_dev, step_dev, ep_dev, ctx)
-        g = self._graphs["steps"].get(t)
+            state.clear()
+            state.update(key=key, warm=0, steps={})
+        if state["warm"] < self._graph_warm_rollouts:             # first rollout for this key runs eagerly (warm-up)
+            return self._device_step(grp, t, src)
+        g = state["steps"].get(t)
         if g is None:
-            # Capture through the library's own graph API: the step consists only of libtrxlppo launches (no torch
+            # Capture through the library's own graph API: the step consists only of libtrxlppo calls (no torch
             # op, no allocation, no RNG inside), so nothing of torch's capture machinery is involved.
+            cur = torch.cuda.current_stream()
             if self._capture_stream is None:
                 self._capture_stream = torch.cuda.Stream(device=self.device)
             cs = self._capture_stream
-            cs.wait_stream(torch.cuda.current_stream())
+            cs.wait_stream(cur)
             try:
                 with torch.cuda.stream(cs):
                     native.graph_begin(cs.cuda_stream)
                     try:
-                        self._device_step(t, obs_dev, step_dev, ep_dev, ctx)
+                        self._device_step(grp, t, src)
                         g = native.graph_end(cs.cuda_stream)
                     except Exception:
                         native.graph_abort(cs.cuda_stream)
                         raise
-                torch.cuda.current_stream().wait_stream(cs)
-                self._graphs["steps"][t] = g
+                cur.wait_stream(cs)
+                state["steps"][t] = g
             except Exception as e:  # noqa: BLE001 -- capture is an optimisation; the eager path is the same kernels
                 torch.cuda.synchronize()
                 print("[trxl] CUDA-graph capture failed (%s); continuing with eager launches" % e)
                 self.use_cuda_graphs = False
-                return self._device_step(t, obs_dev, step_dev, ep_dev, ctx)
+                return self._device_step(grp, t, src)
         native.graph_launch(g)
 
-    def _graphs_finish_rollout(self, mode):
-        if self.use_cuda_graphs and self._graphs.get("key") == self._graph_key(mode):
-            self._graphs["warm"] += 1
+    def _graphs_finish_rollout(self, mode, groups):
+        if not self.use_cuda_graphs:
+            return
+        for grp in groups:
+            if grp.graphs.get("key") == self._graph_key(mode):
+                grp.graphs["warm"] += 1
 
-    def _device_step(self, t, obs_dev, step_dev, ep_dev, ctx):
-        """Everything the GPU does for rollout step t (trainer.py:161-186): store obs, write the mask /
-        window-index rows, run the model with the window read in place, write the new memory row,
-        sample actions, store actions / log-probs / values."""
-        buf, model = self.buffer, self.model
-        W, T, L, nb = self.num_workers, self.config["worker_steps"], self.memory_length, len(self.action_space_shape)
+    @property
+    def _graphs(self):
+        """Captured step graphs of the first worker group (introspection / tests)."""
+        return self._groups[0].graphs if self._groups[0].graphs else self._whole.graphs
+
+    def _device_step(self, grp, t, src):
+        """Everything the GPU does for rollout step t of worker group ``grp`` (trainer.py:161-186): fetch the observations
+        and episode cursors, store obs, write the mask / window-index rows, run the model with the window read in place,
+        write the new memory row, sample actions, store actions / log-probs / values, and hand the actions to the host.
+        ``src`` = (obs_ptr, step_ptr, ep_ptr, on_host): where this step's observations (n, *obs) and cursors (n,) live."""
+        buf, model, ctx = self.buffer, self.model, self._ctx
+        T, L, nb = self.config["worker_steps"], self.memory_length, len(self.action_space_shape)
+        n, lo = grp.n, grp.lo
         obs_bytes = int(np.prod(self.obs_shape)) * 4
-        native.copy_rows(obs_dev.data_ptr(), buf.obs.data_ptr() + t * obs_bytes, W, obs_bytes, obs_bytes, T * obs_bytes)
+        obs_ptr, step_ptr, ep_ptr, on_host = src
+        row0 = lo * T + t                             # flat buffer row of the group's first worker at step t
+        if on_host:
+            # pinned host memory is read IN PLACE by one kernel (zero-copy over PCIe): a captured step then consists of kernels
+            # only.  (Measured: three copy-engine nodes per step cost 160 us + ~250 us of engine-switch gaps at W = 16.)
+            obs_dev, step_dev, ep_dev = grp.obs_dev, grp.step_dev, grp.ep_dev
+            native.rollout_fetch(obs_ptr, obs_bytes // 4, step_ptr, ep_ptr, obs_dev, buf.obs.data_ptr() + row0 * obs_bytes,
+                                 T * obs_bytes // 4, step_dev, ep_dev, n)
+        else:                                         # device-resident feed: use the tensors in place
+            obs_dev, step_dev, ep_dev = obs_ptr, step_ptr, ep_ptr
+            native.copy_rows(obs_dev.data_ptr(), buf.obs.data_ptr() + row0 * obs_bytes, n, obs_bytes, obs_bytes, T * obs_bytes)
         native.rollout_prepare(step_dev, ep_dev, self._mask_table_dev, self._index_table_dev,
-                               ctx["flat_mask"].data_ptr() + t * L, T * L, ctx["flat_idx"].data_ptr() + t * L * 8, T * L,
-                               ctx["flat_ep"].data_ptr() + t * 8, T, W, L)
-        feat = model.encode(obs_dev, weights_packed=ctx["enc_packed"])
+                               ctx["flat_mask"].data_ptr() + row0 * L, T * L, ctx["flat_idx"].data_ptr() + row0 * L * 8, T * L,
+                               ctx["flat_ep"].data_ptr() + row0 * 8, T, n, L)
+        feat = model.encode(obs_dev, weights_packed=grp.enc_packed, slot=grp.index)
         logits, value, new_mem = model.forward_table(feat, self._table, ctx["flat_ep"], ctx["flat_idx"], ctx["flat_mask"],
-                                                     ctx["flat_idx"], sample_index=self._rollout_rows[t], n=W, ws=ctx["ws"],
-                                                     out=ctx["outs"])
+                                                     ctx["flat_idx"], sample_index=grp.rows[t], n=n, ws=grp.ws, out=grp.outs)
         native.memory_scatter(self._table, ep_dev, step_dev, new_mem, self.max_episode_length, ctx["inner"])
-        forced = None if self._forced_actions is None else self._forced_actions[t]
-        native.sample_actions(logits, ctx["uniforms"][t], self.action_space_shape, buf.actions.data_ptr() + t * nb * 8, T * nb,
-                              buf.log_probs.data_ptr() + t * nb * 4, T * nb, self._act_dev, W, forced=forced)
-        native.copy_rows(value.data_ptr(), buf.values.data_ptr() + t * 4, W, 4, 4, T * 4)
+        forced = None if self._forced_actions is None else self._forced_actions[t, lo:grp.hi]
+        native.sample_actions(logits, ctx["uniforms"][t, lo:grp.hi], self.action_space_shape,
+                              buf.actions.data_ptr() + row0 * nb * 8, T * nb, buf.log_probs.data_ptr() + row0 * nb * 4, T * nb,
+                              grp.act_host_dptr if on_host else grp.act_dev, n, forced=forced)      # actions land in host memory
+        native.copy_rows(value.data_ptr(), buf.values.data_ptr() + row0 * 4, n, 4, 4, T * 4)
+
+    def _host_src(self, grp, host_obs):
+        """Device-side addresses of this group's slices of the pinned host buffers (observations, cursors)."""
+        key = host_obs.data_ptr()
+        if self._mapped.get("key") != key:
+            self._mapped = {"key": key, "obs": native.host_device_pointer(host_obs.data_ptr()),
+                            "step": native.host_device_pointer(self._step_host.data_ptr()),
+                            "ep": native.host_device_pointer(self._ep_host.data_ptr())}
+        obs_bytes = int(np.prod(self.obs_shape)) * 4
+        m = self._mapped
+        return (m["obs"] + grp.lo * obs_bytes, m["step"] + grp.lo * 8, m["ep"] + grp.lo * 8, True)
 
     def _sample_training_data(self):
         """Run every worker for ``worker_steps`` steps (trainer.py:145-225)."""
@@ -345,104 +473,190 @@ class PPOTrainer:
             return self._sample_from_device_feed(self.device_feed)
         t0 = time.perf_counter()
         cfg, buf = self.config, self.buffer
-        T = cfg["worker_steps"]
-        episode_infos = []
         self._begin_rollout()
-        ctx = self._rollout_ctx()
-        stream = torch.cuda.current_stream()
-        env_time = 0.0
-        trace = [0.0, 0.0, 0.0] if os.environ.get("TRXL_E2E_TRACE") == "1" else None     # enqueue, device wait, env
+        self._rollout_ctx()
+        self._env_time = 0.0
         with torch.no_grad():
-            for t in range(T):
-                # observations: host -> (pinned) -> device; cursors of every worker's live episode
-                ta = time.perf_counter()
-                self._upload_obs()
-                self._step_dev.copy_(self._step_host, non_blocking=True)
-                self._ep_dev.copy_(self._ep_host, non_blocking=True)
-                self._step_via_graph("workers", t, self._obs_dev, self._step_dev, self._ep_dev, ctx)
-                self._act_pinned.copy_(self._act_dev, non_blocking=True)
-                tb = time.perf_counter()
-                stream.synchronize()
-                actions = self._act_pinned.numpy()
-                te = time.perf_counter()
-                if trace is not None:
-                    trace[0] += tb - ta
-                    trace[1] += te - tb
-                if self._control is not None:
-                    self._step_envs_shared(t, actions, episode_infos)
-                    env_time += time.perf_counter() - te
-                    continue
-                for w, worker in enumerate(self.workers):
-                    worker.child.send(("step", actions[w].copy()))
-                for w, worker in enumerate(self.workers):
-                    obs, buf.rewards[w, t], buf.dones[w, t], info = worker.child.recv()
-                    if info:                                   # episode finished (trainer.py:195)
-                        self._step_host[w] = 0
-                        episode_infos.append(info)
-                        worker.child.send(("reset", None))
-                        obs = worker.child.recv()
-                        # the finished episode keeps its table row; the worker continues on a fresh zero row
-                        self._ep_host[w] = self._new_row()
-                        if t < T - 1:
-                            self._n_episodes = self._n_rows
-                    else:
-                        self._step_host[w] += 1
-                    if obs is not None:                        # None: the worker already wrote it into the shared slab
-                        self.obs[w] = obs
-                env_time += time.perf_counter() - te
-        self._graphs_finish_rollout("workers")
-        if trace is not None:
-            print("[trxl] rollout trace per step: enqueue %.0f us, device wait %.0f us, env %.0f us" %
-                  (1e6 * trace[0] / T, 1e6 * trace[1] / T, 1e6 * env_time / T), flush=True)
+            if self._control is not None:
+                episode_infos = self._rollout_grouped()
+            else:
+                episode_infos = self._rollout_pipes()
         last_value = self.get_last_value()
         buf.calc_advantages(last_value, cfg["gamma"], cfg["lamda"])
         buf.memories = self._table[:self._n_episodes]
-        self.timers["env"] += env_time
+        self.timers["env"] += self._env_time
         self.timers["rollout"] += time.perf_counter() - t0
         return episode_infos
 
-    def _step_envs_shared(self, t, actions, episode_infos):
-        """Step every env worker through the shared-memory fast path (worker.py): publish the actions, bump
-        the command counters, wait for the acknowledgements, then apply the reference's bookkeeping
-        (trainer.py:193-218).  Finished episodes were already reset by their worker; their ``info`` arrives
-        on the pipe."""
+    def _rollout_pipes(self):
+        """The reference's transport (trainer.py:159-218): one forward over all workers, then 2 pipe messages per worker,
+        strictly serial.  Used for workers handed in by the caller (anything with a ``child`` pipe end) and with
+        TRXL_PIPE_STEPPING=1."""
+        buf, T, grp = self.buffer, self.config["worker_steps"], self._whole
+        episode_infos = []
+        self._prepare_group(grp)
+        stream = torch.cuda.current_stream()
+        for t in range(T):
+            self._check_cursors()
+            src = self._host_src(grp, self._stage_host_obs())
+            self._step_via_graph("pipes", grp, t, src)
+            stream.synchronize()
+            actions = grp.act_pinned.numpy()
+            te = time.perf_counter()
+            for w, worker in enumerate(self.workers):
+                worker.child.send(("step", actions[w].copy()))
+            for w, worker in enumerate(self.workers):
+                obs, buf.rewards[w, t], buf.dones[w, t], info = worker.child.recv()
+                if info:                                   # episode finished (trainer.py:195)
+                    self._step_host[w] = 0
+                    episode_infos.append(info)
+                    worker.child.send(("reset", None))
+                    obs = worker.child.recv()
+                    # the finished episode keeps its table row; the worker continues on a fresh zero row
+                    self._ep_host[w] = self._new_row()
+                    if t < T - 1:
+                        self._n_episodes = self._n_rows
+                else:
+                    self._step_host[w] += 1
+                if obs is not None:                        # None: the worker already wrote it into the shared slab
+                    self.obs[w] = obs
+            self._env_time += time.perf_counter() - te
+        self._graphs_finish_rollout("pipes", [grp])
+        return episode_infos
+
+    def _rollout_grouped(self):
+        """Shared-memory transport with overlapped worker groups.  Each group cycles GPU -> ENV independently:
+          GPU : one graph launch on the group's stream = observation / cursor upload, forward, sampling, action download;
+          ENV : actions published to the group's workers (shared arrays + command counters), workers step their
+                environments and write the next observation into the pinned slab, acknowledge.
+        The host thread only polls (CUDA event of each group, acknowledgement counters) and does the reference's episode
+        bookkeeping (trainer.py:193-218) for the group that just finished stepping, so group A's environments step while
+        group B's forward runs.  Per-worker semantics are unchanged: every worker still sees forward(t) -> step(t) ->
+        forward(t+1) in order, and workers never interact inside a rollout."""
         c, buf, T = self._control, self.buffer, self.config["worker_steps"]
-        c["actions"].numpy()[...] = actions
-        cmd = c["cmd"].numpy()
-        cmd += 1
-        if c.get("sems"):
-            for sem in c["sems"]:
-                sem.release()
-        ack = c["ack"].numpy()
+        groups = self._groups
+        cur = torch.cuda.current_stream()
+        host_obs = self._stage_host_obs()
+        if host_obs is not self._obs_slab:
+            raise RuntimeError("shared-memory stepping needs the observation slab registered as pinned memory")
+        acts, cmd, ack = c["actions"].numpy(), c["cmd"].numpy(), c["ack"].numpy()
+        rewards, dones, has_info = c["rewards"].numpy(), c["dones"].numpy(), c["has_info"].numpy()
+        sems = c.get("sems")
+        episode_infos = []
+        trace = [0.0, 0.0, 0.0] if os.environ.get("TRXL_E2E_TRACE") == "1" else None     # enqueue, gpu phase, env phase
+        dev_events = []
+        for grp in groups:
+            self._prepare_group(grp)
+            grp.stream.wait_stream(cur)
+            grp.t, grp.phase = 0, grp.DONE
+
+        def launch(grp):
+            ta = time.perf_counter()
+            if int(self._step_host[grp.lo:grp.hi].max()) >= self.max_episode_length:
+                self._check_cursors()
+            with torch.cuda.stream(grp.stream):
+                if trace is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    dev_events.append((e0, e1))
+                    e0.record(grp.stream)
+                self._step_via_graph("groups", grp, grp.t, self._host_src(grp, host_obs))
+                if trace is not None:
+                    e1.record(grp.stream)
+                grp.event.record(grp.stream)
+            grp.phase, grp.t_phase = grp.GPU, time.perf_counter()
+            if trace is not None:
+                trace[0] += grp.t_phase - ta
+
+        for grp in groups:
+            launch(grp)
+        active, idle_polls = len(groups), 0
         deadline = time.perf_counter() + 120.0
-        # Opt-in (TRXL_CHUNKED_UPLOAD=1): while the slower workers are still stepping, the observations of the groups that have
-        # already answered go to the device (the stream is idle: the step that read obs_dev has been synchronised).  Measured on
-        # the B200 host it only moves time from the device wait into the env wait (0.87 ms/step either way), so it is off.
-        chunks = self._upload_chunks
-        pending = list(range(len(chunks))) if (chunks and self._slab_pinned) else []
-        while True:
-            done = ack == cmd
-            for k in pending[:]:
-                lo, hi = chunks[k]
-                if done[lo:hi].all():
-                    self._obs_dev[lo:hi].copy_(self._obs_slab[lo:hi], non_blocking=True)
-                    pending.remove(k)
-            if done.all():
-                break
-            if time.perf_counter() > deadline:
-                raise RuntimeError("environment workers did not answer within 120 s")
-        self._obs_on_device = bool(chunks and self._slab_pinned)
-        buf.rewards[:, t] = c["rewards"].numpy()
-        buf.dones[:, t] = c["dones"].numpy() != 0
-        finished = np.nonzero(c["has_info"].numpy())[0]
-        self._step_host += 1
-        for w in finished:
-            w = int(w)
-            episode_infos.append(self.workers[w].child.recv())
-            self._step_host[w] = 0
-            self._ep_host[w] = self._new_row()
-            if t < T - 1:
-                self._n_episodes = self._n_rows
+        while active:
+            progressed = False
+            for grp in groups:
+                lo, hi = grp.lo, grp.hi
+                if grp.phase == grp.GPU:
+                    if not grp.event.query():
+                        continue
+                    now = time.perf_counter()
+                    acts[lo:hi] = grp.act_pinned.numpy()
+                    cmd[lo:hi] += 1                       # publish last: the actions above are visible before the command
+                    if sems:
+                        for w in range(lo, hi):
+                            sems[w].release()
+                    grp.phase = grp.ENV
+                    if trace is not None:
+                        trace[1] += now - grp.t_phase
+                    grp.t_phase = now
+                    progressed = True
+                elif grp.phase == grp.ENV:
+                    if not np.array_equal(ack[lo:hi], cmd[lo:hi]):
+                        continue
+                    now = time.perf_counter()
+                    self._env_time += (now - grp.t_phase) / len(groups)
+                    if trace is not None:
+                        trace[2] += now - grp.t_phase
+                    t = grp.t
+                    buf.rewards[lo:hi, t] = rewards[lo:hi]
+                    buf.dones[lo:hi, t] = dones[lo:hi] != 0
+                    self._step_host[lo:hi] += 1
+                    for w in np.nonzero(has_info[lo:hi])[0]:
+                        w = lo + int(w)
+                        episode_infos.append(self.workers[w].child.recv())
+                        self._step_host[w] = 0
+                        self._ep_host[w] = self._new_row()      # may move the table: every group's graphs are re-keyed
+                        if t < T - 1:
+                            self._n_episodes = self._n_rows
+                    grp.t += 1
+                    if grp.t < T:
+                        launch(grp)
+                    else:
+                        grp.phase = grp.DONE
+                        active -= 1
+                    progressed = True
+            if progressed:
+                idle_polls = 0
+                deadline = time.perf_counter() + 120.0
+                continue
+            idle_polls += 1
+            if idle_polls % 8192 == 0:
+                self._check_workers_alive()
+                if time.perf_counter() > deadline:
+                    raise RuntimeError("environment workers did not answer within 120 s")
+        for grp in groups:
+            cur.wait_stream(grp.stream)
+        self._graphs_finish_rollout("groups", groups)
+        if trace is not None:
+            k = 1e6 / (T * len(groups))
+            torch.cuda.synchronize()
+            dev_us = sorted(1e3 * a.elapsed_time(b) for a, b in dev_events)
+            print("[trxl] rollout trace per group step: enqueue %.0f us, gpu phase %.0f us (device time median %.0f us, p90 %.0f us), "
+                  "env phase %.0f us (%d groups, %s workers)"
+                  % (trace[0] * k, trace[1] * k, dev_us[len(dev_us) // 2], dev_us[int(len(dev_us) * 0.9)], trace[2] * k,
+                     len(groups), "blocking" if sems else "spinning"), flush=True)
+        return episode_infos
+
+    def _check_workers_alive(self):
+        """A worker whose env raised dies with a WorkerException; surface its traceback instead of waiting for the
+        stepping timeout (the pipe path raises on recv; the shared-memory path has to look)."""
+        for w, worker in enumerate(self.workers):
+            proc = getattr(worker, "process", None)
+            if proc is not None and not proc.is_alive():
+                detail = ""
+                try:
+                    if worker.child.poll(0):
+                        detail = ": %r" % (worker.child.recv(),)
+                except (EOFError, OSError):
+                    pass
+                raise RuntimeError("environment worker %d exited (exit code %s)%s" % (w, proc.exitcode, detail))
+
+    def _check_cursors(self):
+        """An environment that runs past its advertised max_episode_steps would index past its episode row (the reference
+        raises IndexError at trainer.py:166); fail loudly instead of corrupting the next table row."""
+        if int(self._step_host.max()) >= self.max_episode_length:
+            w = int(self._step_host.argmax())
+            raise IndexError("worker %d reached episode step %d but the environment advertises max_episode_steps = %d"
+                             % (w, int(self._step_host[w]), self.max_episode_length))
 
     def _sample_from_device_feed(self, feed):
         """Rollout against a device-resident synthetic feed (device_feed.py): the episode schedule of the
@@ -469,19 +683,23 @@ class PPOTrainer:
                 if t < T - 1:
                     self._n_episodes = n_rows
                 episode_infos.append(info)
+        if int(step_sched[:T].max()) >= self.max_episode_length:
+            raise IndexError("the feed's schedule runs past max_episode_steps = %d" % self.max_episode_length)
         while n_rows > self._table_cap:
             self._alloc_table(self._table_cap * 2)
         self._n_rows = n_rows
         buf.rewards[:] = feed.rewards.T
         buf.dones[:] = feed.dones.T
         ctx = self._rollout_ctx()
+        grp = self._whole
+        self._prepare_group(grp)
         step_dev, ep_dev = ctx["step_sched"], ctx["ep_sched"]
         step_dev.copy_(torch.from_numpy(step_sched))
         ep_dev.copy_(torch.from_numpy(ep_sched))
         with torch.no_grad():
             for t in range(T):
-                self._step_via_graph("feed", t, feed.obs(t), step_dev[t], ep_dev[t], ctx)
-        self._graphs_finish_rollout("feed")
+                self._step_via_graph("feed", grp, t, (feed.obs(t), step_dev[t], ep_dev[t], False))
+        self._graphs_finish_rollout("feed", [grp])
         self._step_host.copy_(torch.from_numpy(step_sched[T]))
         self._ep_host.copy_(torch.from_numpy(ep_sched[T]))
         self._feed_last_obs = feed.obs(T)
@@ -505,7 +723,7 @@ class PPOTrainer:
             if self.device_feed is not None:
                 self._obs_dev.copy_(self._feed_last_obs)
             else:
-                self._upload_obs()
+                self._obs_dev.copy_(self._stage_host_obs(), non_blocking=True)
             feat = self.model.encode(self._obs_dev)
             pe_idx = self.buffer.memory_indices[:, -1].contiguous()
             _, value, _ = self.model.forward_table(feat, self._table, self._ep_dev, self._win_last, self._mask_last, pe_idx, n=W)
@@ -523,12 +741,18 @@ class PPOTrainer:
         norms = torch.zeros((n_steps, g + 2), dtype=torch.float32, device=self.device)
         i = 0
         for _ in range(self.config["epochs"]):
-            for mini_batch in self.buffer.mini_batch_generator():
-                self._ppo_step(mini_batch, learning_rate, clip_range, beta, stats[i], norms[i])
+            batches = list(self.buffer.mini_batch_generator())
+            # advantage statistics of every minibatch of the epoch (the permutation is known up front): one small
+            # all-reduce per epoch instead of one per optimiser step
+            advstats = torch.zeros((len(batches), 3), dtype=torch.float64, device=self.device)
+            flat_adv = self.buffer.samples_flat["advantages"]
+            for j, mini_batch in enumerate(batches):
+                native.adv_stats(flat_adv, mini_batch.sample_index, mini_batch.sample_index.shape[0], advstats[j])
+            self.dp.all_reduce_(advstats)
+            for j, mini_batch in enumerate(batches):
+                self._ppo_step(mini_batch, learning_rate, clip_range, beta, stats[i], norms[i], advstats=advstats[j])
                 i += 1
         stats, norms = stats[:i].cpu(), norms[:i].cpu()           # the only sync of the update
-        if self.dp.world_size > 1:
-            pass                                                   # stats were all-reduced on the device
         train_info = [[np.float32(v) for v in row] for row in stats.tolist()]
         grad_info = {}
         for row in norms:
@@ -564,7 +788,9 @@ class PPOTrainer:
             self._train_state = {n: st}          # keep one size resident
         return st
 
-    def _ppo_step(self, samples, learning_rate, clip_range, beta, stats_out, norms_out):
+    def _ppo_step(self, samples, learning_rate, clip_range, beta, stats_out, norms_out, advstats=None):
+        """One optimiser step.  ``advstats`` = the (already all-reduced) {sum, sum of squares, count} of the minibatch's
+        advantages; computed (and all-reduced) here when the caller did not batch them per epoch."""
         model, cfg = self.model, self.config
         if isinstance(samples, MiniBatch):
             buf = samples.buffer
@@ -613,10 +839,16 @@ class PPOTrainer:
         logits, value, out_mem = st["out"]
         native.model_forward(model._cfg, model.flat_parameters(), feat, table, table.shape[1], ep_index, win_index, mask,
                              pe_index, sidx, model._pe_table(), n, st["ws"], logits, value, out_mem)
-        native.adv_stats(adv, sidx, n, st["advstats"])
-        self.dp.all_reduce_(st["advstats"])
-        native.ppo_loss(logits, value, actions, old_logp, old_values, adv, sidx, st["advstats"], self.action_space_shape, n,
-                        clip_range, beta, cfg["value_loss_coefficient"], st["dlogits"], st["dvalue"], stats_out,
+        if advstats is None:
+            advstats = st["advstats"]
+            native.adv_stats(adv, sidx, n, advstats)
+            self.dp.all_reduce_(advstats)
+        multi = self.dp.world_size > 1
+        # multi-GPU: the six loss statistics (already divided by the GLOBAL sample count) are written into the tail of the
+        # gradient arena and summed by the same all-reduce as the gradients
+        stats_dst = model.stats_tail() if multi else stats_out
+        native.ppo_loss(logits, value, actions, old_logp, old_values, adv, sidx, advstats, self.action_space_shape, n,
+                        clip_range, beta, cfg["value_loss_coefficient"], st["dlogits"], st["dvalue"], stats_dst,
                         st["loss_scratch"])
         native.model_backward(model._cfg, model.flat_parameters(), model.flat_grads(), feat, table, table.shape[1], ep_index,
                               win_index, mask, pe_index, sidx, model._pe_table(), n, st["ws"], out_mem, st["dlogits"],
@@ -625,9 +857,9 @@ class PPOTrainer:
             model.encode_backward(n, obs.shape[-2], obs.shape[-1], st["dfeat"])
         elif feat_g is not None:
             feat_g.backward(st["dfeat"])           # accumulates into the conv slices of the gradient arena
-        if self.dp.world_size > 1:
-            self.dp.all_reduce_(model.flat_grads())     # ONE collective per optimiser step: the flat gradient arena
-            self.dp.all_reduce_(stats_out)
+        if multi:
+            self.dp.all_reduce_(model.flat_grads_with_tail())     # ONE collective per optimiser step: gradient arena + stats tail
+            stats_out.copy_(model.stats_tail())
         self.optimizer.step(norms_out=norms_out)
 
     # ------------------------------------------------------------------------------------------ logging / io
@@ -656,9 +888,7 @@ class PPOTrainer:
     def _save_model(self):
         """``(state_dict, config)`` pickle at ./models/<run_id>.nn, the reference's checkpoint format (trainer.py:356-362)."""
         os.makedirs("./models", exist_ok=True)
-        state = {k: v.detach().cpu().clone() for k, v in self.model.state_dict().items()}
-        with open("./models/" + self.run_id + ".nn", "wb") as f:
-            pickle.dump((state, self.config), f)
+        save_model_file(self.model, self.config, "./models/" + self.run_id + ".nn")
         print("Model saved to ./models/" + self.run_id + ".nn")
 
     def save_checkpoint(self, path):

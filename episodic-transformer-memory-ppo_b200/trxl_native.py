@@ -48,6 +48,7 @@ SIGNATURES = {
     "trxl_graph_launch": (i32, [vp, vp]),
     "trxl_graph_destroy": (i32, [vp]),
     "trxl_copy_rows": (i32, [vp, vp, i64, i64, i64, i64, vp]),
+    "trxl_copy_async": (i32, [vp, vp, i64, vp]),
     "trxl_layout_num_entries": (i32, [CFGP]),
     "trxl_layout_total_floats": (i64, [CFGP]),
     "trxl_layout_entry": (i32, [CFGP, i32, C.POINTER(ParamEntry)]),
@@ -75,11 +76,21 @@ SIGNATURES = {
     "trxl_gae": (i32, [vp, vp, vp, vp, vp, i32, i32, f64, f64, vp]),
     "trxl_rollout_prepare": (i32, [vp, vp, vp, vp, vp, i64, vp, i64, vp, i64, i32, i32, vp]),
     "trxl_memory_scatter": (i32, [vp, vp, vp, vp, i32, i64, i64, vp]),
+    "trxl_rollout_fetch": (i32, [vp, i64, vp, vp, vp, vp, i64, vp, vp, i32, vp]),
+    "trxl_host_device_pointer": (i32, [vp, C.POINTER(C.c_void_p)]),
     "trxl_sample_actions": (i32, [vp, vp, vp, C.POINTER(C.c_int32), i32, vp, i64, vp, i64, vp, i32, vp]),
     "trxl_adv_stats": (i32, [vp, vp, i32, vp, vp]),
     "trxl_ppo_loss": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int32), i32, i32, f64, f64, f64, vp, vp, vp, vp, vp]),
     "trxl_clip_adamw_step": (i32, [vp, vp, vp, vp, i64, vp, i32, i32, f64, f64, f64, f64, f64, f64, i64, vp, vp, vp]),
+    "trxl_comm_unique_id": (i32, [vp]),
+    "trxl_comm_create": (i32, [vp, i32, i32, C.POINTER(C.c_void_p)]),
+    "trxl_comm_destroy": (i32, [vp]),
+    "trxl_comm_calls": (i64, [vp]),
+    "trxl_comm_nccl_version": (i32, []),
+    "trxl_allreduce_grads": (i32, [vp, vp, i64, vp]),
+    "trxl_allreduce_f64": (i32, [vp, vp, i64, vp]),
 }
+COMM_ID_BYTES = 128
 
 
 class NativeLibraryError(RuntimeError):
@@ -194,6 +205,10 @@ def graph_destroy(graph_exec):
 def copy_rows(src_ptr, dst_ptr, rows, row_bytes, src_stride_bytes, dst_stride_bytes):
     _check(load().trxl_copy_rows(src_ptr, dst_ptr, int(rows), int(row_bytes), int(src_stride_bytes), int(dst_stride_bytes), _stream()),
            "trxl_copy_rows")
+
+
+def copy_async(src_ptr, dst_ptr, nbytes):
+    _check(load().trxl_copy_async(src_ptr, dst_ptr, int(nbytes), _stream()), "trxl_copy_async")
 
 
 def tc_gemm_launches():
@@ -345,14 +360,28 @@ def rollout_prepare(step, ep, mask_table, index_table, mask_out_ptr, mask_stride
                                        idx_out_ptr, idx_stride, ep_out_ptr, ep_stride, w, L, _stream()), "trxl_rollout_prepare")
 
 
+def rollout_fetch(obs_src_ptr, obs_floats, step_src_ptr, ep_src_ptr, obs_dev, obs_store_ptr, store_stride_floats, step_dev, ep_dev, n):
+    _check(load().trxl_rollout_fetch(obs_src_ptr, int(obs_floats), step_src_ptr, ep_src_ptr, _p(obs_dev), obs_store_ptr,
+                                     int(store_stride_floats), _p(step_dev), _p(ep_dev), int(n), _stream()), "trxl_rollout_fetch")
+
+
+def host_device_pointer(host_ptr):
+    """Device-side address of pinned / cudaHostRegister'ed host memory (raises if the buffer is not mapped)."""
+    out = C.c_void_p(None)
+    _check(load().trxl_host_device_pointer(host_ptr, C.byref(out)), "trxl_host_device_pointer")
+    return out.value
+
+
 def memory_scatter(table, ep, step, new_mem, slots, inner):
     _check(load().trxl_memory_scatter(_p(table), _p(ep), _p(step), _p(new_mem), ep.shape[0], int(slots), int(inner), _stream()),
            "trxl_memory_scatter")
 
 
 def sample_actions(logits, u, branch_sizes, act_ptr, act_stride, logp_ptr, logp_stride, act_compact, w, forced=None):
+    """``act_compact``: (w, nb) int64 device tensor, or the raw device-side address of a mapped host buffer."""
+    compact = act_compact if isinstance(act_compact, int) else _p(act_compact)
     _check(load().trxl_sample_actions(_p(logits), _p(u), _p(forced), branch_array(branch_sizes), len(branch_sizes), act_ptr, act_stride,
-                                      logp_ptr, logp_stride, _p(act_compact), w, _stream()), "trxl_sample_actions")
+                                      logp_ptr, logp_stride, compact, w, _stream()), "trxl_sample_actions")
 
 
 def adv_stats(adv, sample_index, n, out3):
@@ -371,3 +400,44 @@ def clip_adamw_step(params, grads, m, v, total, chunks, nchunks, ngroups, max_no
     _check(load().trxl_clip_adamw_step(_p(params), _p(grads), _p(m), _p(v), int(total), _p(chunks), int(nchunks), int(ngroups),
                                        float(max_norm), float(lr), float(betas[0]), float(betas[1]), float(eps),
                                        float(weight_decay), int(step), _p(partial), _p(norms), _stream()), "trxl_clip_adamw_step")
+
+
+# ---- multi-GPU exchange ------------------------------------------------------------------------------------------
+def comm_unique_id():
+    """128 host bytes identifying a new NCCL clique (rank 0 creates it and ships it to the other ranks)."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    _check(load().trxl_comm_unique_id(buf), "trxl_comm_unique_id")
+    return bytes(buf.raw)
+
+
+def comm_create(id_bytes, rank, world_size):
+    assert len(id_bytes) == COMM_ID_BYTES
+    out = C.c_void_p(None)
+    _check(load().trxl_comm_create(C.create_string_buffer(id_bytes, COMM_ID_BYTES), int(rank), int(world_size), C.byref(out)),
+           "trxl_comm_create")
+    return out.value
+
+
+def comm_destroy(comm):
+    if comm:
+        load().trxl_comm_destroy(comm)
+
+
+def comm_calls(comm):
+    return int(load().trxl_comm_calls(comm))
+
+
+def nccl_version():
+    return int(load().trxl_comm_nccl_version())
+
+
+def allreduce_grads(comm, tensor, count=None):
+    """In-place fp32 sum of ``tensor[:count]`` over the ranks of ``comm`` on the current stream."""
+    assert tensor.dtype == torch.float32
+    _check(load().trxl_allreduce_grads(comm, _p(tensor), int(tensor.numel() if count is None else count), _stream()),
+           "trxl_allreduce_grads")
+
+
+def allreduce_f64(comm, tensor):
+    assert tensor.dtype == torch.float64
+    _check(load().trxl_allreduce_f64(comm, _p(tensor), int(tensor.numel()), _stream()), "trxl_allreduce_f64")

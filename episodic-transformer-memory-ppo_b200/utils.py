@@ -6,10 +6,6 @@ from torch import nn
 
 import trxl_native as native
 
-_ENV_HELP = ("environment type %r needs the optional package %s, which is not installed; the B200 engine itself "
-             "only requires the gym-style protocol (observation_space, action_space, max_episode_steps, reset, step)")
-
-
 def create_env(config, render=False):
     """Instantiate an environment from ``config["type"]`` (reference utils.py:11-30).  ``Synthetic``
     is this repo's benchmark environment; the gym-backed types import their
@@ -23,18 +19,17 @@ def create_env(config, render=False):
     if kind == "PocMemoryEnv":
         from environments.poc_memory_env import PocMemoryEnv
         return PocMemoryEnv(glob=False, freeze=True, max_episode_steps=32)
-    try:
-        if kind in ("CartPole", "CartPoleMasked"):
-            from environments.cartpole_env import CartPole
-            return CartPole(mask_velocity=(kind == "CartPoleMasked"))
-        if kind == "Minigrid":
-            from environments.minigrid_env import Minigrid
-            return Minigrid(config["name"])
-        if kind in ("SearingSpotlights", "MortarMayhem", "MortarMayhem-Grid", "MysteryPath", "MysteryPath-Grid"):
-            from environments.memory_gym_env import MemoryGymWrapper
-            return MemoryGymWrapper(env_name=config["name"], reset_params=config["reset_params"], realtime_mode=render)
-    except ImportError as e:
-        raise ImportError(_ENV_HELP % (kind, e.name)) from e
+    # gym-backed types: the adapters import gym / gym_minigrid / gymnasium + memory_gym when constructed and raise
+    # environments.gym_envs.MissingEnvDependency (an ImportError naming the package) when it is not installed
+    if kind in ("CartPole", "CartPoleMasked"):
+        from environments.gym_envs import CartPole
+        return CartPole(mask_velocity=(kind == "CartPoleMasked"))
+    if kind == "Minigrid":
+        from environments.gym_envs import Minigrid
+        return Minigrid(config["name"])
+    if kind in ("SearingSpotlights", "MortarMayhem", "MortarMayhem-Grid", "MysteryPath", "MysteryPath-Grid"):
+        from environments.gym_envs import MemoryGymWrapper
+        return MemoryGymWrapper(env_name=config["name"], reset_params=config.get("reset_params"), realtime_mode=render)
     raise ValueError("unknown environment type %r" % kind)
 
 

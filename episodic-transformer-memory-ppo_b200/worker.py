@@ -153,7 +153,12 @@ def worker_process(remote, config, obs_slab=None, index=0, control=None, cpu=Non
         except (EOFError, KeyboardInterrupt):
             return
         except Exception as e:  # noqa: BLE001 -- surfaced to the parent as in the reference
-            raise WorkerException(e)
+            err = WorkerException(e)
+            try:
+                remote.send(("worker_error", str(err)))      # the shared-memory stepping path polls for a dead worker
+            except Exception:  # noqa: BLE001
+                pass
+            raise err
 
 
 class Worker:

@@ -23,6 +23,7 @@ extern "C" {
 
 #define TRXL_ABI_VERSION 1
 #define TRXL_MAX_BRANCHES 8
+#define TRXL_COMM_ID_BYTES 128
 
 enum { TRXL_LN_NONE = 0, TRXL_LN_PRE = 1, TRXL_LN_POST = 2 };        /* config["transformer"]["layer_norm"] */
 enum { TRXL_PE_NONE = 0, TRXL_PE_RELATIVE = 1, TRXL_PE_LEARNED = 2 }; /* ...["positional_encoding"]          */
@@ -74,6 +75,10 @@ int trxl_graph_destroy(void* graph_exec);
 /* dst[r, 0:row_bytes] = src[r, 0:row_bytes] for `rows` strided rows (device to device) */
 int trxl_copy_rows(const void* src, void* dst, int64_t rows, int64_t row_bytes, int64_t src_stride_bytes, int64_t dst_stride_bytes,
                    void* stream);
+/* plain asynchronous copy of `bytes` bytes; either side may be pinned / cudaHostRegister'ed host memory (the rollout's
+ * observation slab, episode cursors, sampled actions: trainer.py:163,189 of the reference do these as torch copies).
+ * Capturable into a CUDA graph. */
+int trxl_copy_async(const void* src, void* dst, int64_t bytes, void* stream);
 
 /* ---- parameter arena layout ------------------------------------------------------------------ */
 /* Number of entries / total floats of the arena for a config (<0 on invalid config). */
@@ -183,6 +188,16 @@ int trxl_gae(const float* rewards, const uint8_t* dones, const float* values, co
 int trxl_rollout_prepare(const int64_t* step, const int64_t* ep, const uint8_t* mask_table, const int64_t* index_table,
                          uint8_t* mask_out, int64_t mask_stride, int64_t* idx_out, int64_t idx_stride, int64_t* ep_out,
                          int64_t ep_stride, int W, int L, void* stream);
+/* trainer.py:163 + the host->device hand-over of a rollout step in one kernel: observations (n, obs_floats) and the episode
+ * cursors (n,) are read from `*_src` -- device memory, or pinned / cudaHostRegister'ed HOST memory read in place over PCIe
+ * (pass the pointer from trxl_host_device_pointer) -- into the device staging buffers, and the observations also into their
+ * rows of the rollout buffer (row w at obs_store + w * store_stride_floats). */
+int trxl_rollout_fetch(const float* obs_src, int64_t obs_floats, const int64_t* step_src, const int64_t* ep_src, float* obs_dev,
+                       float* obs_store, int64_t store_stride_floats, int64_t* step_dev, int64_t* ep_dev, int n, void* stream);
+/* device-side address of a pinned / registered host buffer (cudaHostGetDevicePointer), for kernels that read or write host
+ * memory in place: trxl_rollout_fetch sources, and `actions_compact` of trxl_sample_actions (actions land in host memory
+ * without a copy node) */
+int trxl_host_device_pointer(const void* host_ptr, void** device_ptr_out);
 /* trainer.py:174: table[ep[w], step[w]] = new_mem[w] (inner = B*D floats) */
 int trxl_memory_scatter(float* table, const int64_t* ep, const int64_t* step, const float* new_mem, int W, int64_t slots,
                         int64_t inner, void* stream);
@@ -206,6 +221,23 @@ int trxl_ppo_loss(const float* logits, const float* value, const int64_t* action
 int trxl_clip_adamw_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t total_floats,
                          const int64_t* chunks, int nchunks, int ngroups, double max_grad_norm, double lr, double beta1,
                          double beta2, double eps, double weight_decay, int64_t step, float* partial, float* norms, void* stream);
+
+/* ---- multi-GPU exchange (SURVEY.md §8b "trxl_allreduce_grads", §8e) -------------------------------
+ * The reference is single-process; data-parallel sharding over workers (trainer.py:145-323 per rank) needs ONE
+ * exchange per optimiser step: the in-place sum of the flat fp32 gradient arena (+ the 6 loss statistics appended to
+ * its tail).  NCCL is bound with dlopen at first use (libnccl.so.2; TRXL_NCCL_LIB overrides), so single-GPU users never
+ * load it.  Rendezvous: rank 0 calls trxl_comm_unique_id and ships the TRXL_COMM_ID_BYTES host bytes to the other ranks
+ * by any means (torch.distributed, a file, MPI); every rank then calls trxl_comm_create with its CUDA device current. */
+int trxl_comm_unique_id(void* id_out);
+int trxl_comm_create(const void* id_bytes, int rank, int world_size, void** comm_out);
+int trxl_comm_destroy(void* comm);
+/* number of collectives enqueued through this communicator so far (bench/tests count them) */
+int64_t trxl_comm_calls(void* comm);
+/* NCCL version code of the bound library (e.g. 22809), or -1 if NCCL cannot be loaded */
+int trxl_comm_nccl_version(void);
+/* in-place sum over ranks on `stream` (asynchronous; ordered with the kernels already enqueued on it) */
+int trxl_allreduce_grads(void* comm, float* buf, int64_t count, void* stream);
+int trxl_allreduce_f64(void* comm, double* buf, int64_t count, void* stream);
 
 #ifdef __cplusplus
 }

@@ -81,6 +81,18 @@ def gru_gate(P, pre, x, y):
     return torch.mul(1 - z, x) + torch.mul(z, h)
 
 
+# Optional tap (tests only): when RELU_MARGINS is a list, every ReLU of a forward appends the per-sample minimum |pre-activation|
+# of that layer (shape (N,)).  The full-size parity test uses it to pick samples whose ReLU decisions cannot flip under fp32
+# rounding noise, so that gradient comparisons measure arithmetic accuracy rather than ties at the ReLU boundary.
+RELU_MARGINS = None
+
+
+def _relu(x):
+    if RELU_MARGINS is not None:
+        RELU_MARGINS.append(x.detach().abs().reshape(x.shape[0], -1).min(dim=1).values)
+    return torch.relu(x)
+
+
 def _ln(P, pre, x):
     return F.layer_norm(x, (x.shape[-1],), P[pre + "weight"], P[pre + "bias"], 1e-5)
 
@@ -99,7 +111,7 @@ def transformer_block(P, pre, tcfg, value, query, mask):
     if mode == "post":
         h = _ln(P, pre + "norm1.", h)                                       # :148-149
     h_in = _ln(P, pre + "norm2.", h) if mode == "pre" else h                # :152-155
-    ff = torch.relu(F.linear(h_in, P[pre + "fc.0.weight"], P[pre + "fc.0.bias"]))  # :158
+    ff = _relu(F.linear(h_in, P[pre + "fc.0.weight"], P[pre + "fc.0.bias"]))  # :158
     out = gru_gate(P, pre + "gate2.", h, ff) if gated else ff + h           # :161-166
     if mode == "post":
         out = _ln(P, pre + "norm2.", out)                                   # :169-170
@@ -108,7 +120,7 @@ def transformer_block(P, pre, tcfg, value, query, mask):
 
 def transformer(P, tcfg, max_episode_steps, h, memories, mask, memory_indices, pre="transformer."):
     """Reference transformer.py:222-253.  Returns (h, out_memories (N, B, D))."""
-    h = torch.relu(F.linear(h, P[pre + "linear_embedding.weight"], P[pre + "linear_embedding.bias"]))  # :234
+    h = _relu(F.linear(h, P[pre + "linear_embedding.weight"], P[pre + "linear_embedding.bias"]))  # :234
     pe_mode = tcfg["positional_encoding"]
     if pe_mode == "relative":                                               # :237-239
         table = sinusoidal_table(max_episode_steps, tcfg["embed_dim"], P.get(pre + "pos_embedding.inv_freqs"))
@@ -131,11 +143,11 @@ def encode_observation(P, obs):
     h = obs
     if "conv1.weight" in P:
         n = h.shape[0]
-        h = torch.relu(F.conv2d(h, P["conv1.weight"], P["conv1.bias"], stride=4))
-        h = torch.relu(F.conv2d(h, P["conv2.weight"], P["conv2.bias"], stride=2))
-        h = torch.relu(F.conv2d(h, P["conv3.weight"], P["conv3.bias"], stride=1))
+        h = _relu(F.conv2d(h, P["conv1.weight"], P["conv1.bias"], stride=4))
+        h = _relu(F.conv2d(h, P["conv2.weight"], P["conv2.bias"], stride=2))
+        h = _relu(F.conv2d(h, P["conv3.weight"], P["conv3.bias"], stride=1))
         h = h.reshape(n, -1)
-    return torch.relu(F.linear(h, P["lin_hidden.weight"], P["lin_hidden.bias"]))
+    return _relu(F.linear(h, P["lin_hidden.weight"], P["lin_hidden.bias"]))
 
 
 def model_forward(P, cfg, obs, memory, memory_mask, memory_indices):
@@ -145,8 +157,8 @@ def model_forward(P, cfg, obs, memory, memory_mask, memory_indices):
     ``categorical_*`` below, which restate what that class computes."""
     h = encode_observation(P, obs)
     h, new_mem = transformer(P, cfg["transformer"], cfg["max_episode_steps"], h, memory, memory_mask, memory_indices)
-    h_policy = torch.relu(F.linear(h, P["lin_policy.weight"], P["lin_policy.bias"]))    # :104
-    h_value = torch.relu(F.linear(h, P["lin_value.weight"], P["lin_value.bias"]))       # :106
+    h_policy = _relu(F.linear(h, P["lin_policy.weight"], P["lin_policy.bias"]))    # :104
+    h_value = _relu(F.linear(h, P["lin_value.weight"], P["lin_value.bias"]))       # :106
     value = F.linear(h_value, P["value.weight"], P["value.bias"]).reshape(-1)           # :108
     logits = [F.linear(h_policy, P["policy_branches.%d.weight" % k], P["policy_branches.%d.bias" % k])
               for k in range(len(cfg["action_space_shape"]))]

@@ -376,7 +376,7 @@ def test_learns_the_memory_task(tmp_path, monkeypatch):
     from conftest import PKG
     import os
     monkeypatch.chdir(tmp_path)
-    cfg = YamlParser(os.path.join(PKG, "configs", "poc_memory.yaml")).get_config()
+    cfg = YamlParser(os.path.join(PKG, "configs", "poc_memory_env.yaml")).get_config()
     torch.manual_seed(0)
     np.random.seed(0)
     workers = [_Worker(PocMemoryEnv(glob=False, freeze=True, max_episode_steps=32)) for _ in range(cfg["n_workers"])]

@@ -278,3 +278,63 @@ def test_shared_memory_stepping_modes(blocking):
         for w in workers:
             w.child.recv()
             w.process.join(5)
+
+
+_REF_LOAD_SCRIPT = r'''
+import os, pickle, sys
+sys.path.insert(0, os.path.join({root!r}, "tests", "golden"))
+import make_golden as mg
+mg.install_stubs()
+sys.path.insert(0, {ref!r})
+import numpy as np, torch
+from model import ActorCriticModel            # the REFERENCE's model.py
+assert os.path.realpath(sys.modules["model"].__file__).startswith(os.path.realpath({ref!r}))
+state_dict, config = pickle.load(open({path!r}, "rb"))
+class Space:
+    def __init__(self, shape): self.shape = shape
+for obs_shape in ({obs_shape!r},):
+    ref = ActorCriticModel(config, Space(obs_shape), (3,), 12)
+    missing = ref.load_state_dict(state_dict, strict=True)      # same keys and shapes, or this raises
+    L, t = config["transformer"]["memory_length"], config["transformer"]
+    torch.manual_seed(0)
+    obs = torch.rand((2,) + tuple(obs_shape)); mem = torch.randn(2, L, t["num_blocks"], t["embed_dim"])
+    mask = torch.tril(torch.ones(L, L), -1)[[0, L - 1]].bool(); idx = torch.arange(L).repeat(2, 1)
+    with torch.no_grad():
+        pi, value, new_mem = ref(obs, mem, mask, idx)
+    np.savez({out!r}, obs=obs.numpy(), mem=mem.numpy(), mask=mask.numpy(), idx=idx.numpy(), value=value.numpy(),
+             new_mem=new_mem.numpy(), logits=pi[0].logits.numpy())
+print("reference loaded the checkpoint")
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the unmodified reference is only present in the build container")
+@pytest.mark.parametrize("obs_shape,ln,gtrxl,pe", [((5,), "pre", True, "learned"), ((3, 84, 84), "post", False, "relative")])
+def test_saved_model_loads_into_the_reference_model(tmp_path, obs_shape, ln, gtrxl, pe):
+    """f3: the ``(state_dict, config)`` pickle written by this engine (trainer.save_model_file, the body of _save_model)
+    loads with strict=True into the UNMODIFIED reference ActorCriticModel (reference enjoy.py:47-57), and the reference's
+    forward on that checkpoint equals the oracle's (which the GPU tests compare the CUDA path with) to 1e-5."""
+    from model import ActorCriticModel
+    from oracle import trxl_oracle as X
+    from parity_util import _Space
+    from trainer import save_model_file
+    cfg = {"hidden_layer_size": 32, "transformer": {"num_blocks": 2, "embed_dim": 32, "num_heads": 4, "memory_length": 6,
+                                                    "positional_encoding": pe, "layer_norm": ln, "gtrxl": gtrxl, "gtrxl_bias": 0.5}}
+    torch.manual_seed(1)
+    model = ActorCriticModel(cfg, _Space(obs_shape), (3,), 12)
+    path, out = str(tmp_path / "m.nn"), str(tmp_path / "ref_out.npz")
+    save_model_file(model, cfg, path)
+    script = tmp_path / "load_ref.py"
+    script.write_text(_REF_LOAD_SCRIPT.format(root=ROOT, ref="/root/reference", path=path, out=out, obs_shape=tuple(obs_shape)))
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    g = dict(np.load(out))
+    P = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    ocfg = dict(cfg, max_episode_steps=12, action_space_shape=(3,))
+    mem = torch.from_numpy(g["mem"])
+    with torch.no_grad():
+        logits, value, new_mem = X.model_forward(P, ocfg, torch.from_numpy(g["obs"]), mem, torch.from_numpy(g["mask"]),
+                                                 torch.from_numpy(g["idx"]))
+    np.testing.assert_allclose(value.numpy(), g["value"], atol=1e-5)
+    np.testing.assert_allclose(new_mem.numpy(), g["new_mem"], atol=1e-5)
+    lg = logits[0]
+    np.testing.assert_allclose((lg - lg.logsumexp(-1, keepdim=True)).numpy(), g["logits"], atol=1e-5)

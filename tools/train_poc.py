@@ -20,7 +20,7 @@ def main():
     from trainer import PPOTrainer
     from utils import polynomial_decay, process_episode_info
     from yaml_parser import YamlParser
-    cfg = YamlParser(os.path.join(PKG, "configs", "poc_memory.yaml")).get_config()
+    cfg = YamlParser(os.path.join(PKG, "configs", "poc_memory_env.yaml")).get_config()
     torch.manual_seed(args.seed)
     np.random.seed(args.seed)
     os.chdir("/tmp")
