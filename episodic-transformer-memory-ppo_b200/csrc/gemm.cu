@@ -373,14 +373,17 @@ int launch_cfg(const GemmArgs& g, cudaStream_t st) {
 
 }  // namespace
 
-int trxl_tc_gemm(const GemmArgs& g, cudaStream_t st);      // tc_gemm.cu
+// tc_gemm.cu: TMA + tcgen05 3xTF32 path
+int trxl_tc_gemm(const GemmArgs& g, int bn, cudaStream_t st);
+bool trxl_tc_gemm_eligible(const GemmArgs& g);
+int trxl_tc_gemm_tile_n(const GemmArgs& g);
 
 // TRXL_TCGEN05=0 disables the tensor-core GEMM (falls back to the SIMT kernels above, same results to ~1e-6)
 static bool tc_enabled() {
     static int state = -1;
     if (state < 0) {
         const char* e = getenv("TRXL_TCGEN05");
-        state = (e && e[0] == '1') ? 1 : 0;
+        state = (e && e[0] == '0') ? 0 : 1;
     }
     return state == 1;
 }
@@ -419,24 +422,35 @@ int trxl_gemm(GemmArgs g, cudaStream_t st) {
         }
     }
     int rc;
-    if (tc_enabled() && g.M >= 128 && g.N >= 48 && g.K >= 32) {
-        // tensor-core path (tc_gemm.cu): 128 x {64,128} tiles, 3xTF32 in TMEM; split K when the tile count is small
-        const int bn = g.N > 64 ? 128 : 64;
-        const long long tc_tiles = (long long)trxl_cdiv(g.M, 128) * trxl_cdiv(g.N, bn) * g.batch;
-        g.ksplit = 1;
-        g.k_per_split = g.K;
-        if (g.ws && g.K >= 256 && tc_tiles * 2 <= 148) {
+    if (tc_enabled() && trxl_tc_gemm_eligible(g)) {
+        // tensor-core path (tc_gemm.cu): 128 x {32,64,128} tiles, TMA-staged operands, 3xTF32 in TMEM; split K when few tiles
+        GemmArgs t = g;
+        const int bn = trxl_tc_gemm_tile_n(t);
+        const long long tc_tiles = (long long)trxl_cdiv(t.M, 128) * trxl_cdiv(t.N, bn) * t.batch;
+        t.ksplit = 1;
+        t.k_per_split = t.K;
+        if (t.ws && t.K >= 256 && tc_tiles * 2 <= 148) {
             int s = (int)((148 + tc_tiles - 1) / tc_tiles);
-            const int maxs = g.K / 64;
+            const int maxs = t.K / 64;
             if (s > maxs) s = maxs;
             if (s > 32) s = 32;
-            while (s > 1 && (long long)s * g.batch * g.M * g.N > g.ws_floats) --s;
+            while (s > 1 && (long long)s * t.batch * t.M * t.N > t.ws_floats) --s;
             if (s > 1) {
-                g.k_per_split = ((g.K + s - 1) / s + 31) / 32 * 32;
-                g.ksplit = (g.K + g.k_per_split - 1) / g.k_per_split;
+                t.k_per_split = ((t.K + s - 1) / s + 31) / 32 * 32;
+                t.ksplit = (t.K + t.k_per_split - 1) / t.k_per_split;
             }
         }
-        rc = trxl_tc_gemm(g, st);
+        rc = trxl_tc_gemm(t, bn, st);
+        if (rc != TRXL_ERR_UNSUPPORTED) {
+            if (rc != TRXL_OK || t.ksplit == 1) return rc;
+            const long long total_t = (long long)t.M * t.N * t.batch;
+            splitk_reduce_kernel<<<trxl_cdiv(total_t, 256), 256, 0, st>>>(t);
+            TRXL_CHECK_LAUNCH("splitk_reduce");
+            return TRXL_OK;
+        }
+        // a tensor map could not be encoded for these operands: SIMT path below
+    }
+    if (false) {
     } else if (g.M <= 32 && g.a_kc && g.N >= 8) {
         // rollout-sized batch: one CTA per 16 output columns; split K only when the panel is deep
         g.ksplit = 1;

@@ -14,6 +14,7 @@ struct GemmArgs {
     int batch = 1; long long sA = 0, sB = 0, sC = 0, sBias = 0, sR = 0;
     float* ws = nullptr; long long ws_floats = 0;   // optional split-K workspace
     int vecA = 0, vecB = 0, ksplit = 1, k_per_split = 0;   // filled by trxl_gemm
+    int debug = 0;                        // TRXL_TC_DEBUG bitmask (timing experiments only; results are wrong when set)
 };
 
 int trxl_gemm(GemmArgs g, cudaStream_t st);

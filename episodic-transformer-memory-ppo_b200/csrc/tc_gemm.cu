@@ -1,22 +1,36 @@
-// tcgen05 (5th-gen tensor core) GEMM with fp32-grade accuracy: 3xTF32.
+// tcgen05 (5th-gen tensor core) GEMM with fp32-grade accuracy (3xTF32), operands staged by TMA.
 //
 //   C[b][m, n] (+)= epi( sum_k A[b](m, k) * B[b](k, n) )     same contract as the SIMT kernel in gemm.cu
 //
-// The parity contract of this engine is fp32 (1e-4 vs the reference's CPU path); a single TF32 MMA
-// (10-bit mantissa) does not hold that through 4 blocks.  Every operand element is therefore split
-// into hi = rna_tf32(x) and lo = rna_tf32(x - hi) and three MMAs accumulate hi*hi + lo*hi + hi*lo in
-// an fp32 TMEM accumulator (the dropped lo*lo term is ~2^-22 relative).
+// Replaces the reference's nn.Linear forward / autograd backward calls on the training path (transformer.py:50-52,82,158,
+// 295-298; model.py:97,104-110).  The parity contract is fp32 (1e-4 vs the reference's CPU path); a single TF32 MMA
+// (10-bit mantissa) does not hold that through 4 blocks, so every operand element is split into hi = rna_tf32(x) and
+// lo = rna_tf32(x - hi) and three MMAs accumulate hi*hi + lo*hi + hi*lo (the dropped lo*lo term is ~2^-22 relative).  The
+// tensor core adds into TMEM with truncation, so three accumulators are kept (hi*hi products alternate between two, the
+// ~2^-11 smaller cross terms go to the third) and summed with round-to-nearest in the epilogue -- the scheme tc_conv.cu
+// established at fp32-SIMT accuracy.
 //
-// Structure (one CTA = one 128 x BN output tile, 160 threads):
-//   warps 0-3  producers: coalesced fp32 global loads of the A and B tiles for one k-block (32 deep),
-//              hi/lo split in registers, st.shared into the canonical UMMA K-major no-swizzle layout
-//              (8-row x 16-byte core matrices; any operand orientation is just a different gather),
-//              fence.proxy.async, mbarrier arrive.  After the main loop the same warps run the
-//              epilogue: tcgen05.ld of their 32 TMEM lanes, bias / ReLU / residual, global stores.
-//   warp 4     allocates TMEM; one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) x 4
-//              k-steps x 3 split terms per stage and tcgen05.commit's the stage back to the producers.
-// Stage ring of mbarriers (full: producers -> MMA, empty: MMA -> producers, tmem_full: MMA -> epilogue).
+// One CTA = one 128 x BN output tile (one split of K), 320 threads:
+//   warp 9     TMA producer: one elected lane issues cp.async.bulk.tensor loads of the raw fp32 A and B tiles of a k-block
+//              (32 deep) into a STAGES-deep shared-memory ring; completion is tracked by the stage's `full` mbarrier (tx bytes).
+//              Out-of-range rows / columns / k are zero-filled by the TMA unit, so no operand needs padding.
+//   warps 0-7  converters: split the landed raw tile IN PLACE into hi and write lo to the twin tile (element-wise, so the
+//              shared-memory swizzle is irrelevant to them), fence.proxy.async, arrive on the stage's `ready` mbarrier.
+//              After the main loop the same warps run the epilogue: tcgen05.ld of their 32 TMEM lanes, bias / ReLU /
+//              residual / accumulate, global stores.
+//   warp 8     allocates TMEM; one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8): 4 k-steps x 3 split terms
+//              per stage, and tcgen05.commit's the stage back to the producer.
+// Operand orientations (all three the model needs, no transposed copies anywhere):
+//   K-major  (x (M,K) row-major; W (N,K) row-major)  : TMA box {32 k, rows}, SWIZZLE_128B       -> UMMA K-major SW128
+//   MN-major (dy (K,M) / x (K,N) / W (K,N) row-major) : TMA boxes {32 mn, 32 k}, SWIZZLE_128B_ATOM_32B
+//                                                       -> UMMA MN-major SWIZZLE_128B_BASE32B (the only MN-major TF32 layout)
 // Every mbarrier wait is bounded and traps instead of hanging the GPU.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include <mutex>
+#include <unordered_map>
+
 #include "gemm.cuh"
 #include "tc_common.cuh"
 
@@ -24,238 +38,388 @@ long long g_trxl_tc_launches = 0;
 
 namespace {
 
-constexpr int TC_BM = 128, TC_BK = 32;
-constexpr int TC_THREADS = 160;
+using namespace tc;
 
-using namespace tc;      // mbarrier / tcgen05 / descriptor primitives (tc_common.cuh)
+constexpr int TM_BM = 128, TM_BK = 32;
+constexpr int TM_CONV_WARPS = 8, TM_MMA_WARP = 8, TM_TMA_WARP = 9, TM_THREADS = 320;
+constexpr int A_TILE_BYTES = TM_BM * TM_BK * 4;      // 16 KB; K-major: 128 rows x 128 B; MN-major: 4 groups x (32 k-rows x 128 B)
 
-// gather a 4-wide k-chunk of row r of a strided operand: kc=1 -> X[r*ld + k], kc=0 -> X[k*ld + r]
-__device__ __forceinline__ float4 load_chunk(const float* __restrict__ X, long long ld, int kc, int vec, int r, int R, int k, int Kend) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r >= R) return v;
-    if (kc) {
-        const float* p = X + (long long)r * ld + k;
-        if (vec && k + 3 < Kend) return *reinterpret_cast<const float4*>(p);
-        if (k < Kend) v.x = p[0];
-        if (k + 1 < Kend) v.y = p[1];
-        if (k + 2 < Kend) v.z = p[2];
-        if (k + 3 < Kend) v.w = p[3];
-    } else {
-        const float* p = X + (long long)k * ld + r;
-        if (k < Kend) v.x = p[0];
-        if (k + 1 < Kend) v.y = p[ld];
-        if (k + 2 < Kend) v.z = p[2 * ld];
-        if (k + 3 < Kend) v.w = p[3 * ld];
-    }
-    return v;
+__host__ __device__ constexpr int tm_stage_bytes(int bn) { return 2 * A_TILE_BYTES + 2 * bn * TM_BK * 4; }
+__host__ __device__ constexpr int tm_stages(int bn) { return bn == 128 ? 3 : (bn == 64 ? 4 : 5); }
+__host__ __device__ constexpr int tm_tmem_cols(int bn) { return bn == 32 ? 128 : (bn == 64 ? 256 : 512); }
+
+struct TmaGemmParams {
+    CUtensorMap ta, tb;          // rank 3: {inner, outer, batch}
+    GemmArgs g;
+};
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void split_store(float* hi, float* lo, const float4& v) {
-    uint4 h, l;
-    h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-    l.x = to_tf32(v.x - __uint_as_float(h.x)); l.y = to_tf32(v.y - __uint_as_float(h.y));
-    l.z = to_tf32(v.z - __uint_as_float(h.z)); l.w = to_tf32(v.w - __uint_as_float(h.w));
-    *reinterpret_cast<uint4*>(hi) = h;
-    *reinterpret_cast<uint4*>(lo) = l;
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const GemmArgs g) {
-    extern __shared__ __align__(1024) unsigned char tc_smem[];
-    constexpr int A_FLOATS = TC_BM * TC_BK, B_FLOATS = BN * TC_BK;
-    constexpr int STAGE_FLOATS = 2 * A_FLOATS + 2 * B_FLOATS;
-    float* tiles = reinterpret_cast<float*>(tc_smem);
-    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_FLOATS);
-    uint64_t* empty = full + STAGES;
+// 32 lanes x 32 consecutive fp32 accumulator columns, no wait (the caller waits once for all three accumulators)
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+// v = (hi*hi even steps + hi*hi odd steps) + cross terms, for 32 accumulator columns of this warp's 32 lanes
+template <int BN>
+__device__ __forceinline__ void load_accumulators3(uint32_t taddr, float (&out)[32]) {
+    uint32_t v[32], u[32], x[32];
+    tmem_ld32_nowait(taddr, v);
+    tmem_ld32_nowait(taddr + BN, u);
+    tmem_ld32_nowait(taddr + 2 * BN, x);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) out[i] = (__uint_as_float(v[i]) + __uint_as_float(u[i])) + __uint_as_float(x[i]);
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(TM_THREADS, 1) tma_gemm_kernel(const __grid_constant__ TmaGemmParams p) {
+    extern __shared__ __align__(1024) unsigned char tm_smem[];
+    constexpr int STAGES = tm_stages(BN);
+    constexpr int B_TILE_BYTES = BN * TM_BK * 4;
+    constexpr int STAGE_BYTES = tm_stage_bytes(BN);
+    unsigned char* tiles = tm_smem + ((1024u - (smem_u32(tm_smem) & 1023u)) & 1023u);       // swizzled layouts need an aligned base
+    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);              // TMA bytes landed
+    uint64_t* ready = full + STAGES;                                                         // hi/lo split done
+    uint64_t* empty = ready + STAGES;                                                        // MMAs have consumed the stage
     uint64_t* tmem_full = empty + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
+    const GemmArgs& g = p.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+    const int m0 = blockIdx.y * TM_BM, n0 = blockIdx.x * BN;
     const int b = blockIdx.z / g.ksplit, split = blockIdx.z % g.ksplit;
     const int k_begin = split * g.k_per_split;
     const int k_end = min(g.K, k_begin + g.k_per_split);
-    const int kblocks = (k_end - k_begin + TC_BK - 1) / TC_BK;
-    const float* __restrict__ A = g.A + (long long)b * g.sA;
-    const float* __restrict__ B = g.B + (long long)b * g.sB;
+    const int kblocks = (k_end - k_begin + TM_BK - 1) / TM_BK;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 4); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], TM_CONV_WARPS); mbar_init(&empty[s], 1); }
         mbar_init(tmem_full, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_init_fence();
     }
-    if (warp == 4) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (warp == TM_TMA_WARP && lane == 0) { prefetch_tmap(&p.ta); prefetch_tmap(&p.tb); }
+    if (warp == TM_MMA_WARP) tmem_alloc(tmem_slot, tm_tmem_cols(BN));
+    fence_before_sync();
     __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t smem_base = smem_u32(tiles);
 
-    if (warp < 4) {
-        // ---------------- producers ----------------
-        // Register-level software pipeline, two k-blocks deep: the global loads of k-block kb+2 are in flight
-        // while kb is split/stored and kb+1 waits in registers, so L2 latency is hidden behind the MMAs.
-        const int r = threadIdx.x;                               // tile row owned by this thread (A: 0..127, B: 0..BN-1)
-        constexpr int NC = TC_BK / 4;                            // 16-byte k-chunks per row per k-block
-        const int row_off = (r >> 3) * 32 + (r & 7) * 4;         // core-matrix layout: chunk c at c*(ROWS*4) + (row/8)*32 + (row%8)*4
-        float4 ra[2][NC], rb[2][NC];
-        auto issue = [&](int kb, float4 (&xa)[NC], float4 (&xb)[NC]) {
-            const int k0 = k_begin + kb * TC_BK;
+    if (warp == TM_TMA_WARP) {
+        // ---------------- TMA producer ----------------
+        if (lane == 0) {
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
+                const int k0 = k_begin + kb * TM_BK;
+                const uint32_t a_dst = smem_base + s * STAGE_BYTES;
+                const uint32_t b_dst = a_dst + 2 * A_TILE_BYTES;
+                if ((g.debug & 4) && kb >= STAGES) { mbar_arrive(&full[s]); continue; }      // timing experiment: no TMA traffic
+                mbar_arrive_expect_tx(&full[s], A_TILE_BYTES + B_TILE_BYTES);
+                if (A_MN) {
 #pragma unroll
-            for (int c = 0; c < NC; ++c) xa[c] = load_chunk(A, g.lda, g.a_kc, g.vecA, m0 + r, g.M, k0 + 4 * c, k_end);
-            if (r < BN) {
+                    for (int grp = 0; grp < TM_BM / 32; ++grp) tma_load_3d(a_dst + grp * 4096, &p.ta, &full[s], m0 + 32 * grp, k0, b);
+                } else {
+                    tma_load_3d(a_dst, &p.ta, &full[s], k0, m0, b);
+                }
+                if (B_MN) {
 #pragma unroll
-                for (int c = 0; c < NC; ++c) xb[c] = load_chunk(B, g.ldb, g.b_kc, g.vecB, n0 + r, g.N, k0 + 4 * c, k_end);
-            }
-        };
-        auto commit = [&](int kb, const float4 (&xa)[NC], const float4 (&xb)[NC]) {
-            const int s = kb % STAGES;
-            mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
-            float* a_hi = tiles + s * STAGE_FLOATS;
-            float* a_lo = a_hi + A_FLOATS;
-            float* b_hi = a_lo + A_FLOATS;
-            float* b_lo = b_hi + B_FLOATS;
-#pragma unroll
-            for (int c = 0; c < NC; ++c) split_store(a_hi + c * (TC_BM * 4) + row_off, a_lo + c * (TC_BM * 4) + row_off, xa[c]);
-            if (r < BN) {
-#pragma unroll
-                for (int c = 0; c < NC; ++c) split_store(b_hi + c * (BN * 4) + row_off, b_lo + c * (BN * 4) + row_off, xb[c]);
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the MMA (async proxy)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[s]);
-        };
-        issue(0, ra[0], rb[0]);
-        if (kblocks > 1) issue(1, ra[1], rb[1]);
-        for (int kb = 0; kb < kblocks; kb += 2) {
-            commit(kb, ra[0], rb[0]);
-            if (kb + 2 < kblocks) issue(kb + 2, ra[0], rb[0]);
-            if (kb + 1 < kblocks) {
-                commit(kb + 1, ra[1], rb[1]);
-                if (kb + 3 < kblocks) issue(kb + 3, ra[1], rb[1]);
+                    for (int grp = 0; grp < BN / 32; ++grp) tma_load_3d(b_dst + grp * 4096, &p.tb, &full[s], n0 + 32 * grp, k0, b);
+                } else {
+                    tma_load_3d(b_dst, &p.tb, &full[s], k0, n0, b);
+                }
             }
         }
+    } else if (warp == TM_MMA_WARP) {
+        // ---------------- MMA issuer ----------------
+        // Descriptors are built once; per stage / k-step only their 14-bit start-address field (16-byte units) advances.
+        // K-major SW128: a k-step is 32 bytes further along the 128-byte span; MN-major SW128_BASE32B: 8 k-rows = 1024 bytes.
+        constexpr uint32_t idesc = idesc_tf32(TM_BM, BN, A_MN, B_MN);
+        constexpr uint32_t A_KSTEP = (A_MN ? 1024 : 32) >> 4, B_KSTEP = (B_MN ? 1024 : 32) >> 4;
+        const uint64_t da0 = A_MN ? make_desc(smem_base, 4096, 512, LAYOUT_SW128_BASE32B) : make_desc(smem_base, 16, 1024, LAYOUT_SW128);
+        const uint64_t db0 = B_MN ? make_desc(smem_base + 2 * A_TILE_BYTES, 4096, 512, LAYOUT_SW128_BASE32B)
+                                  : make_desc(smem_base + 2 * A_TILE_BYTES, 16, 1024, LAYOUT_SW128);
+        for (int kb = 0; kb < kblocks; ++kb) {
+            const int s = kb % STAGES;
+            mbar_wait(&ready[s], (kb / STAGES) & 1);
+            fence_after_sync();
+            if (lane == 0 && (g.debug & 2)) {                    // timing experiment: no MMAs
+                umma_commit(&empty[s]);
+                if (kb == kblocks - 1) umma_commit(tmem_full);
+            } else if (lane == 0) {
+                const uint64_t dah0 = da0 + (uint64_t)((s * STAGE_BYTES) >> 4), dal0 = dah0 + (uint64_t)(A_TILE_BYTES >> 4);
+                const uint64_t dbh0 = db0 + (uint64_t)((s * STAGE_BYTES) >> 4), dbl0 = dbh0 + (uint64_t)(B_TILE_BYTES >> 4);
+#pragma unroll
+                for (int k = 0; k < TM_BK / 8; ++k) {            // one MMA consumes K = 8 tf32
+                    const uint64_t dah = dah0 + k * A_KSTEP, dal = dal0 + k * A_KSTEP;
+                    const uint64_t dbh = dbh0 + k * B_KSTEP, dbl = dbl0 + k * B_KSTEP;
+                    const int step = kb * (TM_BK / 8) + k;
+                    umma_tf32(tmem_base + (uint32_t)((step & 1) * BN), dah, dbh, idesc, step >= 2 ? 1u : 0u);
+                    umma_tf32(tmem_base + 2 * BN, dal, dbh, idesc, step > 0 ? 1u : 0u);
+                    umma_tf32(tmem_base + 2 * BN, dah, dbl, idesc, 1u);
+                }
+                umma_commit(&empty[s]);                          // frees the stage once these MMAs have read it
+                if (kb == kblocks - 1) umma_commit(tmem_full);   // accumulators complete -> epilogue
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---------------- converters (warps 0-7): raw fp32 tile -> hi (in place) + lo (twin tile) ----------------
+        constexpr int A_CHUNKS = A_TILE_BYTES / 16, B_CHUNKS = B_TILE_BYTES / 16;
+        constexpr int NT = TM_CONV_WARPS * 32;
+        constexpr int PER_THREAD = (A_CHUNKS + B_CHUNKS) / NT;
+        static_assert((A_CHUNKS + B_CHUNKS) % NT == 0 && A_CHUNKS % NT == 0, "converter tiling");
+        for (int kb = 0; kb < kblocks; ++kb) {
+            const int s = kb % STAGES;
+            mbar_wait(&full[s], (kb / STAGES) & 1);
+            unsigned char* a_hi = tiles + s * STAGE_BYTES;
+            unsigned char* b_hi = a_hi + 2 * A_TILE_BYTES;
+            // hi = x rounded to TF32 (nearest, ties away: add half an ulp of the 10-bit mantissa to the magnitude, clear the low 13
+            // bits -- what cvt.rna.tf32.f32 computes for finite values, in 2 integer ops instead of its ~10-instruction expansion);
+            // lo = x - hi is exact in fp32 and is stored unrounded: the tensor core only reads its top 19 bits, an error of
+            // 2^-11 |lo| <= 2^-22 |x|, the size of the lo*lo term that 3xTF32 drops anyway.
+            if (!(g.debug & 1)) {
+                float4 v[PER_THREAD];
+#pragma unroll
+                for (int i = 0; i < PER_THREAD; ++i) {           // all loads of the stage in flight first
+                    const int c = threadIdx.x + i * NT;          // A_CHUNKS % NT == 0: chunk i of every thread is on the same side
+                    v[i] = *reinterpret_cast<const float4*>((c < A_CHUNKS) ? a_hi + c * 16 : b_hi + (c - A_CHUNKS) * 16);
+                }
+#pragma unroll
+                for (int i = 0; i < PER_THREAD; ++i) {
+                    const int c = threadIdx.x + i * NT;
+                    unsigned char* hp = (c < A_CHUNKS) ? a_hi + c * 16 : b_hi + (c - A_CHUNKS) * 16;
+                    uint4 h;
+                    float4 l;
+                    h.x = (__float_as_uint(v[i].x) + 0x1000u) & 0xffffe000u; h.y = (__float_as_uint(v[i].y) + 0x1000u) & 0xffffe000u;
+                    h.z = (__float_as_uint(v[i].z) + 0x1000u) & 0xffffe000u; h.w = (__float_as_uint(v[i].w) + 0x1000u) & 0xffffe000u;
+                    l.x = v[i].x - __uint_as_float(h.x); l.y = v[i].y - __uint_as_float(h.y);
+                    l.z = v[i].z - __uint_as_float(h.z); l.w = v[i].w - __uint_as_float(h.w);
+                    *reinterpret_cast<uint4*>(hp) = h;
+                    *reinterpret_cast<float4*>(hp + ((c < A_CHUNKS) ? A_TILE_BYTES : B_TILE_BYTES)) = l;
+                }
+            }
+            fence_async_proxy();                                 // generic-proxy writes -> visible to the MMAs (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ready[s]);
+        }
         // ---------------- epilogue: TMEM -> registers -> global ----------------
+        // warp w reads TMEM lanes 32 (w % 4) .. +31 (rows of the tile) and the 32-column chunks j = w / 4, w / 4 + 2, ...
         mbar_wait(tmem_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int m = m0 + warp * 32 + lane;
-        float* C = g.C + (long long)b * g.sC;
-        const float* bias = g.bias ? g.bias + (long long)b * g.sBias : nullptr;
-        const float* R = g.R ? g.R + (long long)b * g.sR : nullptr;
+        fence_after_sync();
+        const int quarter = warp & 3;
+        const int m = m0 + quarter * 32 + lane;
+        float* __restrict__ C = g.C + (long long)b * g.sC;
+        const float* __restrict__ bias = g.bias ? g.bias + (long long)b * g.sBias : nullptr;
+        const float* __restrict__ R = g.R ? g.R + (long long)b * g.sR : nullptr;
 #pragma unroll 1
-        for (int j = 0; j < BN / 32; ++j) {
-            uint32_t v[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * 32);
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (m < g.M) {
-                const int nb0 = n0 + j * 32;
-                float* dst = (g.ksplit > 1) ? g.ws + ((long long)blockIdx.z * g.M + m) * g.N : C + (long long)m * g.ldc;
-                const bool fast = (nb0 + 32 <= g.N) && ((((uintptr_t)(dst + nb0)) & 15) == 0) &&
-                                  (g.ksplit > 1 || (!R && !g.accumulate));
-                if (fast) {
+        for (int j = warp >> 2; j < BN / 32; j += TM_CONV_WARPS / 4) {
+            float v[32];
+            load_accumulators3<BN>(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * 32), v);
+            const int nb0 = n0 + j * 32;
+            if (m >= g.M || nb0 >= g.N) continue;
+            float* __restrict__ dst = (g.ksplit > 1) ? g.ws + ((long long)blockIdx.z * g.M + m) * g.N : C + (long long)m * g.ldc;
+            const bool full_chunk = nb0 + 32 <= g.N;
+            if (g.ksplit == 1) {
+                const bool bias_vec = bias && full_chunk && ((((uintptr_t)(bias + nb0)) & 15) == 0);
+                if (bias_vec) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
-                        float4 o;
-                        float* of = reinterpret_cast<float*>(&o);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float x = __uint_as_float(v[i + q]);
-                            if (g.ksplit == 1) {
-                                x *= g.alpha;
-                                if (bias) x += bias[nb0 + i + q];
-                                if (g.relu) x = fmaxf(x, 0.f);
-                            }
-                            of[q] = x;
-                        }
-                        *reinterpret_cast<float4*>(dst + nb0 + i) = o;
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + nb0 + i));
+                        v[i] = fmaf(v[i], g.alpha, bv.x); v[i + 1] = fmaf(v[i + 1], g.alpha, bv.y);
+                        v[i + 2] = fmaf(v[i + 2], g.alpha, bv.z); v[i + 3] = fmaf(v[i + 3], g.alpha, bv.w);
                     }
                 } else {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        const int n = nb0 + i;
-                        if (n >= g.N) continue;
-                        float x = __uint_as_float(v[i]);
-                        if (g.ksplit == 1) {
-                            x *= g.alpha;
-                            if (bias) x += bias[n];
-                            if (g.relu) x = fmaxf(x, 0.f);
-                            if (R) x += R[(long long)m * g.ldr + n];
-                            if (g.accumulate) x += dst[n];
-                        }
-                        dst[n] = x;
+                        v[i] *= g.alpha;
+                        if (bias && nb0 + i < g.N) v[i] += __ldg(bias + nb0 + i);
                     }
                 }
-            }
-        }
-    } else {
-        // ---------------- MMA issuer (warp 4) ----------------
-        // instruction descriptor (cute UMMA::InstrDescriptor): c_format F32 (1<<4), a/b format TF32 (2<<7, 2<<10),
-        // K-major A and B (bits 15,16 = 0), N>>3 at bit 17, M>>4 at bit 24
-        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-        for (int kb = 0; kb < kblocks; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
-            mbar_wait(&full[s], ph);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                const uint32_t a_hi = smem_u32(tiles + s * STAGE_FLOATS);
-                const uint32_t a_lo = a_hi + A_FLOATS * 4;
-                const uint32_t b_hi = a_lo + A_FLOATS * 4;
-                const uint32_t b_lo = b_hi + B_FLOATS * 4;
-                constexpr uint32_t A_LBO = TC_BM * 16, B_LBO = BN * 16, SBO = 128;
+                if (g.relu) {
 #pragma unroll
-                for (int k = 0; k < TC_BK / 8; ++k) {            // one UMMA consumes K = 8 tf32 = 2 core matrices
-                    const uint64_t dah = make_desc(a_hi + k * 2 * A_LBO, A_LBO, SBO);
-                    const uint64_t dal = make_desc(a_lo + k * 2 * A_LBO, A_LBO, SBO);
-                    const uint64_t dbh = make_desc(b_hi + k * 2 * B_LBO, B_LBO, SBO);
-                    const uint64_t dbl = make_desc(b_lo + k * 2 * B_LBO, B_LBO, SBO);
-                    umma_tf32(tmem_base, dah, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                    umma_tf32(tmem_base, dal, dbh, idesc, 1u);
-                    umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+                    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
                 }
-                umma_commit(&empty[s]);                          // frees the stage once these MMAs have read it
-                if (kb == kblocks - 1) umma_commit(tmem_full);   // accumulator complete -> epilogue
             }
-            __syncwarp();
+            const bool fast = full_chunk && ((((uintptr_t)(dst + nb0)) & 15) == 0) && (g.ksplit > 1 || (!R && !g.accumulate));
+            if (fast) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                    *reinterpret_cast<float4*>(dst + nb0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int n = nb0 + i;
+                    if (n >= g.N) continue;
+                    float x = v[i];
+                    if (g.ksplit == 1) {
+                        if (R) x += R[(long long)m * g.ldr + n];
+                        if (g.accumulate) x += dst[n];
+                    }
+                    dst[n] = x;
+                }
+            }
         }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    fence_before_sync();
     __syncthreads();
-    if (warp == 4) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
-    }
+    if (warp == TM_MMA_WARP) tmem_dealloc(tmem_base, tm_tmem_cols(BN));
 }
 
-template <int BN, int STAGES>
-int launch_tc(const GemmArgs& g, cudaStream_t st) {
-    constexpr size_t smem = (size_t)STAGES * (2 * TC_BM * TC_BK + 2 * BN * TC_BK) * 4 + (2 * STAGES + 1) * 8 + 16;
+// ---------------------------------------------------------------------------------------------------------------------
+// host side: tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point: no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+struct MapKey {
+    const void* base; long long inner, outer, batch, ld, sb; int box_outer, mn;
+    bool operator==(const MapKey& o) const {
+        return base == o.base && inner == o.inner && outer == o.outer && batch == o.batch && ld == o.ld && sb == o.sb &&
+               box_outer == o.box_outer && mn == o.mn;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = reinterpret_cast<size_t>(k.base);
+        for (long long v : {k.inner, k.outer, k.batch, k.ld, k.sb, (long long)k.box_outer, (long long)k.mn})
+            h = h * 1000003u ^ (size_t)v;
+        return h;
+    }
+};
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+std::mutex g_maps_mutex;
+
+// rank-3 map over a row-major operand: {inner (contiguous), outer (stride ld floats), batch (stride sb floats)};
+// box {32, box_outer, 1}.  mn = 1: MN-major operand (SWIZZLE_128B_ATOM_32B), else K-major (SWIZZLE_128B).
+int get_map(const float* base, long long inner, long long outer, long long batch, long long ld, long long sb, int box_outer, int mn,
+            CUtensorMap* out) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return TRXL_ERR_UNSUPPORTED;
+    MapKey key{base, inner, outer, batch, ld, sb, box_outer, mn};
+    {
+        std::lock_guard<std::mutex> lock(g_maps_mutex);
+        auto it = g_maps.find(key);
+        if (it != g_maps.end()) { *out = it->second; return TRXL_OK; }
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)(batch > 0 ? batch : 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 4, batch > 1 ? (cuuint64_t)sb * 4 : (cuuint64_t)ld * 4 * (cuuint64_t)outer};
+    cuuint32_t box[3] = {32, (cuuint32_t)box_outer, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUtensorMap m;
+    CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return TRXL_ERR_UNSUPPORTED;
+    {
+        std::lock_guard<std::mutex> lock(g_maps_mutex);
+        if (g_maps.size() > 4096) g_maps.clear();          // pointers of freed workspaces would otherwise pile up
+        g_maps.emplace(key, m);
+    }
+    *out = m;
+    return TRXL_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch_tma(const TmaGemmParams& p, cudaStream_t st) {
+    constexpr size_t smem = (size_t)tm_stages(BN) * tm_stage_bytes(BN) + (3 * tm_stages(BN) + 1) * 8 + 16 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { trxl_set_error("tc_gemm: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e)); return TRXL_ERR_CUDA; }
+        cudaError_t e = cudaFuncSetAttribute(tma_gemm_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { trxl_set_error("tma_gemm: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e)); return TRXL_ERR_CUDA; }
         attr_set = true;
     }
-    dim3 grid(trxl_cdiv(g.N, BN), trxl_cdiv(g.M, TC_BM), g.batch * g.ksplit);
-    tc_gemm_kernel<BN, STAGES><<<grid, TC_THREADS, smem, st>>>(g);
+    const GemmArgs& g = p.g;
+    dim3 grid(trxl_cdiv(g.N, BN), trxl_cdiv(g.M, TM_BM), g.batch * g.ksplit);
+    tma_gemm_kernel<BN, A_MN, B_MN><<<grid, TM_THREADS, smem, st>>>(p);
     ++g_trxl_tc_launches;
-    TRXL_CHECK_LAUNCH("tc_gemm");
+    TRXL_CHECK_LAUNCH("tma_gemm");
     return TRXL_OK;
+}
+
+template <int BN>
+int launch_orient(const TmaGemmParams& p, cudaStream_t st) {
+    const bool a_mn = !p.g.a_kc, b_mn = !p.g.b_kc;
+    if (!a_mn && !b_mn) return launch_tma<BN, false, false>(p, st);
+    if (!a_mn && b_mn) return launch_tma<BN, false, true>(p, st);
+    if (a_mn && b_mn) return launch_tma<BN, true, true>(p, st);
+    return launch_tma<BN, true, false>(p, st);
 }
 
 }  // namespace
 
-// Returns TRXL_OK and sets *handled = 1 if the tensor-core path took the GEMM (g.ksplit/k_per_split already chosen).
-int trxl_tc_gemm(const GemmArgs& g, cudaStream_t st) {
-    if (g.N > 64) return launch_tc<128, 3>(g, st);
-    return launch_tc<64, 4>(g, st);
+// Can the TMA path take these operands?  (16-byte aligned bases, leading dimensions / batch strides in whole 16-byte units)
+bool trxl_tc_gemm_eligible(const GemmArgs& g) {
+    auto ok = [](const void* p, long long ld, long long sb, int batch) {
+        return ((uintptr_t)p % 16 == 0) && ld > 0 && (ld % 4 == 0) && (batch <= 1 || (sb > 0 && sb % 4 == 0));
+    };
+    return encode_fn() != nullptr && g.M >= 64 && g.N >= 16 && g.K >= 16 && ok(g.A, g.lda, g.sA, g.batch) && ok(g.B, g.ldb, g.sB, g.batch);
+}
+
+// picks the N tile so that small problems still spread over the SMs; the caller has already chosen g.ksplit / g.k_per_split
+int trxl_tc_gemm_tile_n(const GemmArgs& g) {
+    static int forced = -1;                      // TRXL_TC_BN=32|64|128 pins the tile (tuning experiments)
+    if (forced < 0) { const char* e = getenv("TRXL_TC_BN"); forced = e ? atoi(e) : 0; }
+    if (forced == 32 || forced == 64 || forced == 128) return (g.N <= 32) ? 32 : ((g.N <= 64 && forced == 128) ? 64 : forced);
+    const long long mt = trxl_cdiv(g.M, TM_BM);
+    if (g.N <= 32) return 32;
+    const long long t128 = mt * trxl_cdiv(g.N, 128) * g.batch, t64 = mt * trxl_cdiv(g.N, 64) * g.batch;
+    // measured on B200 (tools/gemm_bench.py): a tile costs ~5 us of fixed latency + ~0.5 us per k-block whatever its width, so
+    // the widest tile that still yields ~100 CTAs wins; below that, more (narrower) CTAs beat wider ones
+    if (g.N > 64 && t128 >= 96) return 128;
+    if (t64 >= 96 || g.N <= 64) return 64;
+    return 32;
+}
+
+// Returns TRXL_ERR_UNSUPPORTED (without launching anything) if a tensor map cannot be encoded; the caller then uses the SIMT path.
+int trxl_tc_gemm(const GemmArgs& g, int bn, cudaStream_t st) {
+    TmaGemmParams p;
+    p.g = g;
+    static int debug = -1;
+    if (debug < 0) { const char* e = getenv("TRXL_TC_DEBUG"); debug = e ? atoi(e) : 0; }
+    p.g.debug = debug;
+    int rc;
+    if (g.a_kc) rc = get_map(g.A, g.K, g.M, g.batch, g.lda, g.sA, TM_BM, 0, &p.ta);       // (M, K) row-major: inner = k
+    else rc = get_map(g.A, g.M, g.K, g.batch, g.lda, g.sA, 32, 1, &p.ta);                  // (K, M) row-major: inner = m
+    if (rc != TRXL_OK) return rc;
+    if (g.b_kc) rc = get_map(g.B, g.K, g.N, g.batch, g.ldb, g.sB, bn, 0, &p.tb);           // (N, K) row-major: inner = k
+    else rc = get_map(g.B, g.N, g.K, g.batch, g.ldb, g.sB, 32, 1, &p.tb);                  // (K, N) row-major: inner = n
+    if (rc != TRXL_OK) return rc;
+    if (bn == 128) return launch_orient<128>(p, st);
+    if (bn == 64) return launch_orient<64>(p, st);
+    return launch_orient<32>(p, st);
 }

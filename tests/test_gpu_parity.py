@@ -319,7 +319,7 @@ def test_forward_backward_c3_dims_vs_oracle(n, ln, pe, gtrxl, dims):
 
 
 def test_tcgen05_gemm_is_used_when_enabled():
-    """With TRXL_TCGEN05=1 the large linears must actually run on the tcgen05 kernel (no silent SIMT fallback)."""
+    """Unless TRXL_TCGEN05=0, the large linears must actually run on the TMA + tcgen05 kernel (no silent SIMT fallback)."""
     import os
     import trxl_native as native
     x, w = torch.randn(512, 256, device=DEV), torch.randn(256, 256, device=DEV)
@@ -328,7 +328,7 @@ def test_tcgen05_gemm_is_used_when_enabled():
     native.linear_forward(x, w, None, y)
     torch.cuda.synchronize()
     used = native.tc_gemm_launches() - before
-    assert used == (1 if os.environ.get("TRXL_TCGEN05", "0") == "1" else 0)
+    assert used == (0 if os.environ.get("TRXL_TCGEN05", "1") == "0" else 1)
     assert torch.allclose(y.double(), x.double() @ w.double().t(), atol=2e-4, rtol=1e-4)
 
 

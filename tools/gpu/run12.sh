@@ -1,0 +1,3 @@
+cd $GRAFT_REPO_ROOT
+for bn in 32 64 128; do echo "== BN $bn"; TRXL_TC_BN=$bn timeout 300 python tools/gemm_bench.py 2>&1 | head -12; done > gpurun_out/r2_gemm_bn2.log 2>&1
+cat gpurun_out/r2_gemm_bn2.log
