@@ -28,10 +28,12 @@ class MiniBatch(dict):
 
     KEYS = ("actions", "values", "log_probs", "advantages", "obs", "memory_mask", "memory_indices", "memories")
 
-    def __init__(self, buffer, sample_index):
+    def __init__(self, buffer, sample_index, sample_index_cpu=None):
         super().__init__()
         self.buffer = buffer
         self.sample_index = sample_index
+        self.sample_index_cpu = sample_index_cpu      # same rows on the host (the trainer groups them by episode)
+        self.groups = None                            # episode grouping for the tensor-core attention (trainer._group_epoch)
 
     def __missing__(self, key):
         flat = self.buffer.samples_flat
@@ -107,10 +109,11 @@ class Buffer():
         """Yield ``n_mini_batch`` shuffled minibatches (plus a short remainder batch if the batch size
         does not divide, as buffer.py:82 does).  The permutation is drawn with torch's CPU generator so
         a seeded run sees the same index stream as the reference on CPU."""
-        perm = torch.randperm(self.batch_size, generator=generator, device="cpu").to(self.device)
+        perm_cpu = torch.randperm(self.batch_size, generator=generator, device="cpu")
+        perm = perm_cpu.to(self.device)
         size = self.batch_size // self.n_mini_batches
         for start in range(0, self.batch_size, size):
-            yield MiniBatch(self, perm[start:start + size].contiguous())
+            yield MiniBatch(self, perm[start:start + size].contiguous(), perm_cpu[start:start + size])
 
     def calc_advantages(self, last_value, gamma, lamda):
         """Generalised advantage estimation (buffer.py:95-113) as one kernel; results are bit-identical

@@ -5,6 +5,7 @@
 
 #include "../../include/trxl_ppo.h"
 #include "attention.cuh"
+#include "attention_tc.cuh"
 #include "conv.cuh"
 #include "tc_conv.cuh"
 #include "elementwise.cuh"
@@ -186,6 +187,49 @@ int trxl_model_forward(const trxl_model_config* cfg, const float* params, const 
     io.N = N; io.feat = feat; io.table = table; io.slots = slots; io.ep_index = (cll)ep_index; io.win_index = (cll)win_index;
     io.mask = mask; io.pe_index = (cll)pe_index; io.sample_index = (cll)sample_index; io.pe_table = pe_table;
     return model_forward(cfg, params, io, workspace, logits, value, out_mem, S(stream));
+}
+
+static void set_groups(ModelIO& io, const trxl_attn_groups* g) {
+    if (!g) return;
+    io.table_pe = g->table_pe; io.n_episodes = g->n_episodes; io.tiles = reinterpret_cast<const int4*>(g->tiles);
+    io.n_tiles = g->n_tiles; io.ranges = reinterpret_cast<const int4*>(g->ranges);
+}
+
+int trxl_model_forward_grouped(const trxl_model_config* cfg, const float* params, const float* feat, const float* table, int64_t slots,
+                               const int64_t* ep_index, const int64_t* win_index, const uint8_t* mask, const int64_t* pe_index,
+                               const int64_t* sample_index, const float* pe_table, int N, float* workspace, float* logits,
+                               float* value, float* out_mem, const trxl_attn_groups* groups, void* stream) {
+    ModelIO io;
+    io.N = N; io.feat = feat; io.table = table; io.slots = slots; io.ep_index = (cll)ep_index; io.win_index = (cll)win_index;
+    io.mask = mask; io.pe_index = (cll)pe_index; io.sample_index = (cll)sample_index; io.pe_table = pe_table;
+    set_groups(io, groups);
+    return model_forward(cfg, params, io, workspace, logits, value, out_mem, S(stream));
+}
+
+int trxl_model_backward_grouped(const trxl_model_config* cfg, const float* params, float* grads, const float* feat, const float* table,
+                                int64_t slots, const int64_t* ep_index, const int64_t* win_index, const uint8_t* mask,
+                                const int64_t* pe_index, const int64_t* sample_index, const float* pe_table, int N, float* workspace,
+                                const float* out_mem, const float* dlogits, const float* dvalue, float* dfeat,
+                                const trxl_attn_groups* groups, void* stream) {
+    ModelIO io;
+    io.N = N; io.feat = feat; io.table = table; io.slots = slots; io.ep_index = (cll)ep_index; io.win_index = (cll)win_index;
+    io.mask = mask; io.pe_index = (cll)pe_index; io.sample_index = (cll)sample_index; io.pe_table = pe_table;
+    set_groups(io, groups);
+    return model_backward(cfg, params, grads, io, workspace, out_mem, dlogits, dvalue, dfeat, S(stream));
+}
+
+int trxl_attention_ranges(const uint8_t* mask, const int64_t* win_index, const int64_t* ep_index, const int64_t* sample_index, int N,
+                          int L, int32_t* ranges4, void* stream) {
+    return attn_tc_ranges(mask, (cll)win_index, (cll)ep_index, (cll)sample_index, N, L, reinterpret_cast<int4*>(ranges4), S(stream));
+}
+
+int trxl_table_add_pe(const float* table, const float* pe_table, float* out, int64_t E, int M, int B, int D, void* stream) {
+    return attn_tc_table_add_pe(table, pe_table, out, E, M, B, D, S(stream));
+}
+
+int trxl_grouped_attention_supported(const trxl_model_config* cfg) {
+    return cfg && cfg->layer_norm != TRXL_LN_PRE && cfg->pos_enc != TRXL_PE_LEARNED &&
+           attn_tc_supported(cfg->embed_dim, cfg->num_heads, cfg->max_episode_steps, cfg->num_blocks) ? 1 : 0;
 }
 
 int trxl_model_backward(const trxl_model_config* cfg, const float* params, float* grads, const float* feat, const float* table,

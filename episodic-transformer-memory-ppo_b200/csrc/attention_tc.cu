@@ -1,0 +1,192 @@
+// Episode-grouped window attention on the tensor cores (query length 1), forward and backward.
+//
+// Reference contractions: transformer.py:59 (einsum nqhd,nkhd->nhqk) and :73 (nhql,nlhd->nqhd), after the query-side fold
+// of attention.cu:  energy[n,h,t] = qk[n,h,:] . (x_t + pe_t),   ctx[n,h,:] = sum_t p[n,h,t] (x_t + pe_t).
+//
+// The per-sample kernel of attention.cu streams every sample's window separately on the FMA pipe.  Here the minibatch is
+// sorted by episode (the host does that once per epoch, trainer.py) and cut into row tiles of 128 (sample, head) rows that
+// belong to ONE episode.  For such a tile both contractions are dense GEMMs against that episode's memory rows of the block
+//     S   (128 x M)  = QK_tile (128 x D)  .  Xpe_e^T (D x M)          all M slots of the episode, window applied afterwards
+//     ctx (128 x D)  = P_tile  (128 x M)  .  Xpe_e   (M x D)
+// and run on the TMA + tcgen05 3xTF32 GEMM of tc_gemm.cu in its grouped mode: the episode's rows are fetched ONCE per tile by
+// TMA straight from the (E, M, B, D) table (a strided rank-3 tensor map: row stride B*D, batch stride M*B*D -- no gather, no
+// copy), instead of once per sample.  The softmax over each row's window (visible slots form one contiguous slot range
+// [lo, lo+cnt); a fully masked row attends uniformly over its L window slots, as the reference's finite -1e20 fill does) is a
+// small warp-per-row kernel between the two GEMMs.  Backward: dP = dctx . Xpe_e^T, dS = P (dP - P.dP) / sqrt(D) on the window,
+// dqk = dS . Xpe_e -- the same two GEMM shapes.  The memory rows carry no gradient (transformer.py:248).
+//
+// Xpe = table + positional row is materialised once per update (trxl_table_add_pe): the table is frozen during the
+// optimisation epochs and the sinusoidal table has no parameters.  Learned positional tables and the pre-LayerNorm fold stay
+// on the per-sample kernel (attention.cu).
+#include "attention_tc.cuh"
+
+#include "gemm.cuh"
+
+int trxl_tc_gemm(const GemmArgs& g, int bn, cudaStream_t st);      // tc_gemm.cu
+bool trxl_tc_gemm_eligible(const GemmArgs& g);
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// ranges[n] = {first visible slot, number of visible slots, uniform (row fully masked), episode}
+__global__ void attn_ranges_kernel(const unsigned char* __restrict__ mask, const long long* __restrict__ win_index,
+                                   const long long* __restrict__ ep_index, const long long* __restrict__ sample_index, int N, int L,
+                                   int4* __restrict__ ranges) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const long long row = sample_index ? sample_index[n] : n;
+    int cnt = 0, first = L;
+    for (int l = lane; l < L; l += 32) {
+        if (mask[row * L + l]) { ++cnt; first = min(first, l); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cnt += __shfl_xor_sync(FULL, cnt, o);
+        first = min(first, __shfl_xor_sync(FULL, first, o));
+    }
+    if (lane == 0) {
+        int4 r;
+        if (cnt == 0) { r.x = (int)win_index[row * L]; r.y = L; r.z = 1; }
+        else { r.x = (int)win_index[row * L + first]; r.y = cnt; r.z = 0; }
+        r.w = (int)(ep_index ? ep_index[row] : row);
+        ranges[n] = r;
+    }
+}
+
+// in place: S (rows, ld) energies over all slots -> P: softmax over [lo, lo+cnt) of S / scale, zero elsewhere.  One warp per row.
+__global__ void attn_softmax_kernel(float* __restrict__ S, long long ld, int M, const int4* __restrict__ ranges, int H, int rows,
+                                    float scale, int L) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const int4 rg = ranges[r / H];
+    float* row = S + (long long)r * ld;
+    const int lo = rg.x, hi = rg.x + rg.y;
+    if (rg.z) {                                   // fully masked: uniform over the L window slots
+        const float u = 1.f / (float)L;
+        for (int t = lane; t < M; t += 32) row[t] = (t >= lo && t < hi) ? u : 0.f;
+        return;
+    }
+    float m = -INFINITY;
+    for (int t = lo + lane; t < hi; t += 32) {
+        const float e = __fdiv_rn(row[t], scale);
+        row[t] = e;
+        m = fmaxf(m, e);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+    float s = 0.f;
+    for (int t = lo + lane; t < hi; t += 32) {
+        const float p = __expf(row[t] - m);
+        row[t] = p;
+        s += p;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    const float inv = 1.f / s;
+    for (int t = lane; t < M; t += 32) row[t] = (t >= lo && t < hi) ? row[t] * inv : 0.f;
+}
+
+// in place: dP (rows, ld) -> dS = P (dP - sum_t P dP) / scale on the window, zero elsewhere (and everywhere for uniform rows)
+__global__ void attn_dscore_kernel(float* __restrict__ dP, const float* __restrict__ P, long long ld, int M,
+                                   const int4* __restrict__ ranges, int H, int rows, float inv_scale) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const int4 rg = ranges[r / H];
+    float* d = dP + (long long)r * ld;
+    const float* p = P + (long long)r * ld;
+    const int lo = rg.x, hi = rg.x + rg.y;
+    float dot = 0.f;
+    if (!rg.z) {
+        for (int t = lo + lane; t < hi; t += 32) dot = fmaf(p[t], d[t], dot);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL, dot, o);
+    }
+    for (int t = lane; t < M; t += 32)
+        d[t] = (!rg.z && t >= lo && t < hi) ? p[t] * (d[t] - dot) * inv_scale : 0.f;
+}
+
+// out[e, m, b, :] = table[e, m, b, :] + pe[m, :]
+__global__ void table_add_pe_kernel(const float4* __restrict__ table, const float4* __restrict__ pe, float4* __restrict__ out,
+                                    long long total4, int M, int B, int D4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        const int d = (int)(i % D4);
+        const int m = (int)((i / ((long long)D4 * B)) % M);
+        float4 v = table[i];
+        const float4 p = pe[(long long)m * D4 + d];
+        v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+        out[i] = v;
+    }
+}
+
+GemmArgs grouped_args(const AttnTcArgs& a, const float* A, long long lda, int K, int Nn, int b_kc, float* C, long long ldc) {
+    GemmArgs g;
+    g.M = a.N * a.H; g.N = Nn; g.K = K;
+    g.A = A; g.lda = lda; g.a_kc = 1;
+    g.B = a.table_pe + (long long)a.blk * a.D; g.ldb = (long long)a.B * a.D; g.b_kc = b_kc;
+    g.sB = a.slots * a.B * a.D; g.b_batch = a.n_episodes;
+    g.C = C; g.ldc = ldc;
+    g.tiles = a.tiles; g.n_tiles = a.n_tiles;
+    g.ksplit = 1; g.k_per_split = K;
+    g.alpha = 1.f;
+    return g;
+}
+
+}  // namespace
+
+long long attn_tc_row_floats(long long slots) { return (slots + 3) / 4 * 4; }
+
+bool attn_tc_supported(int D, int H, long long slots, int B) {
+    return H > 0 && 128 % H == 0 && D % 4 == 0 && D >= 4 && slots >= 1 && ((long long)B * D) % 4 == 0;
+}
+
+int attn_tc_ranges(const unsigned char* mask, const long long* win_index, const long long* ep_index, const long long* sample_index,
+                   int N, int L, int4* ranges, cudaStream_t st) {
+    TRXL_CHECK_ARG(mask && win_index && ranges && N >= 0 && L > 0, "attention_ranges: bad arguments");
+    if (N == 0) return TRXL_OK;
+    attn_ranges_kernel<<<trxl_cdiv(N, 8), 256, 0, st>>>(mask, win_index, ep_index, sample_index, N, L, ranges);
+    TRXL_CHECK_LAUNCH("attention_ranges");
+    return TRXL_OK;
+}
+
+int attn_tc_table_add_pe(const float* table, const float* pe, float* out, long long E, int M, int B, int D, cudaStream_t st) {
+    TRXL_CHECK_ARG(table && pe && out && D % 4 == 0, "table_add_pe: bad arguments");
+    const long long total4 = E * M * B * (D / 4);
+    if (total4 == 0) return TRXL_OK;
+    int blocks = trxl_cdiv(total4, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    table_add_pe_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(table), reinterpret_cast<const float4*>(pe),
+                                               reinterpret_cast<float4*>(out), total4, M, B, D / 4);
+    TRXL_CHECK_LAUNCH("table_add_pe");
+    return TRXL_OK;
+}
+
+// qk (N, H, D) -> P (N*H, ld) [saved for the backward], ctx (N, H, D)
+int attn_tc_forward(const AttnTcArgs& a, const float* qk, float* P, float* ctx, cudaStream_t st) {
+    const long long ld = attn_tc_row_floats(a.slots);
+    const int rows = a.N * a.H;
+    GemmArgs g1 = grouped_args(a, qk, a.D, a.D, (int)a.slots, 1, P, ld);               // S = QK . Xpe^T     (B K-major: rows = slots)
+    TRXL_CHECK_ARG(trxl_tc_gemm_eligible(g1), "attention_tc: operands not TMA-eligible");
+    TRXL_PROPAGATE(trxl_tc_gemm(g1, 128, st));
+    attn_softmax_kernel<<<trxl_cdiv(rows, 8), 256, 0, st>>>(P, ld, (int)a.slots, a.ranges, a.H, rows, a.scale, a.L);
+    TRXL_CHECK_LAUNCH("attention_softmax");
+    GemmArgs g2 = grouped_args(a, P, ld, (int)a.slots, a.D, 0, ctx, a.D);               // ctx = P . Xpe      (B MN-major: k = slot)
+    TRXL_PROPAGATE(trxl_tc_gemm(g2, 128, st));
+    return TRXL_OK;
+}
+
+// dctx (N, H, D), P from the forward -> dqk (N, H, D); scratch (N*H, ld)
+int attn_tc_backward(const AttnTcArgs& a, const float* P, const float* dctx, float* scratch, float* dqk, cudaStream_t st) {
+    const long long ld = attn_tc_row_floats(a.slots);
+    const int rows = a.N * a.H;
+    GemmArgs g1 = grouped_args(a, dctx, a.D, a.D, (int)a.slots, 1, scratch, ld);        // dP = dctx . Xpe^T
+    TRXL_PROPAGATE(trxl_tc_gemm(g1, 128, st));
+    attn_dscore_kernel<<<trxl_cdiv(rows, 8), 256, 0, st>>>(scratch, P, ld, (int)a.slots, a.ranges, a.H, rows, 1.f / a.scale);
+    TRXL_CHECK_LAUNCH("attention_dscore");
+    GemmArgs g2 = grouped_args(a, scratch, ld, (int)a.slots, a.D, 0, dqk, a.D);         // dqk = dS . Xpe
+    TRXL_PROPAGATE(trxl_tc_gemm(g2, 128, st));
+    return TRXL_OK;
+}

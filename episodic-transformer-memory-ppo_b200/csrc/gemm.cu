@@ -422,7 +422,7 @@ int trxl_gemm(GemmArgs g, cudaStream_t st) {
         }
     }
     int rc;
-    if (tc_enabled() && trxl_tc_gemm_eligible(g)) {
+    if (tc_enabled() && g.M >= 64 && g.N >= 16 && g.K >= 16 && trxl_tc_gemm_eligible(g)) {
         // tensor-core path (tc_gemm.cu): 128 x {32,64,128} tiles, TMA-staged operands, 3xTF32 in TMEM; split K when few tiles
         GemmArgs t = g;
         const int bn = trxl_tc_gemm_tile_n(t);

@@ -12,6 +12,7 @@
 
 #include "../../include/trxl_ppo.h"
 #include "attention.cuh"
+#include "attention_tc.cuh"
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "model.cuh"
@@ -166,7 +167,7 @@ struct Acts {
     std::vector<BlockA> blk;
     // backward scratch
     float *pool[2][9], *dH0;
-    float *dctx, *dqk, *dqkb, *dA1, *dz, *drx, *dWg, *dvec, *dhp, *dhv, *ew;
+    float *dctx, *dqk, *dqkb, *dscore, *dA1, *dz, *drx, *dWg, *dvec, *dhp, *dhv, *ew;
     float* gemm_ws; long long gemm_ws_n;      // split-K partials of the weight-gradient GEMMs
     long long total;
 };
@@ -195,7 +196,11 @@ void carve(const trxl_model_config* c, int N, float* ws, Acts& A) {
         if (pre) { k.q_in = b.take(ND); k.m1 = b.take(N); k.r1 = b.take(N); k.h_ = b.take(ND); k.m2 = b.take(N); k.r2 = b.take(N);
                    k.qkb = b.take((long long)N * H); k.Wkg = b.take(D * D); k.kb = b.take(D); k.Wvg = b.take(D * D); k.bv = b.take(D); }
         if (post) { k.h1 = b.take(ND); k.m1 = b.take(N); k.r1 = b.take(N); k.out_pre = b.take(ND); k.m2 = b.take(N); k.r2 = b.take(N); }
-        k.Q = b.take(ND); k.qk = b.take(ND * H); k.probs = b.take((long long)N * H * L); k.ctx = b.take(ND * H);
+        // probs: (N, H, L) for the per-sample kernel; the episode-grouped tensor-core path keeps P over all slots of the episode
+        long long probs_row = L;
+        if (!pre && c->pos_enc != TRXL_PE_LEARNED && attn_tc_row_floats(c->max_episode_steps) > probs_row)
+            probs_row = attn_tc_row_floats(c->max_episode_steps);
+        k.Q = b.take(ND); k.qk = b.take(ND * H); k.probs = b.take((long long)N * H * probs_row); k.ctx = b.take(ND * H);
         k.att_o = b.take(ND); k.h1pre = b.take(ND); k.f = b.take(ND);
         if (c->gtrxl) {
             k.att = b.take(ND);
@@ -208,6 +213,7 @@ void carve(const trxl_model_config* c, int N, float* ws, Acts& A) {
     for (int p = 0; p < 2; ++p) for (int i = 0; i < 9; ++i) A.pool[p][i] = b.take(ND);
     A.dH0 = b.take(ND);
     A.dctx = b.take(ND * H); A.dqk = b.take(ND * H); A.dqkb = b.take((long long)N * H);
+    A.dscore = b.take((long long)N * H * attn_tc_row_floats(c->max_episode_steps > 0 ? c->max_episode_steps : 1));
     A.dA1 = b.take(3 * ND); A.dz = b.take(ND); A.drx = b.take(ND);
     A.dWg = b.take(D * D); A.dvec = b.take(D);
     A.dhp = b.take(N * hid); A.dhv = b.take(N * hid);
@@ -226,6 +232,21 @@ AttnArgs attn_args(const trxl_model_config* c, const ModelIO& io, int blk, const
     t.qk = a.qk; t.qkb = (c->layer_norm == TRXL_LN_PRE) ? a.qkb : nullptr; t.ln = c->layer_norm == TRXL_LN_PRE;
     t.scale = (float)sqrt((double)c->embed_dim);
     t.probs = a.probs; t.ctx = a.ctx;
+    return t;
+}
+
+// the episode-grouped tensor-core attention applies when the caller supplied the grouping and the block needs neither the
+// pre-LayerNorm fold nor gradients into a learned positional table
+bool use_grouped_attention(const trxl_model_config* c, const ModelIO& io) {
+    return io.tiles && io.ranges && io.table_pe && io.n_tiles > 0 && c->layer_norm != TRXL_LN_PRE && c->pos_enc != TRXL_PE_LEARNED &&
+           io.slots == c->max_episode_steps && attn_tc_supported(c->embed_dim, c->num_heads, io.slots, c->num_blocks);
+}
+
+AttnTcArgs attn_tc_args(const trxl_model_config* c, const ModelIO& io, int blk) {
+    AttnTcArgs t;
+    t.N = io.N; t.L = c->memory_length; t.D = c->embed_dim; t.H = c->num_heads; t.B = c->num_blocks; t.blk = blk;
+    t.table_pe = io.table_pe; t.slots = io.slots; t.n_episodes = io.n_episodes; t.tiles = io.tiles; t.n_tiles = io.n_tiles;
+    t.ranges = io.ranges; t.scale = (float)sqrt((double)c->embed_dim);
     return t;
 }
 
@@ -337,6 +358,7 @@ int model_forward(const trxl_model_config* c, const float* P, const ModelIO& io,
     const bool pre = c->layer_norm == TRXL_LN_PRE, post = c->layer_norm == TRXL_LN_POST;
     const float* pe = c->pos_enc == TRXL_PE_RELATIVE ? io.pe_table : (c->pos_enc == TRXL_PE_LEARNED ? P + L.pos : nullptr);
 
+    const bool grouped = use_grouped_attention(c, io);
     TRXL_PROPAGATE(gemm_nt(st, N, D, c->feat_dim, io.feat, c->feat_dim, P + L.Wh, c->feat_dim, A.h0, D, P + L.bh, 1));
     TRXL_PROPAGATE(gemm_nt(st, N, D, D, A.h0, D, P + L.We, D, out_mem, BD, P + L.be, 1));
     for (int i = 0; i < B; ++i) {
@@ -362,7 +384,8 @@ int model_forward(const trxl_model_config* c, const float* P, const ModelIO& io,
         }
         // qk[n,h,:] = Q[n, h*dh:(h+1)*dh] @ Wkg[h*dh:(h+1)*dh, :]
         TRXL_PROPAGATE(per_head_gemm(st, N, D, dh, a.Q, D, 1, dh, Wkg, D, 0, (long long)dh * D, a.qk, (long long)H * D, D, H));
-        TRXL_PROPAGATE(trxl_window_attn_fwd(attn_args(c, io, i, a, pe), st));
+        if (grouped) TRXL_PROPAGATE(attn_tc_forward(attn_tc_args(c, io, i), a.qk, a.probs, a.ctx, st));
+        else TRXL_PROPAGATE(trxl_window_attn_fwd(attn_args(c, io, i, a, pe), st));
         // att_o[n, h*dh + j] = ctx[n,h,:] . Wvg[h*dh + j, :] (+ bv)
         TRXL_PROPAGATE(per_head_gemm(st, N, dh, D, a.ctx, (long long)H * D, 1, D, Wvg, D, 1, (long long)dh * D, a.att_o, D, dh, H, bv, dh));
         if (c->gtrxl) {
@@ -412,6 +435,7 @@ int model_backward(const trxl_model_config* c, const float* P, float* G, const M
     const bool pre = c->layer_norm == TRXL_LN_PRE, post = c->layer_norm == TRXL_LN_POST;
     const float* pe = c->pos_enc == TRXL_PE_RELATIVE ? io.pe_table : (c->pos_enc == TRXL_PE_LEARNED ? P + L.pos : nullptr);
 
+    const bool grouped = use_grouped_attention(c, io);
     // ---- heads ----
     float* dH = A.dH0;        // gradient w.r.t. the current block output; never inside the pool being used
     TRXL_PROPAGATE(gemm_tn(st, L.sumA, hid, N, dlogits, L.sumA, A.hp, hid, G + L.Wbr, hid, 0, A.gemm_ws, A.gemm_ws_n));
@@ -488,10 +512,14 @@ int model_backward(const trxl_model_config* c, const float* P, float* G, const M
             TRXL_PROPAGATE(ew_colsum(st, dAtto, D, A.dvec, N, D, 1.f, 0, A.ew));
             TRXL_PROPAGATE(ew_unfold(st, A.dWg, A.dvec, P + p.Wv, P + p.nkw, P + p.nkb, G + p.Wv, G + p.nkw, G + p.nkb, D, D, 0));
         }
-        AttnBwdArgs ab;
-        ab.dctx = A.dctx; ab.dqk = A.dqk; ab.dqkb = pre ? A.dqkb : nullptr;
-        ab.dpe = (c->pos_enc == TRXL_PE_LEARNED) ? G + L.pos : nullptr;
-        TRXL_PROPAGATE(trxl_window_attn_bwd(attn_args(c, io, i, a, pe), ab, st));
+        if (grouped) {
+            TRXL_PROPAGATE(attn_tc_backward(attn_tc_args(c, io, i), a.probs, A.dctx, A.dscore, A.dqk, st));
+        } else {
+            AttnBwdArgs ab;
+            ab.dctx = A.dctx; ab.dqk = A.dqk; ab.dqkb = pre ? A.dqkb : nullptr;
+            ab.dpe = (c->pos_enc == TRXL_PE_LEARNED) ? G + L.pos : nullptr;
+            TRXL_PROPAGATE(trxl_window_attn_bwd(attn_args(c, io, i, a, pe), ab, st));
+        }
         // dQ[n, h*dh + j] = dqk[n,h,:] . Wkg[h*dh + j, :]
         float* dQ = S[4];
         TRXL_PROPAGATE(per_head_gemm(st, N, dh, D, A.dqk, HD, 1, D, Wkg, D, 1, (long long)dh * D, dQ, D, dh, H));

@@ -14,6 +14,12 @@ struct ModelIO {
     const long long* pe_index = nullptr;
     const long long* sample_index = nullptr;
     const float* pe_table = nullptr;
+    // optional episode grouping (trxl_attn_groups): enables the tensor-core attention path for post-/no-LayerNorm blocks with a
+    // parameter-free positional table
+    const float* table_pe = nullptr;            // (E, slots, B, D) table + positional rows
+    int n_episodes = 0;
+    const int4* tiles = nullptr; int n_tiles = 0;
+    const int4* ranges = nullptr;
 };
 
 int model_layout(const trxl_model_config* cfg, std::vector<trxl_param_entry>& out, long long* total, int* groups);

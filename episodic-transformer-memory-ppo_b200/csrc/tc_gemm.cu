@@ -104,8 +104,14 @@ __global__ void __launch_bounds__(TM_THREADS, 1) tma_gemm_kernel(const __grid_co
 
     const GemmArgs& g = p.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * TM_BM, n0 = blockIdx.x * BN;
+    int m0 = blockIdx.y * TM_BM, m_end = g.M;
+    const int n0 = blockIdx.x * BN;
     const int b = blockIdx.z / g.ksplit, split = blockIdx.z % g.ksplit;
+    int b_of_B = b;
+    if (g.tiles) {                                    // grouped mode: this CTA's rows and B batch element come from the tile table
+        const int4 t = g.tiles[blockIdx.y];
+        m0 = t.x; m_end = min(g.M, t.x + t.y); b_of_B = t.z;
+    }
     const int k_begin = split * g.k_per_split;
     const int k_end = min(g.K, k_begin + g.k_per_split);
     const int kblocks = (k_end - k_begin + TM_BK - 1) / TM_BK;
@@ -142,9 +148,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) tma_gemm_kernel(const __grid_co
                 }
                 if (B_MN) {
 #pragma unroll
-                    for (int grp = 0; grp < BN / 32; ++grp) tma_load_3d(b_dst + grp * 4096, &p.tb, &full[s], n0 + 32 * grp, k0, b);
+                    for (int grp = 0; grp < BN / 32; ++grp) tma_load_3d(b_dst + grp * 4096, &p.tb, &full[s], n0 + 32 * grp, k0, b_of_B);
                 } else {
-                    tma_load_3d(b_dst, &p.tb, &full[s], k0, n0, b);
+                    tma_load_3d(b_dst, &p.tb, &full[s], k0, n0, b_of_B);
                 }
             }
         }
@@ -235,7 +241,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) tma_gemm_kernel(const __grid_co
             float v[32];
             load_accumulators3<BN>(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * 32), v);
             const int nb0 = n0 + j * 32;
-            if (m >= g.M || nb0 >= g.N) continue;
+            if (m >= m_end || nb0 >= g.N) continue;
             float* __restrict__ dst = (g.ksplit > 1) ? g.ws + ((long long)blockIdx.z * g.M + m) * g.N : C + (long long)m * g.ldc;
             const bool full_chunk = nb0 + 32 <= g.N;
             if (g.ksplit == 1) {
@@ -364,7 +370,7 @@ int launch_tma(const TmaGemmParams& p, cudaStream_t st) {
         attr_set = true;
     }
     const GemmArgs& g = p.g;
-    dim3 grid(trxl_cdiv(g.N, BN), trxl_cdiv(g.M, TM_BM), g.batch * g.ksplit);
+    dim3 grid(trxl_cdiv(g.N, BN), g.tiles ? g.n_tiles : trxl_cdiv(g.M, TM_BM), g.batch * g.ksplit);
     tma_gemm_kernel<BN, A_MN, B_MN><<<grid, TM_THREADS, smem, st>>>(p);
     ++g_trxl_tc_launches;
     TRXL_CHECK_LAUNCH("tma_gemm");
@@ -387,7 +393,8 @@ bool trxl_tc_gemm_eligible(const GemmArgs& g) {
     auto ok = [](const void* p, long long ld, long long sb, int batch) {
         return ((uintptr_t)p % 16 == 0) && ld > 0 && (ld % 4 == 0) && (batch <= 1 || (sb > 0 && sb % 4 == 0));
     };
-    return encode_fn() != nullptr && g.M >= 64 && g.N >= 16 && g.K >= 16 && ok(g.A, g.lda, g.sA, g.batch) && ok(g.B, g.ldb, g.sB, g.batch);
+    const int nb = g.tiles ? g.b_batch : g.batch;
+    return encode_fn() != nullptr && g.M >= 1 && g.N >= 1 && g.K >= 1 && ok(g.A, g.lda, g.sA, g.batch) && ok(g.B, g.ldb, g.sB, nb);
 }
 
 // picks the N tile so that small problems still spread over the SMs; the caller has already chosen g.ksplit / g.k_per_split
@@ -416,8 +423,9 @@ int trxl_tc_gemm(const GemmArgs& g, int bn, cudaStream_t st) {
     if (g.a_kc) rc = get_map(g.A, g.K, g.M, g.batch, g.lda, g.sA, TM_BM, 0, &p.ta);       // (M, K) row-major: inner = k
     else rc = get_map(g.A, g.M, g.K, g.batch, g.lda, g.sA, 32, 1, &p.ta);                  // (K, M) row-major: inner = m
     if (rc != TRXL_OK) return rc;
-    if (g.b_kc) rc = get_map(g.B, g.K, g.N, g.batch, g.ldb, g.sB, bn, 0, &p.tb);           // (N, K) row-major: inner = k
-    else rc = get_map(g.B, g.N, g.K, g.batch, g.ldb, g.sB, 32, 1, &p.tb);                  // (K, N) row-major: inner = n
+    const long long nb = g.tiles ? g.b_batch : g.batch;
+    if (g.b_kc) rc = get_map(g.B, g.K, g.N, nb, g.ldb, g.sB, bn, 0, &p.tb);                // (N, K) row-major: inner = k
+    else rc = get_map(g.B, g.N, g.K, nb, g.ldb, g.sB, 32, 1, &p.tb);                       // (K, N) row-major: inner = n
     if (rc != TRXL_OK) return rc;
     if (bn == 128) return launch_orient<128>(p, st);
     if (bn == 64) return launch_orient<64>(p, st);

@@ -219,6 +219,7 @@ class PPOTrainer:
         self.use_cuda_graphs = os.environ.get("TRXL_NO_GRAPHS", "0") != "1"
         self._capture_stream = None
         self._mapped = {}
+        self._table_pe = None           # table + positional rows for the episode-grouped tensor-core attention
         self._start_update = 0          # first update of run_training (advanced by load_checkpoint)
         self.device_feed = None         # optional device_feed.SyntheticDeviceFeed replacing the env workers (bench.py)
         self._forced_buf = None         # persistent (T, W, n_branches) int64 device buffer behind ``_forced_actions``
@@ -740,8 +741,11 @@ class PPOTrainer:
         stats = torch.zeros((n_steps, 6), dtype=torch.float32, device=self.device)
         norms = torch.zeros((n_steps, g + 2), dtype=torch.float32, device=self.device)
         i = 0
+        grouping = self._begin_grouped_attention()
         for _ in range(self.config["epochs"]):
             batches = list(self.buffer.mini_batch_generator())
+            if grouping is not None:
+                self._group_epoch(batches, grouping)
             # advantage statistics of every minibatch of the epoch (the permutation is known up front): one small
             # all-reduce per epoch instead of one per optimiser step
             advstats = torch.zeros((len(batches), 3), dtype=torch.float64, device=self.device)
@@ -760,6 +764,62 @@ class PPOTrainer:
                 grad_info.setdefault(key, []).append(value)
         self.timers["train"] += time.perf_counter() - t0
         return train_info, grad_info
+
+    # -- episode-grouped tensor-core attention (csrc/attention_tc.cu): the host sorts every minibatch by episode and cuts it into
+    #    row tiles whose samples share an episode, so that the energies / context contractions become dense GEMMs per tile
+    def _begin_grouped_attention(self):
+        """Once per update: the table with positional rows added (the table is frozen during the epochs) and the episode of
+        every buffer row on the host.  Returns None when the configuration uses the per-sample kernel."""
+        model, buf = self.model, self.buffer
+        if os.environ.get("TRXL_GROUPED_ATTENTION", "1") == "0" or not native.grouped_attention_supported(model._cfg):
+            return None
+        table = buf.memories
+        if not torch.is_tensor(table) or table.dim() != 4 or table.shape[1] != self.max_episode_length:
+            return None
+        pe = model._pe_table()
+        if pe is None:
+            table_pe = table                                           # no positional encoding
+        else:
+            if self._table_pe is None or self._table_pe.shape != self._table.shape:
+                self._table_pe = torch.empty_like(self._table)
+            table_pe = self._table_pe[:table.shape[0]]
+            native.table_add_pe(table, pe, table_pe, table.shape[0])
+        episode_of_row = buf.samples_flat["memory_index"].cpu().numpy()       # (W*T,) -- one small download per update
+        return {"table_pe": table_pe, "n_episodes": int(table.shape[0]), "episode_of_row": episode_of_row,
+                "rows_per_tile": 128 // self.model.transformer.num_heads * self.model.transformer.num_heads}
+
+    def _group_epoch(self, batches, grouping):
+        """Sort every minibatch of the epoch by episode (a minibatch is a set: the loss and its gradient do not depend on the
+        order) and build its tile table {first (sample, head) row, rows, episode, 0}; one upload for the whole epoch."""
+        H = self.model.transformer.num_heads
+        spt = 128 // H                                                   # samples per 128-row tile
+        sorted_idx, tiles, n_tiles = [], [], []
+        for mb in batches:
+            idx = mb.sample_index_cpu.numpy()
+            ep = grouping["episode_of_row"][idx]
+            order = np.argsort(ep, kind="stable")
+            idx, ep = idx[order], ep[order]
+            bounds = np.flatnonzero(np.diff(ep)) + 1
+            starts = np.concatenate(([0], bounds))
+            ends = np.concatenate((bounds, [len(ep)]))
+            rows = []
+            for s0, s1 in zip(starts.tolist(), ends.tolist()):
+                e = int(ep[s0])
+                for r in range(s0, s1, spt):
+                    rows.append((r * H, (min(s1, r + spt) - r) * H, e, 0))
+            sorted_idx.append(idx)
+            tiles.append(np.asarray(rows, dtype=np.int32).reshape(-1, 4))
+            n_tiles.append(len(rows))
+        idx_dev = torch.from_numpy(np.concatenate(sorted_idx)).to(self.device)
+        tiles_dev = torch.from_numpy(np.concatenate(tiles, axis=0)).to(self.device)
+        i0 = t0 = 0
+        for mb, idx, nt in zip(batches, sorted_idx, n_tiles):
+            mb.sample_index = idx_dev[i0:i0 + len(idx)]
+            mb.sample_index_cpu = torch.from_numpy(idx)
+            mb.groups = {"tiles": tiles_dev[t0:t0 + nt], "n_tiles": nt, "table_pe": grouping["table_pe"],
+                         "n_episodes": grouping["n_episodes"]}
+            i0 += len(idx)
+            t0 += nt
 
     def _train_mini_batch(self, samples, learning_rate, clip_range, beta):
         """One optimiser step on one minibatch (trainer.py:258-323).  ``samples`` is either a ``MiniBatch``
@@ -837,8 +897,15 @@ class PPOTrainer:
         else:
             feat_g, feat = None, obs.reshape(n, -1)
         logits, value, out_mem = st["out"]
+        groups = None
+        if isinstance(samples, MiniBatch) and samples.groups is not None:
+            if st.get("ranges") is None:
+                st["ranges"] = torch.empty((n, 4), dtype=torch.int32, device=self.device)
+            native.attention_ranges(mask, win_index, ep_index, sidx, n, self.memory_length, st["ranges"])
+            gr = samples.groups
+            groups = native.attn_groups(gr["table_pe"], gr["n_episodes"], gr["tiles"], gr["n_tiles"], st["ranges"])
         native.model_forward(model._cfg, model.flat_parameters(), feat, table, table.shape[1], ep_index, win_index, mask,
-                             pe_index, sidx, model._pe_table(), n, st["ws"], logits, value, out_mem)
+                             pe_index, sidx, model._pe_table(), n, st["ws"], logits, value, out_mem, groups=groups)
         if advstats is None:
             advstats = st["advstats"]
             native.adv_stats(adv, sidx, n, advstats)
@@ -852,7 +919,7 @@ class PPOTrainer:
                         st["loss_scratch"])
         native.model_backward(model._cfg, model.flat_parameters(), model.flat_grads(), feat, table, table.shape[1], ep_index,
                               win_index, mask, pe_index, sidx, model._pe_table(), n, st["ws"], out_mem, st["dlogits"],
-                              st["dvalue"], st["dfeat"])
+                              st["dvalue"], st["dfeat"], groups=groups)
         if tc_enc:
             model.encode_backward(n, obs.shape[-2], obs.shape[-1], st["dfeat"])
         elif feat_g is not None:

@@ -33,7 +33,13 @@ class ParamEntry(C.Structure):
                 ("group", C.c_int32)]
 
 
+class AttnGroups(C.Structure):
+    _fields_ = [("table_pe", C.c_void_p), ("n_episodes", C.c_int32), ("tiles", C.c_void_p), ("n_tiles", C.c_int32),
+                ("ranges", C.c_void_p)]
+
+
 CFGP = C.POINTER(ModelConfig)
+GRPP = C.POINTER(AttnGroups)
 
 # name -> (restype, argtypes); this is the full exported surface of include/trxl_ppo.h
 SIGNATURES = {
@@ -57,6 +63,11 @@ SIGNATURES = {
     "trxl_fused_forward_supported": (i32, [CFGP]),
     "trxl_model_forward": (i32, [CFGP, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
     "trxl_model_backward": (i32, [CFGP, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]),
+    "trxl_model_forward_grouped": (i32, [CFGP, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, GRPP, vp]),
+    "trxl_model_backward_grouped": (i32, [CFGP, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, GRPP, vp]),
+    "trxl_grouped_attention_supported": (i32, [CFGP]),
+    "trxl_table_add_pe": (i32, [vp, vp, vp, i64, i32, i32, i32, vp]),
+    "trxl_attention_ranges": (i32, [vp, vp, vp, vp, i32, i32, vp, vp]),
     "trxl_conv_encoder_workspace_floats": (i64, [CFGP, i32, i32, i32]),
     "trxl_conv_encoder_forward": (i32, [CFGP, vp, vp, i32, i32, i32, vp, vp, vp]),
     "trxl_conv_train_supported": (i32, [CFGP, i32, i32]),
@@ -238,17 +249,50 @@ def workspace_floats(cfg, n):
     return int(v)
 
 
+def attn_groups(table_pe, n_episodes, tiles, n_tiles, ranges):
+    """trxl_attn_groups for the episode-grouped tensor-core attention (device tensors; the struct only holds pointers, keep the
+    tensors alive while it is in use)."""
+    g = AttnGroups()
+    g.table_pe, g.n_episodes, g.tiles, g.n_tiles, g.ranges = _p(table_pe), int(n_episodes), _p(tiles), int(n_tiles), _p(ranges)
+    return g
+
+
+def grouped_attention_supported(cfg):
+    return bool(load().trxl_grouped_attention_supported(C.byref(cfg)))
+
+
+def table_add_pe(table, pe_table, out, n_episodes):
+    _, m, b, d = table.shape
+    _check(load().trxl_table_add_pe(_p(table), _p(pe_table), _p(out), int(n_episodes), m, b, d, _stream()), "trxl_table_add_pe")
+
+
+def attention_ranges(mask, win_index, ep_index, sample_index, n, L, ranges):
+    _check(load().trxl_attention_ranges(_p(mask), _p(win_index), _p(ep_index), _p(sample_index), int(n), int(L), _p(ranges),
+                                        _stream()), "trxl_attention_ranges")
+
+
 def model_forward(cfg, params, feat, table, slots, ep_index, win_index, mask, pe_index, sample_index, pe_table, n, ws,
-                  logits, value, out_mem):
+                  logits, value, out_mem, groups=None):
     lib = load()
+    if groups is not None:
+        _check(lib.trxl_model_forward_grouped(C.byref(cfg), _p(params), _p(feat), _p(table), int(slots), _p(ep_index), _p(win_index),
+                                              _p(mask), _p(pe_index), _p(sample_index), _p(pe_table), int(n), _p(ws), _p(logits),
+                                              _p(value), _p(out_mem), C.byref(groups), _stream()), "trxl_model_forward_grouped")
+        return
     _check(lib.trxl_model_forward(C.byref(cfg), _p(params), _p(feat), _p(table), int(slots), _p(ep_index), _p(win_index),
                                   _p(mask), _p(pe_index), _p(sample_index), _p(pe_table), int(n), _p(ws), _p(logits),
                                   _p(value), _p(out_mem), _stream()), "trxl_model_forward")
 
 
 def model_backward(cfg, params, grads, feat, table, slots, ep_index, win_index, mask, pe_index, sample_index, pe_table, n, ws,
-                   out_mem, dlogits, dvalue, dfeat):
+                   out_mem, dlogits, dvalue, dfeat, groups=None):
     lib = load()
+    if groups is not None:
+        _check(lib.trxl_model_backward_grouped(C.byref(cfg), _p(params), _p(grads), _p(feat), _p(table), int(slots), _p(ep_index),
+                                               _p(win_index), _p(mask), _p(pe_index), _p(sample_index), _p(pe_table), int(n), _p(ws),
+                                               _p(out_mem), _p(dlogits), _p(dvalue), _p(dfeat), C.byref(groups), _stream()),
+               "trxl_model_backward_grouped")
+        return
     _check(lib.trxl_model_backward(C.byref(cfg), _p(params), _p(grads), _p(feat), _p(table), int(slots), _p(ep_index),
                                    _p(win_index), _p(mask), _p(pe_index), _p(sample_index), _p(pe_table), int(n), _p(ws),
                                    _p(out_mem), _p(dlogits), _p(dvalue), _p(dfeat), _stream()), "trxl_model_backward")

@@ -222,6 +222,36 @@ int trxl_clip_adamw_step(float* params, float* grads, float* exp_avg, float* exp
                          const int64_t* chunks, int nchunks, int ngroups, double max_grad_norm, double lr, double beta1,
                          double beta2, double eps, double weight_decay, int64_t step, float* partial, float* norms, void* stream);
 
+/* ---- episode-grouped attention on the tensor cores ------------------------------------------------------------------
+ * transformer.py:59,73: for a minibatch sorted by episode, the energies / context contractions of all samples of one
+ * episode are dense GEMMs against that episode's memory rows (fetched once per 128-row tile by TMA from the (E, M, B, D)
+ * table) and run as 3xTF32 tcgen05 GEMMs; the per-row window softmax sits between them.  Applies to post-/no-LayerNorm blocks
+ * with relative or no positional encoding; other configurations ignore the grouping and use the per-sample kernel. */
+typedef struct trxl_attn_groups {
+    const float* table_pe;     /* (E, M, B, D) table + positional rows (trxl_table_add_pe); the table itself if no PE        */
+    int32_t n_episodes;        /* E                                                                                           */
+    const int32_t* tiles;      /* (n_tiles, 4) {first (sample, head) row, rows, episode, 0}; rows of a tile share the episode, */
+    int32_t n_tiles;           /*   a tile has at most 128 rows and starts at a multiple of num_heads                         */
+    const int32_t* ranges;     /* (N, 4) from trxl_attention_ranges                                                           */
+} trxl_attn_groups;
+int trxl_grouped_attention_supported(const trxl_model_config* cfg);
+/* out[e, m, b, :] = table[e, m, b, :] + pe_table[m, :]  (once per update: the table is frozen during the optimisation epochs) */
+int trxl_table_add_pe(const float* table, const float* pe_table, float* out, int64_t E, int M, int B, int D, void* stream);
+/* ranges[n] = {first visible slot, visible slots, fully-masked flag, episode} of sample n (visible slots are contiguous:
+ * trainer.py:78-90 builds masks as lower-triangular rows and windows as consecutive slots) */
+int trxl_attention_ranges(const uint8_t* mask, const int64_t* win_index, const int64_t* ep_index, const int64_t* sample_index,
+                          int N, int L, int32_t* ranges4, void* stream);
+/* trxl_model_forward / trxl_model_backward with the grouping (samples must be ordered so that every tile's rows are contiguous) */
+int trxl_model_forward_grouped(const trxl_model_config* cfg, const float* params, const float* feat, const float* table, int64_t slots,
+                               const int64_t* ep_index, const int64_t* win_index, const uint8_t* mask, const int64_t* pe_index,
+                               const int64_t* sample_index, const float* pe_table, int N, float* workspace, float* logits,
+                               float* value, float* out_mem, const trxl_attn_groups* groups, void* stream);
+int trxl_model_backward_grouped(const trxl_model_config* cfg, const float* params, float* grads, const float* feat, const float* table,
+                                int64_t slots, const int64_t* ep_index, const int64_t* win_index, const uint8_t* mask,
+                                const int64_t* pe_index, const int64_t* sample_index, const float* pe_table, int N, float* workspace,
+                                const float* out_mem, const float* dlogits, const float* dvalue, float* dfeat,
+                                const trxl_attn_groups* groups, void* stream);
+
 /* ---- multi-GPU exchange (SURVEY.md §8b "trxl_allreduce_grads", §8e) -------------------------------
  * The reference is single-process; data-parallel sharding over workers (trainer.py:145-323 per rank) needs ONE
  * exchange per optimiser step: the in-place sum of the flat fp32 gradient arena (+ the 6 loss statistics appended to

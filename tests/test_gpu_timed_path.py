@@ -234,10 +234,16 @@ def c3_minibatch_errors(verbose=False, safe=True, tau=5e-5):
     P64 = {k: (v.double() if v.dtype == torch.float32 else v.clone()) for k, v in P32.items()}
     ocfg = dict(cfg, max_episode_steps=e["max_episode_steps"], action_space_shape=(e["n_actions"],))
     if safe:
-        mb = MiniBatch(tr.buffer, _safe_sample_index(tr, ocfg, P32, tr.buffer.mini_batch_size, tau))
+        idx = _safe_sample_index(tr, ocfg, P32, tr.buffer.mini_batch_size, tau)
+        mb = MiniBatch(tr.buffer, idx, idx.cpu())
     else:
         torch.manual_seed(12)
         mb = next(iter(tr.buffer.mini_batch_generator()))
+    # as _train_epochs does: sort by episode and build the tile table of the episode-grouped tensor-core attention
+    grouping = tr._begin_grouped_attention()
+    assert grouping is not None, "c3 (post-LN, relative PE) must take the grouped tensor-core attention path"
+    tr._group_epoch([mb], grouping)
+    assert mb.groups is not None and mb.groups["n_tiles"] >= grouping["n_episodes"] // 4
     n = mb.sample_index.shape[0]
     assert n == 2048 and tuple(tr.buffer.samples_flat["obs"].shape[1:]) == (3, 84, 84)
     mb_cpu = {k: mb[k].detach().cpu() for k in ("actions", "values", "log_probs", "advantages", "obs", "memory_mask",
@@ -285,6 +291,38 @@ def test_full_c3_minibatch_step_vs_oracle(tmp_path, monkeypatch):
     for name, (scale, e32, e64, ref_noise, pfrac, pmax) in errs.items():
         assert e32 <= 2e-4 * scale, (name, e32 / scale, e64 / scale, ref_noise / scale)
         assert pfrac <= 5e-4 and pmax <= 4 * 3e-4, (name, pfrac, pmax)
+
+
+@pytest.mark.parametrize("heads,gtrxl,pe", [(4, False, "relative"), (2, True, "relative"), (8, False, "")])
+def test_grouped_tensor_core_attention_matches_per_sample_kernel(heads, gtrxl, pe, tmp_path, monkeypatch):
+    """The episode-grouped TMA + tcgen05 attention (attention_tc.cu) against the per-sample streaming kernel (attention.cu) on
+    the same rollout data: episodes of different lengths (several tiles per episode, partial tiles), step-0 rows that attend
+    uniformly, windows that slide.  Same minibatches, same weights: statistics, gradients and parameters after two epochs
+    agree to fp32 rounding (the two paths only differ in summation order)."""
+    import trainer as trainer_mod
+    monkeypatch.chdir(tmp_path)
+    cfg = _cfg(n_workers=6, worker_steps=96, n_mini_batch=2, epochs=2,
+               environment={"obs_shape": [7], "max_episode_steps": 40, "min_episode_steps": 1},
+               transformer={"num_heads": heads, "embed_dim": 64, "memory_length": 16, "num_blocks": 3, "gtrxl": gtrxl,
+                            "positional_encoding": pe})
+    results = []
+    for grouped in ("1", "0"):
+        monkeypatch.setenv("TRXL_GROUPED_ATTENTION", grouped)
+        torch.manual_seed(5)
+        tr = trainer_mod.PPOTrainer(cfg, run_id="ga", device=torch.device(DEV), workers=_synthetic_workers(cfg), summary_writer=False)
+        torch.manual_seed(6)
+        tr._sample_training_data()
+        tr.buffer.prepare_batch_dict()
+        assert (tr._begin_grouped_attention() is not None) == (grouped == "1")
+        torch.manual_seed(7)
+        stats, _ = tr._train_epochs(3e-4, 0.2, 1e-3)
+        results.append((np.array(stats, dtype=np.float64), tr.model.flat_grads().detach().cpu().clone(),
+                        tr.model.flat_parameters().detach().cpu().clone()))
+        tr.close(exit_process=False)
+    (s1, g1, p1), (s0, g0, p0) = results
+    np.testing.assert_allclose(s1, s0, rtol=2e-4, atol=2e-6)
+    assert float((g1 - g0).abs().max()) <= 2e-4 * float(g0.abs().max())
+    assert float((p1 - p0).abs().max()) <= 4 * 3e-4 and float(((p1 - p0).abs() > 2e-5).float().mean()) <= 2e-3
 
 
 # ------------------------------------------------------------------------------------------------ f3: checkpoint / enjoy
