@@ -85,16 +85,20 @@ def main():
         stats = torch.zeros(6, device="cuda:0")
         norms = torch.zeros(tr.model._n_groups + 2, device="cuda:0")
         mbs = [next(gen) for _ in range(args.minibatches + 1)]
+        grouping = tr._begin_grouped_attention()
+        if grouping is not None:
+            tr._group_epoch(mbs, grouping)
         tr._ppo_step(mbs[0], 3e-4, 0.1, 1e-3, stats, norms)         # warm this exact shape
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
-        ctx = tr._rollout_ctx()
+        tr._rollout_ctx()
+        tr._prepare_group(tr._whole)
         with torch.no_grad():
             feed = tr.device_feed
             step = torch.zeros(tr.num_workers, dtype=torch.long, device="cuda:0") + 100
             ep = torch.arange(tr.num_workers, device="cuda:0")
             for t in range(args.rollout_steps):
-                tr._device_step(t, feed.obs(t), step, ep, ctx)
+                tr._device_step(tr._whole, t, (feed.obs(t), step, ep, False))
         for mb in mbs[1:]:
             tr._ppo_step(mb, 3e-4, 0.1, 1e-3, stats, norms)
         torch.cuda.synchronize()
