@@ -37,8 +37,12 @@ for _p in (ROOT, PKG):
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-METRIC = "env-steps/sec (whole box) Minigrid 3x84x84 mem_len=128"
+METRIC = "env-steps/sec (whole box) Minigrid 3x84x84 mem_len=128"       # BASELINE.json's metric (quoted on c3 = configs[2])
 UNIT = "env-steps/s"
+
+
+def metric_name(name):
+    return METRIC if name.startswith("c3_") else "env-steps/sec (whole box) " + name
 
 
 def load_workload(name):
@@ -46,15 +50,18 @@ def load_workload(name):
     return YamlParser(os.path.join(PKG, "configs", name + ".yaml")).get_config()
 
 
-def workload_desc(cfg, name, n_gpus):
+def workload_desc(cfg, name, n_gpus, scaling="weak"):
     t = cfg["transformer"]
     return {"workload": name, "obs_shape": cfg["environment"]["obs_shape"], "n_workers_per_gpu": cfg["n_workers"],
+            "n_workers_total": cfg["n_workers"] * n_gpus, "scaling_mode": scaling,
             "worker_steps": cfg["worker_steps"], "memory_length": t["memory_length"], "embed_dim": t["embed_dim"],
             "num_heads": t["num_heads"], "num_blocks": t["num_blocks"], "epochs": cfg["epochs"],
             "n_mini_batch": cfg["n_mini_batch"], "layer_norm": t["layer_norm"], "positional_encoding": t["positional_encoding"],
             "global_env_steps_per_update": cfg["n_workers"] * cfg["worker_steps"] * n_gpus,
-            "parallelism": "dp%d (workers sharded, 1 flat-grad all-reduce / optimiser step)" % n_gpus,
-            "l2_note": "per-step inputs (1.4 GB obs buffer + 168 MB memory table + 173 MB minibatch obs) exceed the 126 MB L2"}
+            "parallelism": "dp%d (workers sharded, 1 flat-grad all-reduce / optimiser step + 1 advantage-statistics all-reduce / epoch)" % n_gpus,
+            "l2_note": "per-step inputs (rollout obs buffer %.2f GB + minibatch obs %.0f MB + episode table) exceed the 126 MB L2"
+                       % (cfg["n_workers"] * cfg["worker_steps"] * float(np.prod(cfg["environment"]["obs_shape"])) * 4 / 1e9,
+                          cfg["n_workers"] * cfg["worker_steps"] / cfg["n_mini_batch"] * float(np.prod(cfg["environment"]["obs_shape"])) * 4 / 1e6)}
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -151,6 +158,11 @@ def cpu_reference_sample(cfg, rollout_steps=8, threads=None, seed=0, mb_sample=5
     n_opt = cfg["epochs"] * cfg["n_mini_batch"]
     update_s = T * t_roll + n_opt * t_mb
     detail = {"rollout_step_s": t_roll, "minibatch_step_s": t_mb, "optimiser_steps_per_update": n_opt,
+              "extrapolation": {"rollout_steps_timed": rollout_steps, "rollout_steps_per_update": T,
+                                "minibatch_samples_timed": mb_size, "minibatch_samples": mb_full,
+                                "optimiser_steps_timed": 1, "optimiser_steps_per_update": n_opt,
+                                "cpu_seconds_measured": rollout_steps * t_roll + t_best, "update_seconds_extrapolated": update_s,
+                                "factor": update_s / max(1e-9, rollout_steps * t_roll + t_best)},
               "sample": "%d rollout steps (W=%d, in-process synthetic envs) + optimiser step on %d of the %d minibatch samples "
                         "(best of %d, scaled x%.0f) timed on %d threads; update = %d*rollout_step + %d*minibatch_step"
                         % (rollout_steps, W, mb_size, mb_full, reps, mb_full / mb_size, threads, T, n_opt)}
@@ -163,24 +175,43 @@ def run_reference(args, cfg, name):
     if rank != 0:
         return
     vals, detail, threads = [], None, None
-    many = args.steps + args.warmup > 4
+    mb_full = cfg["n_workers"] * cfg["worker_steps"] // cfg["n_mini_batch"]
+    # Every timed step = 8 rollout steps over all workers + ONE FULL-SIZE optimiser step (when the oracle can hold it: the
+    # reference materialises (mb, M, B, D) + (mb, L, B, D)), extrapolated to an update; warm-up steps use a quarter-size batch.
+    # A long run (the driver's --steps 20) bounds the total CPU time by timing the full-size step on every 4th step.
+    window_gb = mb_full * (cfg["environment"]["max_episode_steps"] + cfg["transformer"]["memory_length"]) * \
+        cfg["transformer"]["num_blocks"] * cfg["transformer"]["embed_dim"] * 4 / 1e9
+    full_ok = window_gb * 3 < 0.5 * _host_mem_gb()
     for i in range(args.warmup + args.steps):
+        timed = i >= args.warmup
+        full = timed and full_ok and (args.steps <= 6 or (i - args.warmup) % 4 == 0)
         # the thread-count probe runs once (first step); later steps reuse its choice so K steps stay within minutes
-        v, detail = cpu_reference_sample(cfg, rollout_steps=4 if many else 8, seed=i, threads=threads,
-                                         mb_sample=256 if many else 512, reps=1 if many else 2)
+        v, detail = cpu_reference_sample(cfg, rollout_steps=8 if timed else 4, seed=i, threads=threads,
+                                         mb_sample=mb_full if full else max(64, mb_full // 4), reps=1)
         threads = detail["threads"]
-        if i >= args.warmup:
+        if timed:
             vals.append(v)
     value = float(np.mean(vals))
     cores = detail["threads"]
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": metric_name(name), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * cfg["n_workers"] * cfg["worker_steps"] / value,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_desc(cfg, name, 1),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": detail["sample"],
-                             "rollout_step_s": detail["rollout_step_s"], "minibatch_step_s": detail["minibatch_step_s"]},
+                             "rollout_step_s": detail["rollout_step_s"], "minibatch_step_s": detail["minibatch_step_s"],
+                             "extrapolation": detail["extrapolation"]},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def _host_mem_gb():
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                return float(ln.split()[1]) / 1e6
+    except OSError:
+        pass
+    return 16.0
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -201,6 +232,10 @@ def run_b200(args, cfg, name):
     dp = parallel.DataParallelContext(device)
     rank, world = dp.rank, dp.world_size
     env_cfg = cfg["environment"]
+    if args.scaling == "strong":                 # the configuration's workers are partitioned over the ranks
+        if cfg["n_workers"] % world:
+            raise SystemExit("--scaling strong: n_workers=%d is not divisible by %d ranks" % (cfg["n_workers"], world))
+        cfg = dict(cfg, n_workers=cfg["n_workers"] // world)
     W, T = cfg["n_workers"], cfg["worker_steps"]
     torch.manual_seed(1234 + rank)
     os.chdir(os.environ.get("TMPDIR", "/tmp"))
@@ -232,8 +267,11 @@ def run_b200(args, cfg, name):
         e2e = {"value": world * W * T * n_e2e / float(dt), "unit": UNIT,
                "h2d_bytes_per_step": T * (W * obs_bytes + 2 * W * 8), "d2h_bytes_per_step": T * W * 8 + 40 * 4 * 32,
                "updates_timed": n_e2e,
-               "env_transport": ("1 process per env; observations through a shared pinned slab, actions/acks through shared-memory "
-                                 "stepping (worker.py)" if tr._control is not None else "1 process per env, pipes (worker.py)"),
+               "env_transport": ("1 process per env; observations written into a shared pinned slab that one kernel per step reads in "
+                                 "place over PCIe, actions written by the sampling kernel straight into pinned host memory, "
+                                 "actions/acks through shared-memory stepping (worker.py); %d worker groups overlap env stepping "
+                                 "with the other group's forward" % len(tr._groups)
+                                 if tr._control is not None else "1 process per env, pipes (worker.py)"),
                "env_wait_s_per_update": tr.timers["env"] / n_e2e, "rollout_s_per_update": tr.timers["rollout"] / n_e2e,
                "train_s_per_update": tr.timers["train"] / n_e2e}
         tr.close(exit_process=False)
@@ -272,12 +310,11 @@ def run_b200(args, cfg, name):
     dp.max_(ms)
     ms = float(ms)
     launches = native.launch_count() - launches0
-    native.profile_enable(False) if False else None
     clock_info = clocks.stop() if rank == 0 else None
     mb = W * T // cfg["n_mini_batch"]
     t = cfg["transformer"]
-    fwd_ms, fwd_n, fwd_samples = native.profile_read(0, mb)
-    bwd_ms, bwd_n, bwd_samples = native.profile_read(1, mb)
+    prof = {k: native.profile_read(k, mb) for k in range(4)}
+    tiles = {k: native.profile_aux(k, mb) for k in (2, 3)}
     native.profile_enable(False)
     if rank != 0:
         return
@@ -286,28 +323,21 @@ def run_b200(args, cfg, name):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except (OSError, ValueError):
         pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    bytes_per_launch = mb * 4.0 * t["memory_length"] * t["embed_dim"]
-    achieved = bytes_per_launch / (fwd_ms / max(1, fwd_n) * 1e-3) / 1e9 if fwd_n else None
-    roofline = {"kernel": "window_attn_fwd_kernel (training launches, N=%d samples x 1 block each)" % mb, "bound": "hbm",
-                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": fwd_ms / max(1, fwd_n), "launches_timed": fwd_n,
-                "traffic": ncu_traffic_bytes("window_attn_fwd_kernel"), "traffic_source": "profiles/r1_ncu_attn.txt (ncu --set full, dram read + write per launch)",
-                "bwd_kernel": {"avg_launch_ms": bwd_ms / max(1, bwd_n), "launches_timed": bwd_n,
-                               "achieved": (bytes_per_launch / (bwd_ms / max(1, bwd_n) * 1e-3) / 1e9) if bwd_n else None},
-                "share_of_step": (fwd_ms + bwd_ms) / ms if ms else None}
+    roofline = attention_roofline(cfg, mb, prof, tiles, peaks, ms)
     value = world * W * T * args.steps / (ms * 1e-3)
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_desc(cfg, name, world), "clocks": clock_info, "gpu_launches": launches,
+    line = {"metric": metric_name(name), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_desc(cfg, name, world, args.scaling), "clocks": clock_info, "gpu_launches": launches,
             "roofline": roofline, "e2e": e2e,
             "breakdown_s_per_update": {"rollout": tr.timers["rollout"] / args.steps, "train": tr.timers["train"] / args.steps},
             "last_stats": [float(x) for x in np.mean(np.array(stats, dtype=np.float64), axis=0)]}
     if world == 1 and not args.no_cpu_baseline:
-        v, detail = cpu_reference_sample(cfg, rollout_steps=8)
+        mb_full = W * T // cfg["n_mini_batch"]
+        window_gb = mb_full * (env_cfg["max_episode_steps"] + t["memory_length"]) * t["num_blocks"] * t["embed_dim"] * 4 / 1e9
+        full_ok = window_gb * 3 < 0.5 * _host_mem_gb()
+        v, detail = cpu_reference_sample(cfg, rollout_steps=8, mb_sample=mb_full if full_ok else max(64, mb_full // 8), reps=1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": detail["threads"], "host_cores": os.cpu_count(),
-                                "kind": "port", "sample": detail["sample"],
+                                "kind": "port", "sample": detail["sample"], "extrapolation": detail["extrapolation"],
                                 "rollout_step_s": detail["rollout_step_s"], "minibatch_step_s": detail["minibatch_step_s"]}
     print(json.dumps(line))
 
@@ -317,7 +347,7 @@ def _s(schedule):
             "power": schedule["power"]}
 
 
-def ncu_traffic_bytes(kernel, profile=os.path.join(ROOT, "profiles", "r1_ncu_attn.txt")):
+def ncu_traffic_bytes(kernel, profile):
     """dram__bytes_read.sum + dram__bytes_write.sum of the first launch of `kernel` in a committed ncu summary (bytes), or None."""
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     try:
@@ -338,13 +368,70 @@ def ncu_traffic_bytes(kernel, profile=os.path.join(ROOT, "profiles", "r1_ncu_att
     return total if found == 2 else None
 
 
+def attention_roofline(cfg, mb, prof, tiles, peaks, step_ms_total):
+    """`roofline` object for the window attention of the training minibatches (the kernel BASELINE.json's north_star grades),
+    timed with CUDA events on its launch stream inside the timed region.
+
+    Episode-grouped tensor-core path (post-/no-LN, relative/no PE -- c2, c3, c4): one "launch" = the forward of one block =
+    grouped GEMM S = QK.Xpe^T, window softmax, grouped GEMM ctx = P.Xpe.  bound = tensor.  `achieved` counts the EXECUTED
+    tensor-core work (3 TF32 passes over tiles x 128 x M x D MACs per GEMM, padding included), the peak is the measured dense
+    bf16 rate halved (TF32 issues at half the bf16 rate).  `reference_equivalent` is SURVEY.md §8(d)'s algorithmic figure for
+    the same launch, N (4 L D^2 + 4 L D + 4 D^2) FLOP: the work the reference's formulation would need, most of which the
+    query-side fold and the per-episode grouping eliminate -- reported, not claimed as utilisation.
+    Per-sample streaming path (pre-LN or learned PE -- c1, c5): bound = hbm on the 4 L D algorithmic bytes per (sample, block)."""
+    t = cfg["transformer"]
+    L, D, H, M = t["memory_length"], t["embed_dim"], t["num_heads"], cfg["environment"]["max_episode_steps"]
+    ref_flops = mb * (4.0 * L * D * D + 4.0 * L * D + 4.0 * D * D)
+    bf16_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    src = "MEASURED_PEAKS.json (measured)" if peaks else "fallback (B200_PROFILING.md)"
+    fwd_ms, fwd_n, _ = prof[2]
+    if fwd_n:                                   # grouped tensor-core path
+        bwd_ms, bwd_n, _ = prof[3]
+        avg = fwd_ms / fwd_n
+        exec_flops = tiles[2] / fwd_n * 128.0 * M * D * 2.0 * 2.0 * 3.0
+        achieved = exec_flops / (avg * 1e-3) / 1e12
+        peak = bf16_peak / 2.0
+        return {"kernel": "episode-grouped attention forward of one block (N=%d): tma_gemm_kernel<128> S=QK.X^T, attn_softmax_kernel, "
+                          "tma_gemm_kernel<128> ctx=P.X" % mb,
+                "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "peak_source": src + ": sustained dense bf16 / 2 (TF32 rate)",
+                "executed_flops_per_launch": exec_flops, "tiles_per_launch": tiles[2] / fwd_n, "avg_launch_ms": avg,
+                "launches_timed": fwd_n,
+                "reference_equivalent": {"flops_per_launch": ref_flops, "tflops": ref_flops / (avg * 1e-3) / 1e12,
+                                         "note": "SURVEY.md 8(d) algorithmic FLOPs of the reference's formulation; eliminated work, not utilisation"},
+                "useful_flops_per_launch": mb * H * 4.0 * L * D,
+                "traffic": ncu_traffic_bytes("tma_gemm_kernel", os.path.join(ROOT, "profiles", "r2_ncu_grouped_attention.txt")),
+                "traffic_source": "profiles/r2_ncu_grouped_attention.txt (ncu --set full, dram read + write of the S GEMM launch)",
+                "bwd": {"avg_launch_ms": bwd_ms / max(1, bwd_n), "launches_timed": bwd_n,
+                        "achieved": (tiles[3] / max(1, bwd_n) * 128.0 * M * D * 12.0) / (bwd_ms / max(1, bwd_n) * 1e-3) / 1e12 if bwd_n else None},
+                "share_of_step": (fwd_ms + bwd_ms) / step_ms_total if step_ms_total else None}
+    fwd_ms, fwd_n, _ = prof[0]
+    bwd_ms, bwd_n, _ = prof[1]
+    bytes_per_launch = mb * 4.0 * L * D
+    achieved = bytes_per_launch / (fwd_ms / max(1, fwd_n) * 1e-3) / 1e9 if fwd_n else None
+    return {"kernel": "window_attn_fwd_kernel (per-sample streaming, N=%d samples x 1 block)" % mb, "bound": "hbm",
+            "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
+            "peak_source": src, "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": fwd_ms / max(1, fwd_n),
+            "launches_timed": fwd_n, "traffic": ncu_traffic_bytes("window_attn_fwd_kernel", os.path.join(ROOT, "profiles", "r1_ncu_attn.txt")),
+            "traffic_source": "profiles/r1_ncu_attn.txt",
+            "note": "issue-bound in practice (r1 ncu: DRAM 4 %, L2 26 %, issue-active 59 %); most window rows hit L2",
+            "reference_equivalent": {"flops_per_launch": ref_flops},
+            "bwd": {"avg_launch_ms": bwd_ms / max(1, bwd_n), "launches_timed": bwd_n},
+            "share_of_step": (fwd_ms + bwd_ms) / step_ms_total if step_ms_total else None}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3_minigrid_synthetic")
+    ap.add_argument("--workload", default="c3_minigrid_synthetic",
+                    help="configs/<name>.yaml: c1_poc_synthetic, c2_cartpole_synthetic, c3_minigrid_synthetic (BASELINE.json's metric), "
+                         "c4_minigrid_gtrxl_synthetic, c5_mortar_synthetic")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every GPU runs the configuration's n_workers; strong: n_workers is partitioned over the GPUs")
     ap.add_argument("--e2e-steps", type=int, default=2, help="PPO updates timed for the e2e (env-process) arm")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -26,11 +26,11 @@ long long g_trxl_launches = 0;
 
 // ---- optional launch timing of the two attention kernels (bench.py roofline) ----
 namespace {
-constexpr int PROF_KINDS = 2, PROF_CAP = 8192;
-struct ProfSlot { cudaEvent_t a, b; int n; };
+constexpr int PROF_KINDS = 4, PROF_CAP = 8192;
+struct ProfSlot { cudaEvent_t a, b; int n; long long aux; };
 bool g_prof_on = false;
-ProfSlot* g_prof[PROF_KINDS] = {nullptr, nullptr};
-int g_prof_count[PROF_KINDS] = {0, 0};
+ProfSlot* g_prof[PROF_KINDS] = {nullptr, nullptr, nullptr, nullptr};
+int g_prof_count[PROF_KINDS] = {0, 0, 0, 0};
 }  // namespace
 
 static bool stream_capturing(cudaStream_t st) {
@@ -46,7 +46,12 @@ void trxl_prof_begin(int kind, int n, cudaStream_t st) {
     }
     ProfSlot& s = g_prof[kind][g_prof_count[kind]];
     s.n = n;
+    s.aux = 0;
     cudaEventRecord(s.a, st);
+}
+void trxl_prof_aux(int kind, long long aux) {
+    if (!g_prof_on || g_prof_count[kind] >= PROF_CAP || !g_prof[kind]) return;
+    g_prof[kind][g_prof_count[kind]].aux = aux;
 }
 void trxl_prof_end(int kind, cudaStream_t st) {
     if (!g_prof_on || g_prof_count[kind] >= PROF_CAP || !g_prof[kind] || stream_capturing(st)) return;
@@ -135,7 +140,7 @@ int trxl_copy_async(const void* src, void* dst, int64_t bytes, void* stream) {
 
 int trxl_profile_enable(int on) {
     g_prof_on = on != 0;
-    if (on) { g_prof_count[0] = 0; g_prof_count[1] = 0; }
+    if (on) { for (int k = 0; k < PROF_KINDS; ++k) g_prof_count[k] = 0; }
     return TRXL_OK;
 }
 int trxl_profile_read(int kind, int min_samples, double* total_ms, int64_t* launches, int64_t* samples) {
@@ -150,6 +155,14 @@ int trxl_profile_read(int kind, int min_samples, double* total_ms, int64_t* laun
         *total_ms += ms; *launches += 1; *samples += s.n;
     }
     return TRXL_OK;
+}
+
+int64_t trxl_profile_aux(int kind, int min_samples) {
+    if (kind < 0 || kind >= PROF_KINDS) return -1;
+    long long total = 0;
+    for (int i = 0; i < g_prof_count[kind]; ++i)
+        if (g_prof[kind][i].n >= min_samples) total += g_prof[kind][i].aux;
+    return total;
 }
 
 int trxl_layout_num_entries(const trxl_model_config* cfg) {

@@ -170,11 +170,14 @@ int attn_tc_forward(const AttnTcArgs& a, const float* qk, float* P, float* ctx, 
     const int rows = a.N * a.H;
     GemmArgs g1 = grouped_args(a, qk, a.D, a.D, (int)a.slots, 1, P, ld);               // S = QK . Xpe^T     (B K-major: rows = slots)
     TRXL_CHECK_ARG(trxl_tc_gemm_eligible(g1), "attention_tc: operands not TMA-eligible");
+    trxl_prof_begin(2, a.N, st);
+    trxl_prof_aux(2, a.n_tiles);
     TRXL_PROPAGATE(trxl_tc_gemm(g1, 128, st));
     attn_softmax_kernel<<<trxl_cdiv(rows, 8), 256, 0, st>>>(P, ld, (int)a.slots, a.ranges, a.H, rows, a.scale, a.L);
     TRXL_CHECK_LAUNCH("attention_softmax");
     GemmArgs g2 = grouped_args(a, P, ld, (int)a.slots, a.D, 0, ctx, a.D);               // ctx = P . Xpe      (B MN-major: k = slot)
     TRXL_PROPAGATE(trxl_tc_gemm(g2, 128, st));
+    trxl_prof_end(2, st);
     return TRXL_OK;
 }
 
@@ -183,10 +186,13 @@ int attn_tc_backward(const AttnTcArgs& a, const float* P, const float* dctx, flo
     const long long ld = attn_tc_row_floats(a.slots);
     const int rows = a.N * a.H;
     GemmArgs g1 = grouped_args(a, dctx, a.D, a.D, (int)a.slots, 1, scratch, ld);        // dP = dctx . Xpe^T
+    trxl_prof_begin(3, a.N, st);
+    trxl_prof_aux(3, a.n_tiles);
     TRXL_PROPAGATE(trxl_tc_gemm(g1, 128, st));
     attn_dscore_kernel<<<trxl_cdiv(rows, 8), 256, 0, st>>>(scratch, P, ld, (int)a.slots, a.ranges, a.H, rows, 1.f / a.scale);
     TRXL_CHECK_LAUNCH("attention_dscore");
     GemmArgs g2 = grouped_args(a, scratch, ld, (int)a.slots, a.D, 0, dqk, a.D);         // dqk = dS . Xpe
     TRXL_PROPAGATE(trxl_tc_gemm(g2, 128, st));
+    trxl_prof_end(3, st);
     return TRXL_OK;
 }

@@ -16,6 +16,7 @@ extern long long g_trxl_launches;
 // optional per-launch timing of the attention kernels (CUDA events on the launch stream); see api.cu
 void trxl_prof_begin(int kind, int n, cudaStream_t st);
 void trxl_prof_end(int kind, cudaStream_t st);
+void trxl_prof_aux(int kind, long long aux);      // attach a count (e.g. tiles) to the slot opened by trxl_prof_begin
 
 #define TRXL_CHECK_ARG(cond, ...)                 \
     do {                                          \

@@ -49,6 +49,7 @@ SIGNATURES = {
     "trxl_tc_gemm_launches": (i64, []),
     "trxl_profile_enable": (i32, [i32]),
     "trxl_profile_read": (i32, [i32, i32, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "trxl_profile_aux": (i64, [i32, i32]),
     "trxl_graph_begin": (i32, [vp]),
     "trxl_graph_end": (i32, [vp, C.POINTER(C.c_void_p)]),
     "trxl_graph_launch": (i32, [vp, vp]),
@@ -236,6 +237,10 @@ def profile_read(kind, min_samples=0):
     _check(load().trxl_profile_read(int(kind), int(min_samples), C.byref(ms), C.byref(launches), C.byref(samples)),
            "trxl_profile_read")
     return ms.value, launches.value, samples.value
+
+
+def profile_aux(kind, min_samples=0):
+    return int(load().trxl_profile_aux(int(kind), int(min_samples)))
 
 
 def fused_forward_supported(cfg):

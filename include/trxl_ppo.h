@@ -65,6 +65,9 @@ int64_t trxl_tc_gemm_launches(void);
  * processed at least min_samples samples; synchronises on those events only. */
 int trxl_profile_enable(int on);
 int trxl_profile_read(int kind, int min_samples, double* total_ms, int64_t* launches, int64_t* samples);
+/* sum of the counts attached to the timed launches of `kind` (kinds 2 / 3 = episode-grouped attention forward / backward:
+ * number of 128-row tiles) */
+int64_t trxl_profile_aux(int kind, int min_samples);
 
 /* Capture / replay of a sequence of this library's launches as a CUDA graph (the ~45 launches of one rollout step).
  * `stream` must be a non-default stream for begin/end; only calls of this library may be issued in between. */

@@ -250,6 +250,8 @@ def test_trainer_two_updates_vs_reference(name, tmp_path, monkeypatch):
     (40, "post", "relative", True, (256, 384, 4, 3)),        # c4-like: L=256, D=384 (3 float4 per lane, 2 heads per pass)
     (24, "pre", "relative", False, (512, 512, 8, 2)),        # c5-like: L=512, D=512, 8 heads
     (20, "pre", "learned", False, (118, 384, 4, 2)),         # mortar_mayhem_grid.yaml: L=118 (not a multiple of 4)
+    (16, "post", "relative", True, (256, 384, 4, 6)),        # c4 at its full depth: GTrXL, 6 blocks (BASELINE.json configs[3])
+    (10, "pre", "relative", False, (512, 512, 4, 8)),        # c5 at its full depth: 8 blocks, L=512, D=512 (configs[4])
 ])
 def test_forward_backward_c3_dims_vs_oracle(n, ln, pe, gtrxl, dims):
     """c3 dimensions (L=128, D=256, H=4, B=4, lin_hidden K=3136 fed directly as a vector observation) at rollout and

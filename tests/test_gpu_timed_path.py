@@ -293,17 +293,20 @@ def test_full_c3_minibatch_step_vs_oracle(tmp_path, monkeypatch):
         assert pfrac <= 5e-4 and pmax <= 4 * 3e-4, (name, pfrac, pmax)
 
 
-@pytest.mark.parametrize("heads,gtrxl,pe", [(4, False, "relative"), (2, True, "relative"), (8, False, "")])
-def test_grouped_tensor_core_attention_matches_per_sample_kernel(heads, gtrxl, pe, tmp_path, monkeypatch):
+@pytest.mark.parametrize("heads,gtrxl,pe,dims", [(4, False, "relative", (64, 16, 40, 3)), (2, True, "relative", (64, 16, 40, 3)),
+                                                   (8, False, "", (64, 16, 40, 3)),
+                                                   (4, True, "relative", (384, 48, 130, 2))])      # c4-like width, M % 32 != 0
+def test_grouped_tensor_core_attention_matches_per_sample_kernel(heads, gtrxl, pe, dims, tmp_path, monkeypatch):
     """The episode-grouped TMA + tcgen05 attention (attention_tc.cu) against the per-sample streaming kernel (attention.cu) on
     the same rollout data: episodes of different lengths (several tiles per episode, partial tiles), step-0 rows that attend
     uniformly, windows that slide.  Same minibatches, same weights: statistics, gradients and parameters after two epochs
     agree to fp32 rounding (the two paths only differ in summation order)."""
     import trainer as trainer_mod
     monkeypatch.chdir(tmp_path)
+    D, L, M, B = dims
     cfg = _cfg(n_workers=6, worker_steps=96, n_mini_batch=2, epochs=2,
-               environment={"obs_shape": [7], "max_episode_steps": 40, "min_episode_steps": 1},
-               transformer={"num_heads": heads, "embed_dim": 64, "memory_length": 16, "num_blocks": 3, "gtrxl": gtrxl,
+               environment={"obs_shape": [7], "max_episode_steps": M, "min_episode_steps": 1},
+               transformer={"num_heads": heads, "embed_dim": D, "memory_length": L, "num_blocks": B, "gtrxl": gtrxl,
                             "positional_encoding": pe})
     results = []
     for grouped in ("1", "0"):
