@@ -236,12 +236,13 @@ int trxl_attention_ranges(const uint8_t* mask, const int64_t* win_index, const i
     return attn_tc_ranges(mask, (cll)win_index, (cll)ep_index, (cll)sample_index, N, L, reinterpret_cast<int4*>(ranges4), S(stream));
 }
 
-int trxl_table_add_pe(const float* table, const float* pe_table, float* out, int64_t E, int M, int B, int D, void* stream) {
-    return attn_tc_table_add_pe(table, pe_table, out, E, M, B, D, S(stream));
+int trxl_table_add_pe(const float* table, const float* pe_table, float* out, int64_t E, int M, int B, int D, int layer_norm,
+                      void* stream) {
+    return attn_tc_table_add_pe(table, pe_table, out, E, M, B, D, layer_norm, S(stream));
 }
 
 int trxl_grouped_attention_supported(const trxl_model_config* cfg) {
-    return cfg && cfg->layer_norm != TRXL_LN_PRE && cfg->pos_enc != TRXL_PE_LEARNED &&
+    return cfg && cfg->pos_enc != TRXL_PE_LEARNED &&
            attn_tc_supported(cfg->embed_dim, cfg->num_heads, cfg->max_episode_steps, cfg->num_blocks) ? 1 : 0;
 }
 

@@ -16,8 +16,10 @@
 // dqk = dS . Xpe_e -- the same two GEMM shapes.  The memory rows carry no gradient (transformer.py:248).
 //
 // Xpe = table + positional row is materialised once per update (trxl_table_add_pe): the table is frozen during the
-// optimisation epochs and the sinusoidal table has no parameters.  Learned positional tables and the pre-LayerNorm fold stay
-// on the per-sample kernel (attention.cu).
+// optimisation epochs and the sinusoidal table has no parameters.  For pre-LayerNorm models the rows are also normalised there
+// (norm_kv without its affine part, which the model folds into Wk / Wv): the kernels below then see plain rows; the energy
+// bias of the fold (qkb) is constant over a row's window, cancels in the softmax and receives no gradient.  Learned positional
+// tables (gradients flow into the rows) stay on the per-sample kernel (attention.cu).
 #include "attention_tc.cuh"
 
 #include "gemm.cuh"
@@ -122,6 +124,33 @@ __global__ void table_add_pe_kernel(const float4* __restrict__ table, const floa
     }
 }
 
+// out[e, m, b, :] = LayerNorm_noaffine(table[e, m, b, :] + pe[m, :])   (eps 1e-5, biased variance; one warp per row).
+// The pre-LayerNorm block normalises every window row with norm_kv (transformer.py:131); gamma / beta are folded into Wk / Wv by
+// the caller, and the normalisation itself depends only on the stored row, so it is done once per update here.
+__global__ void table_add_pe_ln_kernel(const float* __restrict__ table, const float* __restrict__ pe, float* __restrict__ out,
+                                       long long rows, int M, int B, int D) {
+    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const int m = (int)((r / B) % M);
+    const float* x = table + r * D;
+    const float* p = pe ? pe + (long long)m * D : nullptr;
+    float s = 0.f;
+    for (int j = lane; j < D; j += 32) s += x[j] + (p ? p[j] : 0.f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    const float mu = s / (float)D;
+    float v = 0.f;
+    for (int j = lane; j < D; j += 32) {
+        const float d = x[j] + (p ? p[j] : 0.f) - mu;
+        v = fmaf(d, d, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    const float rstd = rsqrtf(v / (float)D + 1e-5f);
+    for (int j = lane; j < D; j += 32) out[r * D + j] = (x[j] + (p ? p[j] : 0.f) - mu) * rstd;
+}
+
 GemmArgs grouped_args(const AttnTcArgs& a, const float* A, long long lda, int K, int Nn, int b_kc, float* C, long long ldc) {
     GemmArgs g;
     g.M = a.N * a.H; g.N = Nn; g.K = K;
@@ -152,10 +181,17 @@ int attn_tc_ranges(const unsigned char* mask, const long long* win_index, const 
     return TRXL_OK;
 }
 
-int attn_tc_table_add_pe(const float* table, const float* pe, float* out, long long E, int M, int B, int D, cudaStream_t st) {
-    TRXL_CHECK_ARG(table && pe && out && D % 4 == 0, "table_add_pe: bad arguments");
+int attn_tc_table_add_pe(const float* table, const float* pe, float* out, long long E, int M, int B, int D, int layer_norm,
+                         cudaStream_t st) {
+    TRXL_CHECK_ARG(table && out && D % 4 == 0 && (pe || layer_norm), "table_add_pe: bad arguments");
     const long long total4 = E * M * B * (D / 4);
     if (total4 == 0) return TRXL_OK;
+    if (layer_norm) {
+        const long long rows = E * M * B;
+        table_add_pe_ln_kernel<<<trxl_cdiv(rows, 8), 256, 0, st>>>(table, pe, out, rows, M, B, D);
+        TRXL_CHECK_LAUNCH("table_add_pe_ln");
+        return TRXL_OK;
+    }
     int blocks = trxl_cdiv(total4, 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     table_add_pe_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(table), reinterpret_cast<const float4*>(pe),

@@ -17,6 +17,7 @@ long long attn_tc_row_floats(long long slots);
 bool attn_tc_supported(int D, int H, long long slots, int B);
 int attn_tc_ranges(const unsigned char* mask, const long long* win_index, const long long* ep_index, const long long* sample_index,
                    int N, int L, int4* ranges, cudaStream_t st);
-int attn_tc_table_add_pe(const float* table, const float* pe, float* out, long long E, int M, int B, int D, cudaStream_t st);
+int attn_tc_table_add_pe(const float* table, const float* pe, float* out, long long E, int M, int B, int D, int layer_norm,
+                         cudaStream_t st);
 int attn_tc_forward(const AttnTcArgs& a, const float* qk, float* P, float* ctx, cudaStream_t st);
 int attn_tc_backward(const AttnTcArgs& a, const float* P, const float* dctx, float* scratch, float* dqk, cudaStream_t st);

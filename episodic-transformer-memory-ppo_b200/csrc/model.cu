@@ -198,7 +198,7 @@ void carve(const trxl_model_config* c, int N, float* ws, Acts& A) {
         if (post) { k.h1 = b.take(ND); k.m1 = b.take(N); k.r1 = b.take(N); k.out_pre = b.take(ND); k.m2 = b.take(N); k.r2 = b.take(N); }
         // probs: (N, H, L) for the per-sample kernel; the episode-grouped tensor-core path keeps P over all slots of the episode
         long long probs_row = L;
-        if (!pre && c->pos_enc != TRXL_PE_LEARNED && attn_tc_row_floats(c->max_episode_steps) > probs_row)
+        if (c->pos_enc != TRXL_PE_LEARNED && attn_tc_row_floats(c->max_episode_steps) > probs_row)
             probs_row = attn_tc_row_floats(c->max_episode_steps);
         k.Q = b.take(ND); k.qk = b.take(ND * H); k.probs = b.take((long long)N * H * probs_row); k.ctx = b.take(ND * H);
         k.att_o = b.take(ND); k.h1pre = b.take(ND); k.f = b.take(ND);
@@ -238,7 +238,7 @@ AttnArgs attn_args(const trxl_model_config* c, const ModelIO& io, int blk, const
 // the episode-grouped tensor-core attention applies when the caller supplied the grouping and the block needs neither the
 // pre-LayerNorm fold nor gradients into a learned positional table
 bool use_grouped_attention(const trxl_model_config* c, const ModelIO& io) {
-    return io.tiles && io.ranges && io.table_pe && io.n_tiles > 0 && c->layer_norm != TRXL_LN_PRE && c->pos_enc != TRXL_PE_LEARNED &&
+    return io.tiles && io.ranges && io.table_pe && io.n_tiles > 0 && c->pos_enc != TRXL_PE_LEARNED &&
            io.slots == c->max_episode_steps && attn_tc_supported(c->embed_dim, c->num_heads, io.slots, c->num_blocks);
 }
 
@@ -513,6 +513,8 @@ int model_backward(const trxl_model_config* c, const float* P, float* G, const M
             TRXL_PROPAGATE(ew_unfold(st, A.dWg, A.dvec, P + p.Wv, P + p.nkw, P + p.nkb, G + p.Wv, G + p.nkw, G + p.nkb, D, D, 0));
         }
         if (grouped) {
+            // (pre-LN: the energy bias qkb is constant over a row's window, so it cancels in the softmax and gets no gradient)
+            if (pre) cudaMemsetAsync(A.dqkb, 0, sizeof(float) * (size_t)N * H, st);
             TRXL_PROPAGATE(attn_tc_backward(attn_tc_args(c, io, i), a.probs, A.dctx, A.dscore, A.dqk, st));
         } else {
             AttnBwdArgs ab;

@@ -777,13 +777,14 @@ class PPOTrainer:
         if not torch.is_tensor(table) or table.dim() != 4 or table.shape[1] != self.max_episode_length:
             return None
         pe = model._pe_table()
-        if pe is None:
-            table_pe = table                                           # no positional encoding
+        pre_ln = model.transformer.config["layer_norm"] == "pre"
+        if pe is None and not pre_ln:
+            table_pe = table                                           # neither positional rows nor norm_kv: read the table itself
         else:
             if self._table_pe is None or self._table_pe.shape != self._table.shape:
                 self._table_pe = torch.empty_like(self._table)
             table_pe = self._table_pe[:table.shape[0]]
-            native.table_add_pe(table, pe, table_pe, table.shape[0])
+            native.table_add_pe(table, pe, table_pe, table.shape[0], layer_norm=pre_ln)
         episode_of_row = buf.samples_flat["memory_index"].cpu().numpy()       # (W*T,) -- one small download per update
         return {"table_pe": table_pe, "n_episodes": int(table.shape[0]), "episode_of_row": episode_of_row,
                 "rows_per_tile": 128 // self.model.transformer.num_heads * self.model.transformer.num_heads}

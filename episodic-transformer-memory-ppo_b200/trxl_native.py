@@ -67,7 +67,7 @@ SIGNATURES = {
     "trxl_model_forward_grouped": (i32, [CFGP, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, GRPP, vp]),
     "trxl_model_backward_grouped": (i32, [CFGP, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, GRPP, vp]),
     "trxl_grouped_attention_supported": (i32, [CFGP]),
-    "trxl_table_add_pe": (i32, [vp, vp, vp, i64, i32, i32, i32, vp]),
+    "trxl_table_add_pe": (i32, [vp, vp, vp, i64, i32, i32, i32, i32, vp]),
     "trxl_attention_ranges": (i32, [vp, vp, vp, vp, i32, i32, vp, vp]),
     "trxl_conv_encoder_workspace_floats": (i64, [CFGP, i32, i32, i32]),
     "trxl_conv_encoder_forward": (i32, [CFGP, vp, vp, i32, i32, i32, vp, vp, vp]),
@@ -266,9 +266,10 @@ def grouped_attention_supported(cfg):
     return bool(load().trxl_grouped_attention_supported(C.byref(cfg)))
 
 
-def table_add_pe(table, pe_table, out, n_episodes):
+def table_add_pe(table, pe_table, out, n_episodes, layer_norm=False):
     _, m, b, d = table.shape
-    _check(load().trxl_table_add_pe(_p(table), _p(pe_table), _p(out), int(n_episodes), m, b, d, _stream()), "trxl_table_add_pe")
+    _check(load().trxl_table_add_pe(_p(table), _p(pe_table), _p(out), int(n_episodes), m, b, d, int(bool(layer_norm)), _stream()),
+           "trxl_table_add_pe")
 
 
 def attention_ranges(mask, win_index, ep_index, sample_index, n, L, ranges):

@@ -228,18 +228,23 @@ int trxl_clip_adamw_step(float* params, float* grads, float* exp_avg, float* exp
 /* ---- episode-grouped attention on the tensor cores ------------------------------------------------------------------
  * transformer.py:59,73: for a minibatch sorted by episode, the energies / context contractions of all samples of one
  * episode are dense GEMMs against that episode's memory rows (fetched once per 128-row tile by TMA from the (E, M, B, D)
- * table) and run as 3xTF32 tcgen05 GEMMs; the per-row window softmax sits between them.  Applies to post-/no-LayerNorm blocks
- * with relative or no positional encoding; other configurations ignore the grouping and use the per-sample kernel. */
+ * table) and run as 3xTF32 tcgen05 GEMMs; the per-row window softmax sits between them.  Applies to relative or no positional
+ * encoding (a learned table needs gradients into the rows); other configurations ignore the grouping and use the per-sample
+ * kernel. */
 typedef struct trxl_attn_groups {
-    const float* table_pe;     /* (E, M, B, D) table + positional rows (trxl_table_add_pe); the table itself if no PE        */
+    const float* table_pe;     /* (E, M, B, D) from trxl_table_add_pe (layer_norm = 1 for pre-LN models); the table itself if   */
+                               /*   there is neither a positional table nor a pre-LayerNorm                                    */
     int32_t n_episodes;        /* E                                                                                           */
     const int32_t* tiles;      /* (n_tiles, 4) {first (sample, head) row, rows, episode, 0}; rows of a tile share the episode, */
     int32_t n_tiles;           /*   a tile has at most 128 rows and starts at a multiple of num_heads                         */
     const int32_t* ranges;     /* (N, 4) from trxl_attention_ranges                                                           */
 } trxl_attn_groups;
 int trxl_grouped_attention_supported(const trxl_model_config* cfg);
-/* out[e, m, b, :] = table[e, m, b, :] + pe_table[m, :]  (once per update: the table is frozen during the optimisation epochs) */
-int trxl_table_add_pe(const float* table, const float* pe_table, float* out, int64_t E, int M, int B, int D, void* stream);
+/* out[e, m, b, :] = table[e, m, b, :] + pe_table[m, :] (pe_table may be NULL), and with layer_norm != 0 additionally normalised
+ * per row (LayerNorm without affine, eps 1e-5: the norm_kv of a pre-LayerNorm block, transformer.py:131, whose gamma / beta the
+ * model folds into Wk / Wv).  Once per update: the table is frozen during the optimisation epochs. */
+int trxl_table_add_pe(const float* table, const float* pe_table, float* out, int64_t E, int M, int B, int D, int layer_norm,
+                      void* stream);
 /* ranges[n] = {first visible slot, visible slots, fully-masked flag, episode} of sample n (visible slots are contiguous:
  * trainer.py:78-90 builds masks as lower-triangular rows and windows as consecutive slots) */
 int trxl_attention_ranges(const uint8_t* mask, const int64_t* win_index, const int64_t* ep_index, const int64_t* sample_index,

@@ -293,10 +293,12 @@ def test_full_c3_minibatch_step_vs_oracle(tmp_path, monkeypatch):
         assert pfrac <= 5e-4 and pmax <= 4 * 3e-4, (name, pfrac, pmax)
 
 
-@pytest.mark.parametrize("heads,gtrxl,pe,dims", [(4, False, "relative", (64, 16, 40, 3)), (2, True, "relative", (64, 16, 40, 3)),
-                                                   (8, False, "", (64, 16, 40, 3)),
-                                                   (4, True, "relative", (384, 48, 130, 2))])      # c4-like width, M % 32 != 0
-def test_grouped_tensor_core_attention_matches_per_sample_kernel(heads, gtrxl, pe, dims, tmp_path, monkeypatch):
+@pytest.mark.parametrize("heads,gtrxl,pe,ln,dims", [(4, False, "relative", "post", (64, 16, 40, 3)), (2, True, "relative", "post", (64, 16, 40, 3)),
+                                                      (8, False, "", "post", (64, 16, 40, 3)),
+                                                      (4, True, "relative", "post", (384, 48, 130, 2)),      # c4-like width, M % 32 != 0
+                                                      (4, False, "relative", "pre", (64, 16, 40, 3)),       # pre-LN: norm_kv folded into the table
+                                                      (1, True, "", "pre", (64, 16, 40, 2))])               # c1-like: one head, pre-LN, no PE
+def test_grouped_tensor_core_attention_matches_per_sample_kernel(heads, gtrxl, pe, ln, dims, tmp_path, monkeypatch):
     """The episode-grouped TMA + tcgen05 attention (attention_tc.cu) against the per-sample streaming kernel (attention.cu) on
     the same rollout data: episodes of different lengths (several tiles per episode, partial tiles), step-0 rows that attend
     uniformly, windows that slide.  Same minibatches, same weights: statistics, gradients and parameters after two epochs
@@ -307,7 +309,7 @@ def test_grouped_tensor_core_attention_matches_per_sample_kernel(heads, gtrxl, p
     cfg = _cfg(n_workers=6, worker_steps=96, n_mini_batch=2, epochs=2,
                environment={"obs_shape": [7], "max_episode_steps": M, "min_episode_steps": 1},
                transformer={"num_heads": heads, "embed_dim": D, "memory_length": L, "num_blocks": B, "gtrxl": gtrxl,
-                            "positional_encoding": pe})
+                            "positional_encoding": pe, "layer_norm": ln})
     results = []
     for grouped in ("1", "0"):
         monkeypatch.setenv("TRXL_GROUPED_ATTENTION", grouped)
