@@ -30,7 +30,7 @@ from model import ActorCriticModel
 from optim_native import FusedClipAdamW
 from parallel import DataParallelContext
 from utils import create_env, polynomial_decay, process_episode_info
-from worker import Worker, make_control, physical_cpus
+from worker import FUTEX_WORD_STRIDE, Worker, _Futex, make_control, physical_cpus
 
 
 def save_model_file(model, config, path):
@@ -143,6 +143,11 @@ class PPOTrainer:
         # (pass workers=[] together with trainer.device_feed = SyntheticDeviceFeed(...) to run without env processes)
         self._obs_slab = None
         self._control = None          # shared-memory stepping arrays (own workers only)
+        n_groups = int(os.environ.get("TRXL_ROLLOUT_GROUPS", "2" if (workers is None and self.num_workers >= 8 and
+                                                                      os.environ.get("TRXL_PIPE_STEPPING", "0") != "1") else "1"))
+        n_groups = max(1, min(n_groups, self.num_workers, 64))
+        self._group_bounds = [round(i * self.num_workers / n_groups) for i in range(n_groups + 1)]
+        group_of = [max(g for g in range(n_groups) if self._group_bounds[g] <= w) for w in range(self.num_workers)]
         if workers is None:
             self._obs_slab = torch.zeros((self.num_workers,) + self.obs_shape, dtype=torch.float32).share_memory_()
             procs = self.dp.world_size * (self.num_workers + 1)
@@ -162,7 +167,8 @@ class PPOTrainer:
                 cores = []
             first = 1 + self.dp.rank * (self.num_workers + 1)          # core `first - 1` is left to this rank's main thread
             workers = [Worker(self._env_config(w), self._obs_slab, w, self._control,
-                              cpu=cores[(first + w) % len(cores)] if cores else None) for w in range(self.num_workers)]
+                              cpu=cores[(first + w) % len(cores)] if cores else None, group=group_of[w])
+                       for w in range(self.num_workers)]
             rc = torch.cuda.cudart().cudaHostRegister(self._obs_slab.data_ptr(), self._obs_slab.numel() * 4, 0)
             self._slab_pinned = (int(rc) == 0) if not isinstance(rc, tuple) else (int(rc[0]) == 0)
         self.workers = workers
@@ -209,16 +215,15 @@ class PPOTrainer:
         self._ctx = None
         # worker groups: with shared-memory stepping the workers are split into groups that alternate between the GPU (forward +
         # sampling on the group's own stream) and the environments, so env stepping overlaps the other group's device work
-        n_groups = int(os.environ.get("TRXL_ROLLOUT_GROUPS", "2" if (self._control is not None and W >= 8) else "1"))
-        n_groups = max(1, min(n_groups, W))
-        bounds = [round(i * W / n_groups) for i in range(n_groups + 1)]
-        self._groups = [_WorkerGroup(i, bounds[i], bounds[i + 1], self) for i in range(n_groups) if bounds[i + 1] > bounds[i]]
+        bounds = self._group_bounds if self._control is not None else [0, W]
+        self._groups = [_WorkerGroup(i, bounds[i], bounds[i + 1], self) for i in range(len(bounds) - 1) if bounds[i + 1] > bounds[i]]
         self._whole = self._groups[0] if len(self._groups) == 1 else _WorkerGroup(len(self._groups), 0, W, self)
         for grp in self._groups + [self._whole]:
             grp.rows = self._rollout_rows[:, grp.lo:grp.hi].contiguous()
         self.use_cuda_graphs = os.environ.get("TRXL_NO_GRAPHS", "0") != "1"
         self._capture_stream = None
         self._mapped = {}
+        self._futex = None
         self._table_pe = None           # table + positional rows for the episode-grouped tensor-core attention
         self._start_update = 0          # first update of run_training (advanced by load_checkpoint)
         self.device_feed = None         # optional device_feed.SyntheticDeviceFeed replacing the env workers (bench.py)
@@ -543,6 +548,11 @@ class PPOTrainer:
         acts, cmd, ack = c["actions"].numpy(), c["cmd"].numpy(), c["ack"].numpy()
         rewards, dones, has_info = c["rewards"].numpy(), c["dones"].numpy(), c["has_info"].numpy()
         sems = c.get("sems")
+        futex_words = c.get("futex")
+        if futex_words is not None:
+            if self._futex is None:
+                self._futex = _Futex()
+            fwords, fbase = futex_words.numpy(), futex_words.data_ptr()
         episode_infos = []
         trace = [0.0, 0.0, 0.0] if os.environ.get("TRXL_E2E_TRACE") == "1" else None     # enqueue, gpu phase, env phase
         dev_events = []
@@ -582,7 +592,10 @@ class PPOTrainer:
                     now = time.perf_counter()
                     acts[lo:hi] = grp.act_pinned.numpy()
                     cmd[lo:hi] += 1                       # publish last: the actions above are visible before the command
-                    if sems:
+                    if futex_words is not None:           # one system call wakes the whole group
+                        fwords[FUTEX_WORD_STRIDE * grp.index] += 1
+                        self._futex.wake(fbase + 4 * FUTEX_WORD_STRIDE * grp.index)
+                    elif sems:
                         for w in range(lo, hi):
                             sems[w].release()
                     grp.phase = grp.ENV
@@ -634,7 +647,7 @@ class PPOTrainer:
             print("[trxl] rollout trace per group step: enqueue %.0f us, gpu phase %.0f us (device time median %.0f us, p90 %.0f us), "
                   "env phase %.0f us (%d groups, %s workers)"
                   % (trace[0] * k, trace[1] * k, dev_us[len(dev_us) // 2], dev_us[int(len(dev_us) * 0.9)], trace[2] * k,
-                     len(groups), "blocking" if sems else "spinning"), flush=True)
+                     len(groups), "futex-blocking" if futex_words is not None else ("blocking" if sems else "spinning")), flush=True)
         return episode_infos
 
     def _check_workers_alive(self):
@@ -771,7 +784,16 @@ class PPOTrainer:
         """Once per update: the table with positional rows added (the table is frozen during the epochs) and the episode of
         every buffer row on the host.  Returns None when the configuration uses the per-sample kernel."""
         model, buf = self.model, self.buffer
-        if os.environ.get("TRXL_GROUPED_ATTENTION", "1") == "0" or not native.grouped_attention_supported(model._cfg):
+        forced = os.environ.get("TRXL_GROUPED_ATTENTION")
+        if forced == "0" or not native.grouped_attention_supported(model._cfg):
+            return None
+        # tiny minibatches (c1: 64 samples x 1 head) are one short launch of the per-sample kernel; three launches plus the host
+        # grouping only pay off once there are enough (sample, head) rows to fill 128-row tiles
+        if forced != "1" and buf.mini_batch_size * model.transformer.num_heads < 1024:
+            return None
+        # the grouped GEMMs cover all M slots of an episode, the per-sample kernel only the L window slots: with short windows
+        # in long episodes (c2: L = 32, M = 200; measured 160 k vs 173 k env-steps/s) the streaming kernel does less work
+        if forced != "1" and self.max_episode_length > 4 * self.memory_length:
             return None
         table = buf.memories
         if not torch.is_tensor(table) or table.dim() != 4 or table.shape[1] != self.max_episode_length:

@@ -32,14 +32,56 @@ class WorkerException(Exception):
         raise self.ee
 
 
-def make_control(n_workers, n_branches, blocking=False):
+FUTEX_WORD_STRIDE = 16          # int32 words between two groups' futex words (one 64-byte line each)
+
+
+def futex_available():
+    """Shared-memory futexes through libc's syscall(2): Linux on x86-64 (syscall number 202)."""
+    import platform
+    return sys.platform.startswith("linux") and platform.machine() in ("x86_64", "AMD64")
+
+
+class _Futex:
+    """FUTEX_WAIT / FUTEX_WAKE on an int32 that lives in memory shared between the trainer and its env processes (a torch tensor
+    in shared memory, mapped at the same address after fork).  One wake call releases every waiter of a worker group."""
+    SYS_FUTEX, WAIT, WAKE = 202, 0, 1
+
+    def __init__(self):
+        import ctypes
+
+        class Timespec(ctypes.Structure):
+            _fields_ = [("tv_sec", ctypes.c_long), ("tv_nsec", ctypes.c_long)]
+        self._ct = ctypes
+        self._ts = Timespec
+        self._libc = ctypes.CDLL(None, use_errno=True)
+        self._libc.syscall.restype = ctypes.c_long
+
+    def wait(self, addr, expected, timeout_s):
+        """Sleep until woken, until ``*addr != expected`` (returns at once), or until the timeout."""
+        ct = self._ct
+        ts = self._ts(int(timeout_s), int((timeout_s % 1.0) * 1e9))
+        self._libc.syscall(ct.c_long(self.SYS_FUTEX), ct.c_void_p(addr), ct.c_int(self.WAIT), ct.c_int(expected), ct.byref(ts),
+                           ct.c_void_p(0), ct.c_int(0))
+
+    def wake(self, addr, n=1 << 20):
+        ct = self._ct
+        self._libc.syscall(ct.c_long(self.SYS_FUTEX), ct.c_void_p(addr), ct.c_int(self.WAKE), ct.c_int(n), ct.c_void_p(0),
+                           ct.c_void_p(0), ct.c_int(0))
+
+
+def make_control(n_workers, n_branches, blocking=False, futex=None):
     """Shared arrays of the stepping fast path (torch tensors in shared memory, inherited by fork).
-    ``blocking=True`` adds one semaphore per worker: workers then sleep in the kernel between steps instead of
-    spinning on their command counter (needed as soon as env processes outnumber idle cores: spinning siblings slow
-    the envs that are actually stepping)."""
+    ``blocking=True``: workers sleep in the kernel between steps instead of spinning on their command counter (needed as
+    soon as env processes outnumber idle cores: spinning siblings slow the envs that are actually stepping).  They sleep on a
+    futex word per worker group (one wake system call releases the whole group) where that is available, otherwise on one
+    semaphore per worker."""
     import torch
-    sems = [multiprocessing.get_context("fork").Semaphore(0) for _ in range(n_workers)] if blocking else None
-    return {"sems": sems,
+    if futex is None:
+        futex = futex_available()
+    use_futex = bool(blocking and futex)
+    sems = [multiprocessing.get_context("fork").Semaphore(0) for _ in range(n_workers)] if (blocking and not use_futex) else None
+    return {"sems": sems, "blocking": bool(blocking),
+            "futex": torch.zeros(64 * FUTEX_WORD_STRIDE, dtype=torch.int32).share_memory_() if use_futex else None,
             "actions": torch.zeros((n_workers, n_branches), dtype=torch.int64).share_memory_(),
             "rewards": torch.zeros(n_workers, dtype=torch.float32).share_memory_(),
             "dones": torch.zeros(n_workers, dtype=torch.uint8).share_memory_(),
@@ -70,7 +112,7 @@ def physical_cpus():
     return cores
 
 
-def worker_process(remote, config, obs_slab=None, index=0, control=None, cpu=None):
+def worker_process(remote, config, obs_slab=None, index=0, control=None, cpu=None, group=0):
     import os
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     if cpu is not None:
@@ -105,9 +147,36 @@ def worker_process(remote, config, obs_slab=None, index=0, control=None, cpu=Non
         c_cmd, c_ack = control["cmd"].numpy(), control["ack"].numpy()
         last, idle = int(c_cmd[index]), 0
         sem = control["sems"][index] if control.get("sems") else None
+        fut, fword, faddr = None, None, 0
+        if control.get("futex") is not None:
+            fut = _Futex()
+            fword = control["futex"].numpy()
+            faddr = control["futex"].data_ptr() + 4 * FUTEX_WORD_STRIDE * group
     while True:
         try:
-            if control is not None and sem is not None:
+            if control is not None and fut is not None:
+                # futex variant: sleep until the trainer bumps this group's generation word (one wake call per group)
+                seq = int(c_cmd[index])
+                if seq == last:
+                    gen = int(fword[FUTEX_WORD_STRIDE * group])      # read the generation BEFORE re-checking the command
+                    seq = int(c_cmd[index])
+                    if seq == last:
+                        fut.wait(faddr, gen, 0.02)
+                        seq = int(c_cmd[index])
+                if seq != last:
+                    obs, reward, done, info = env.step(c_act.copy())
+                    if info:
+                        remote.send(info)
+                        obs = env.reset()
+                    if slot is not None:
+                        slot[...] = obs
+                    c_rew[index], c_done[index], c_info[index] = reward, 1 if done else 0, 1 if info else 0
+                    last = seq
+                    c_ack[index] = seq
+                    continue
+                if not remote.poll(0):
+                    continue
+            elif control is not None and sem is not None:
                 # blocking variant: sleep on the semaphore; the pipe (control messages) is polled every 20 ms
                 if sem.acquire(timeout=0.02):
                     seq = int(c_cmd[index])
@@ -166,8 +235,8 @@ class Worker:
     child: multiprocessing.connection.Connection
     process: multiprocessing.Process
 
-    def __init__(self, env_config, obs_slab=None, index=0, control=None, cpu=None):
+    def __init__(self, env_config, obs_slab=None, index=0, control=None, cpu=None, group=0):
         ctx = multiprocessing.get_context("fork")
         self.child, parent = ctx.Pipe()
-        self.process = ctx.Process(target=worker_process, args=(parent, env_config, obs_slab, index, control, cpu), daemon=True)
+        self.process = ctx.Process(target=worker_process, args=(parent, env_config, obs_slab, index, control, cpu, group), daemon=True)
         self.process.start()

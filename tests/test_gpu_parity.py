@@ -196,6 +196,9 @@ def test_trainer_two_updates_vs_reference(name, tmp_path, monkeypatch):
     import trainer as trainer_mod
     from environments.synthetic_env import SyntheticEnv
     monkeypatch.chdir(tmp_path)
+    # these minibatches are far below the size at which the trainer switches to the episode-grouped tensor-core attention;
+    # force it (it applies to the relative-PE fixtures, pre- and post-LN) so that path is checked against the reference too
+    monkeypatch.setenv("TRXL_GROUPED_ATTENTION", "1")
     g = load_golden(name)
     nact, max_steps = int(g["n_actions"]), int(g["max_steps"])
     obs_shape = tuple(int(x) for x in g["obs_shape"])

@@ -312,7 +312,7 @@ def test_grouped_tensor_core_attention_matches_per_sample_kernel(heads, gtrxl, p
                             "positional_encoding": pe, "layer_norm": ln})
     results = []
     for grouped in ("1", "0"):
-        monkeypatch.setenv("TRXL_GROUPED_ATTENTION", grouped)
+        monkeypatch.setenv("TRXL_GROUPED_ATTENTION", grouped)          # "1" also overrides the small-minibatch heuristic
         torch.manual_seed(5)
         tr = trainer_mod.PPOTrainer(cfg, run_id="ga", device=torch.device(DEV), workers=_synthetic_workers(cfg), summary_writer=False)
         torch.manual_seed(6)

@@ -238,7 +238,7 @@ def test_two_rank_gradient_allreduce_matches_single_rank(tmp_path):
     assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
 
 
-@pytest.mark.parametrize("blocking", [False, True])
+@pytest.mark.parametrize("blocking", [False, True, "futex"])
 def test_shared_memory_stepping_modes(blocking):
     """The rollout's env transport (worker.py): spinning and semaphore-blocking workers speak the same protocol --
     actions in, (reward, done) out through shared arrays, observation into the shared slab, auto-reset + info on the pipe."""
@@ -246,9 +246,14 @@ def test_shared_memory_stepping_modes(blocking):
     from worker import Worker, make_control
     n, obs_shape = 3, (3, 8, 8)
     slab = torch.zeros((n,) + obs_shape, dtype=torch.float32).share_memory_()
-    control = make_control(n, 1, blocking=blocking)
+    from worker import FUTEX_WORD_STRIDE, _Futex, futex_available
+    if blocking == "futex" and not futex_available():
+        pytest.skip("no shared-memory futex on this platform")
+    control = make_control(n, 1, blocking=bool(blocking), futex=(blocking == "futex"))
+    assert (control["futex"] is not None) == (blocking == "futex")
+    fut = _Futex() if blocking == "futex" else None
     cfg = {"type": "Synthetic", "obs_shape": list(obs_shape), "n_actions": 4, "max_episode_steps": 5, "min_episode_steps": 2, "seed": 0}
-    workers = [Worker(dict(cfg, seed=w), slab, w, control) for w in range(n)]
+    workers = [Worker(dict(cfg, seed=w), slab, w, control, group=w % 2) for w in range(n)]
     try:
         for w in workers:
             w.child.send(("reset", None))
@@ -260,7 +265,11 @@ def test_shared_memory_stepping_modes(blocking):
         for step in range(12):
             control["actions"].numpy()[...] = step % 4
             control["cmd"].numpy()[...] += 1
-            if control["sems"]:
+            if fut is not None:
+                for grp in (0, 1):
+                    control["futex"].numpy()[FUTEX_WORD_STRIDE * grp] += 1
+                    fut.wake(control["futex"].data_ptr() + 4 * FUTEX_WORD_STRIDE * grp)
+            elif control["sems"]:
                 for sem in control["sems"]:
                     sem.release()
             deadline = time.time() + 20

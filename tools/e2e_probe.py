@@ -29,7 +29,8 @@ def main():
     cfg = YamlParser(os.path.join(PKG, "configs", args.workload + ".yaml")).get_config()
     os.chdir(os.environ.get("TMPDIR", "/tmp"))
     tr = PPOTrainer(cfg, run_id="probe", device=torch.device("cuda:0"), summary_writer=False)
-    mode = "pipes" if tr._control is None else ("blocking" if tr._control.get("sems") else "spinning")
+    mode = "pipes" if tr._control is None else ("futex" if tr._control.get("futex") is not None else
+                                                ("blocking" if tr._control.get("sems") else "spinning"))
     print("[probe] groups=%d mode=%s effective_cpus=%.1f cpu_count=%d" % (len(tr._groups), mode, effective_cpus(), os.cpu_count()), flush=True)
     for r in range(args.rollouts):
         tr.timers = {"rollout": 0.0, "train": 0.0, "env": 0.0}
