@@ -34,6 +34,7 @@ class SyntheticEnv:
         self._t = 0
         self._len = self._max_steps
         self._ret = 0.0
+        self._out = None
 
     @property
     def observation_space(self):
@@ -47,7 +48,15 @@ class SyntheticEnv:
     def max_episode_steps(self):
         return self._max_steps
 
+    def set_observation_buffer(self, out):
+        """Optional: draw every observation directly into ``out`` (a float32 array of the observation shape, e.g. this
+        worker's slot of the trainer's shared pinned slab) instead of allocating a new array per step; same random stream."""
+        assert out.shape == self._obs_shape and out.dtype == np.float32
+        self._out = out
+
     def _obs(self):
+        if self._out is not None:
+            return self._rng.random(self._obs_shape, dtype=np.float32, out=self._out)
         return self._rng.random(self._obs_shape, dtype=np.float32)
 
     def reset(self, **kwargs):

@@ -142,6 +142,7 @@ class PPOTrainer:
         # so the per-step image payload goes env process -> slab -> (DMA) GPU without pickling or staging copies.
         # (pass workers=[] together with trainer.device_feed = SyntheticDeviceFeed(...) to run without env processes)
         self._obs_slab = None
+        self._yield_when_idle = False
         self._control = None          # shared-memory stepping arrays (own workers only)
         n_groups = int(os.environ.get("TRXL_ROLLOUT_GROUPS", "2" if (workers is None and self.num_workers >= 8 and
                                                                       os.environ.get("TRXL_PIPE_STEPPING", "0") != "1") else "1"))
@@ -159,6 +160,7 @@ class PPOTrainer:
                 # workers sleep on a semaphore between steps.
                 import platform
                 can_spin = procs + 1 <= effective_cpus() and platform.machine() in ("x86_64", "AMD64")
+                self._yield_when_idle = procs + 1 > effective_cpus() and hasattr(os, "sched_yield")
                 spin = os.environ.get("TRXL_SPIN_STEPPING", "1" if can_spin else "0") == "1"
                 self._control = make_control(self.num_workers, len(self.action_space_shape), blocking=not spin)
             # one physical core per env worker when the box has enough of them (TRXL_PIN_WORKERS=0 leaves placement to the OS)
@@ -633,6 +635,8 @@ class PPOTrainer:
                 deadline = time.perf_counter() + 120.0
                 continue
             idle_polls += 1
+            if self._yield_when_idle:
+                os.sched_yield()          # more processes than CPUs: let a runnable env worker have this core while we wait
             if idle_polls % 8192 == 0:
                 self._check_workers_alive()
                 if time.perf_counter() > deadline:

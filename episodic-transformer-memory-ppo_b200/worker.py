@@ -126,6 +126,8 @@ def worker_process(remote, config, obs_slab=None, index=0, control=None, cpu=Non
     except KeyboardInterrupt:
         return
     slot = None if obs_slab is None else obs_slab.numpy()[index]
+    if slot is not None and hasattr(env, "set_observation_buffer"):
+        env.set_observation_buffer(slot)          # the env draws observations straight into the shared slab
 
     def do_step(data):
         obs, reward, done, info = env.step(data)
@@ -168,7 +170,7 @@ def worker_process(remote, config, obs_slab=None, index=0, control=None, cpu=Non
                     if info:
                         remote.send(info)
                         obs = env.reset()
-                    if slot is not None:
+                    if slot is not None and obs is not slot:
                         slot[...] = obs
                     c_rew[index], c_done[index], c_info[index] = reward, 1 if done else 0, 1 if info else 0
                     last = seq

@@ -47,7 +47,7 @@ def launch_list(path, out):
         total += v
     with open(out, "w") as f:
         f.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold cache, serialised: compare SHARES)\n")
-        f.write("# slice: 2 rollout steps (W=32) + 2 PPO minibatch steps (mb=2048) of the c3 workload; %d launches, %.1f us total\n"
+        f.write("# slice: 2 rollout steps (W=32) + 2 PPO minibatch steps (mb=2048, episode-grouped attention) of the c3 workload; %d launches, %.1f us total\n"
                 % (len(rows), total))
         f.write("%-86s %6s %11s %7s %9s\n" % ("kernel", "n", "total_us", "share", "avg_us"))
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -92,7 +92,11 @@ def main():
             fdst.write("# torch.profiler (CUPTI) over ONE full PPO update of the c3 workload, device feed; top rows by device time\n")
             fdst.write(fsrc.read())
         print("wrote kineto table")
-    for rep, title in (("attn_%s" % args.round, "fused window attention fwd/bwd, training minibatch (N=2048, L=128, D=256, H=4)"),
+    for rep, title in (("attn_%s" % args.round, "fused window attention fwd/bwd, training minibatch (N=2048, L=128, D=256, H=4)") if args.round == "r1" else
+                       ("attn_%s" % args.round, "episode-grouped attention forward of block 0, c3 minibatch (N=2048, H=4, D=256, M=256): grouped "
+                                                "tma_gemm_kernel<128> S = QK.Xpe^T (K-major B from the strided table), then ctx = P.Xpe (MN-major B)"),
+                       ("tmagemm_%s" % args.round, "TMA + tcgen05 3xTF32 trunk GEMMs of one c3 minibatch step, in launch order: lin_hidden "
+                                                   "(2048x256x3136), embedding (2048x256x256), Q projection, per-head K fold (batch 4, K=64)"),
                        ("sgemm_%s" % args.round, "SIMT sgemm launches: 1 rollout step (M=32) + 1 minibatch step (M=2048)"),
                        ("tcgemm_%s" % args.round, "tcgen05 3xTF32 GEMM (opt-in), linear forward M=2048 N=256 K=256"),
                        ("rollout_%s" % args.round, "one rollout step (W=32): tcgen05 conv1/2/3 forward + the cluster-per-sample fused trunk kernel "
@@ -101,7 +105,9 @@ def main():
                                                   "forward, wgrad3, dgrad3, wgrad2, dgrad2 x4 parity classes, wgrad1 (launch order)")):
         p = os.path.join(args.src, rep + ".ncu-rep")
         if os.path.exists(p):
-            ncu_report(p, os.path.join(dst, "%s_ncu_%s.txt" % (args.round, rep.split("_")[0])), title)
+            names = {"attn": "grouped_attention" if args.round != "r1" else "attn", "tmagemm": "tma_gemm"}
+            key = rep.split("_")[0]
+            ncu_report(p, os.path.join(dst, "%s_ncu_%s.txt" % (args.round, names.get(key, key))), title)
 
 
 if __name__ == "__main__":
