@@ -452,6 +452,17 @@ int trxl_sample_actions(const float* logits, const float* u, const int64_t* forc
                               (long long*)actions_compact, W);
 }
 
+int trxl_sample_actions_notify(const float* logits, const float* u, const int64_t* forced_actions, const int32_t* branch_sizes,
+                               int num_branches, int64_t* actions, int64_t act_stride, float* log_probs, int64_t logp_stride,
+                               int64_t* actions_compact, int W, int64_t* done_counter, int64_t* done_flag, void* stream) {
+    TRXL_CHECK_ARG(logits && (u || forced_actions) && actions && log_probs && done_counter && done_flag, "sample_actions_notify: null pointer");
+    BranchSpec bs;
+    int sumA = 0;
+    TRXL_PROPAGATE(branch_spec(branch_sizes, num_branches, bs, &sumA));
+    return ppo_sample_actions(S(stream), logits, sumA, u, (cll)forced_actions, bs, (long long*)actions, act_stride, log_probs, logp_stride,
+                              (long long*)actions_compact, W, (long long*)done_counter, (long long*)done_flag);
+}
+
 int trxl_adv_stats(const float* advantages, const int64_t* sample_index, int N, double* out3, void* stream) {
     TRXL_CHECK_ARG(advantages && out3 && N > 0, "adv_stats: bad arguments");
     return ppo_adv_stats(S(stream), advantages, (cll)sample_index, N, out3);

@@ -146,10 +146,10 @@ __global__ void rollout_fetch_scalar_kernel(const float* __restrict__ obs_src, l
 
 // ------------------------------------------------------------------------------------ action sampling
 // Inverse-CDF sampling from softmax(logits) per branch with caller-provided uniforms (torch RNG).
-__global__ void sample_actions_kernel(const float* __restrict__ logits, int sumA, const float* __restrict__ u,
-                                      const long long* __restrict__ forced, BranchSpec bs, long long* __restrict__ act_out, long long act_stride, float* __restrict__ logp_out,
-                                      long long logp_stride, long long* __restrict__ act_compact, int W) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void sample_one(const float* __restrict__ logits, int sumA, const float* __restrict__ u,
+                                           const long long* __restrict__ forced, const BranchSpec& bs, long long* __restrict__ act_out,
+                                           long long act_stride, float* __restrict__ logp_out, long long logp_stride,
+                                           long long* __restrict__ act_compact, int W, int i) {
     if (i >= W * bs.n) return;
     const int w = i / bs.n, k = i % bs.n;
     const float* z = logits + (long long)w * sumA + bs.off[k];
@@ -173,6 +173,28 @@ __global__ void sample_actions_kernel(const float* __restrict__ logits, int sumA
     act_out[w * act_stride + k] = a;
     logp_out[w * logp_stride + k] = z[a] - lse;
     if (act_compact) act_compact[i] = a;
+}
+
+__global__ void sample_actions_kernel(const float* __restrict__ logits, int sumA, const float* __restrict__ u,
+                                      const long long* __restrict__ forced, BranchSpec bs, long long* __restrict__ act_out, long long act_stride, float* __restrict__ logp_out,
+                                      long long logp_stride, long long* __restrict__ act_compact, int W,
+                                      long long* __restrict__ done_counter, volatile long long* __restrict__ done_flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (done_flag) {
+        // single-block launches only (checked by the host wrapper): once every action of the step is in (pinned host) memory,
+        // publish a launch sequence number the host can poll without a CUDA call
+        sample_one(logits, sumA, u, forced, bs, act_out, act_stride, logp_out, logp_stride, act_compact, W, i);
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const long long seq = *done_counter + 1;
+            *done_counter = seq;
+            __threadfence_system();
+            *done_flag = seq;
+        }
+        return;
+    }
+    sample_one(logits, sumA, u, forced, bs, act_out, act_stride, logp_out, logp_stride, act_compact, W, i);
 }
 
 // ------------------------------------------------------------------------------------ advantage statistics
@@ -419,10 +441,13 @@ int ppo_rollout_fetch(cudaStream_t st, const float* obs_src, long long obs_float
 
 int ppo_sample_actions(cudaStream_t st, const float* logits, int sumA, const float* u, const long long* forced,
                        const BranchSpec& bs, long long* act_out,
-                       long long act_stride, float* logp_out, long long logp_stride, long long* act_compact, int W) {
+                       long long act_stride, float* logp_out, long long logp_stride, long long* act_compact, int W,
+                       long long* done_counter, long long* done_flag) {
     if (W == 0) return TRXL_OK;
-    sample_actions_kernel<<<trxl_cdiv(W * bs.n, 128), 128, 0, st>>>(logits, sumA, u, forced, bs, act_out, act_stride, logp_out,
-                                                                   logp_stride, act_compact, W);
+    TRXL_CHECK_ARG(!done_flag || (done_counter && W * bs.n <= 1024), "sample_actions: the completion flag needs a counter and W * branches <= 1024");
+    const int threads = done_flag ? ((W * bs.n + 31) / 32 * 32) : 128;
+    sample_actions_kernel<<<done_flag ? 1 : trxl_cdiv(W * bs.n, 128), threads, 0, st>>>(logits, sumA, u, forced, bs, act_out, act_stride, logp_out,
+                                                                   logp_stride, act_compact, W, done_counter, done_flag);
     TRXL_CHECK_LAUNCH("sample_actions");
     return TRXL_OK;
 }

@@ -46,7 +46,8 @@ int ppo_rollout_fetch(cudaStream_t st, const float* obs_src, long long obs_float
                       float* obs_dev, float* obs_store, long long store_stride_floats, long long* step_dev, long long* ep_dev, int n);
 int ppo_sample_actions(cudaStream_t st, const float* logits, int sumA, const float* u, const long long* forced,
                        const BranchSpec& bs, long long* act_out,
-                       long long act_stride, float* logp_out, long long logp_stride, long long* act_compact, int W);
+                       long long act_stride, float* logp_out, long long logp_stride, long long* act_compact, int W,
+                       long long* done_counter = nullptr, long long* done_flag = nullptr);
 int ppo_adv_stats(cudaStream_t st, const float* adv, const long long* sidx, int N, double* out);
 int ppo_loss(cudaStream_t st, PpoLossArgs a, float* stats);
 long long ppo_loss_partial_floats(int N);

@@ -77,6 +77,15 @@ class _WorkerGroup:
         self.act_dev = torch.zeros((self.n, nb), dtype=torch.long, device=dev)
         self.act_pinned = torch.zeros((self.n, nb), dtype=torch.long).pin_memory()
         self.act_host_dptr = native.host_device_pointer(self.act_pinned.data_ptr())     # kernels write the actions here
+        # completion flag: the sampling kernel publishes a launch sequence number into pinned host memory, so the host polls a
+        # plain int64 instead of a CUDA event (W * branches <= 1024 per group, else the event is used)
+        self.done_counter = torch.zeros(1, dtype=torch.long, device=dev)
+        self.done_flag = torch.zeros(1, dtype=torch.long).pin_memory()
+        self.done_flag_np = self.done_flag.numpy()
+        self.done_flag_dptr = native.host_device_pointer(self.done_flag.data_ptr())
+        self.use_flag = self.n * nb <= 1024
+        self.expected = 0
+        self.stream_handle = self.stream.cuda_stream
         self.step_dev = torch.zeros(self.n, dtype=torch.long, device=dev)
         self.ep_dev = torch.zeros(self.n, dtype=torch.long, device=dev)
         self.rows = None            # (T, n) int64: flat buffer rows of this group's workers at each step
@@ -461,7 +470,8 @@ class PPOTrainer:
         forced = None if self._forced_actions is None else self._forced_actions[t, lo:grp.hi]
         native.sample_actions(logits, ctx["uniforms"][t, lo:grp.hi], self.action_space_shape,
                               buf.actions.data_ptr() + row0 * nb * 8, T * nb, buf.log_probs.data_ptr() + row0 * nb * 4, T * nb,
-                              grp.act_host_dptr if on_host else grp.act_dev, n, forced=forced)      # actions land in host memory
+                              grp.act_host_dptr if on_host else grp.act_dev, n, forced=forced,      # actions land in host memory
+                              notify=(grp.done_counter, grp.done_flag_dptr) if (on_host and grp.use_flag) else None)
         native.copy_rows(value.data_ptr(), buf.values.data_ptr() + row0 * 4, n, 4, 4, T * 4)
 
     def _host_src(self, grp, host_obs):
@@ -562,8 +572,31 @@ class PPOTrainer:
             self._prepare_group(grp)
             grp.stream.wait_stream(cur)
             grp.t, grp.phase = 0, grp.DONE
+            if grp.use_flag:                     # resynchronise the expected sequence number with the device counter
+                grp.expected = int(grp.done_counter.item())
+
+        # fast path: when every step graph of this key is captured, a step is ONE ctypes call (cudaGraphLaunch on the group's
+        # stream handle); completion is read from the group's pinned flag
+        key = self._graph_key("groups")
+        fast = {}
+        if self.use_cuda_graphs and trace is None:
+            for grp in groups:
+                st = grp.graphs
+                if st.get("key") == key and st.get("warm", 0) >= self._graph_warm_rollouts and len(st.get("steps", {})) == T and grp.use_flag:
+                    fast[grp.index] = st["steps"]
+        table_ptr = self._table.data_ptr()
+        max_len = self.max_episode_length
+        step_np, ep_np = self._step_host.numpy(), self._ep_host.numpy()      # numpy views: cheaper per-step bookkeeping than torch ops
 
         def launch(grp):
+            steps = fast.get(grp.index)
+            if steps is not None and self._table.data_ptr() == table_ptr:
+                if step_np[grp.lo:grp.hi].max() >= max_len:
+                    self._check_cursors()
+                native.graph_launch_on(steps[grp.t], grp.stream_handle)
+                grp.expected += 1
+                grp.phase, grp.t_phase = grp.GPU, 0.0
+                return
             ta = time.perf_counter()
             if int(self._step_host[grp.lo:grp.hi].max()) >= self.max_episode_length:
                 self._check_cursors()
@@ -576,6 +609,8 @@ class PPOTrainer:
                 if trace is not None:
                     e1.record(grp.stream)
                 grp.event.record(grp.stream)
+            if grp.use_flag:
+                grp.expected += 1
             grp.phase, grp.t_phase = grp.GPU, time.perf_counter()
             if trace is not None:
                 trace[0] += grp.t_phase - ta
@@ -589,7 +624,10 @@ class PPOTrainer:
             for grp in groups:
                 lo, hi = grp.lo, grp.hi
                 if grp.phase == grp.GPU:
-                    if not grp.event.query():
+                    if grp.use_flag:
+                        if grp.done_flag_np[0] < grp.expected:
+                            continue
+                    elif not grp.event.query():
                         continue
                     now = time.perf_counter()
                     acts[lo:hi] = grp.act_pinned.numpy()
@@ -615,12 +653,12 @@ class PPOTrainer:
                     t = grp.t
                     buf.rewards[lo:hi, t] = rewards[lo:hi]
                     buf.dones[lo:hi, t] = dones[lo:hi] != 0
-                    self._step_host[lo:hi] += 1
+                    step_np[lo:hi] += 1
                     for w in np.nonzero(has_info[lo:hi])[0]:
                         w = lo + int(w)
                         episode_infos.append(self.workers[w].child.recv())
-                        self._step_host[w] = 0
-                        self._ep_host[w] = self._new_row()      # may move the table: every group's graphs are re-keyed
+                        step_np[w] = 0
+                        ep_np[w] = self._new_row()              # may move the table: every group's graphs are re-keyed
                         if t < T - 1:
                             self._n_episodes = self._n_rows
                     grp.t += 1

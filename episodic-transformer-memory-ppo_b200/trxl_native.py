@@ -91,6 +91,7 @@ SIGNATURES = {
     "trxl_rollout_fetch": (i32, [vp, i64, vp, vp, vp, vp, i64, vp, vp, i32, vp]),
     "trxl_host_device_pointer": (i32, [vp, C.POINTER(C.c_void_p)]),
     "trxl_sample_actions": (i32, [vp, vp, vp, C.POINTER(C.c_int32), i32, vp, i64, vp, i64, vp, i32, vp]),
+    "trxl_sample_actions_notify": (i32, [vp, vp, vp, C.POINTER(C.c_int32), i32, vp, i64, vp, i64, vp, i32, vp, vp, vp]),
     "trxl_adv_stats": (i32, [vp, vp, i32, vp, vp]),
     "trxl_ppo_loss": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int32), i32, i32, f64, f64, f64, vp, vp, vp, vp, vp]),
     "trxl_clip_adamw_step": (i32, [vp, vp, vp, vp, i64, vp, i32, i32, f64, f64, f64, f64, f64, f64, i64, vp, vp, vp]),
@@ -208,6 +209,12 @@ def graph_abort(stream_handle):
 
 def graph_launch(graph_exec):
     _check(load().trxl_graph_launch(graph_exec, _stream()), "trxl_graph_launch")
+
+
+def graph_launch_on(graph_exec, stream_handle):
+    """Replay on an explicit stream handle (no torch stream lookup: the rollout's per-step fast path)."""
+    if _lib.trxl_graph_launch(graph_exec, stream_handle) != 0:
+        raise RuntimeError("trxl_graph_launch failed: %s" % _lib.trxl_last_error().decode())
 
 
 def graph_destroy(graph_exec):
@@ -427,9 +434,15 @@ def memory_scatter(table, ep, step, new_mem, slots, inner):
            "trxl_memory_scatter")
 
 
-def sample_actions(logits, u, branch_sizes, act_ptr, act_stride, logp_ptr, logp_stride, act_compact, w, forced=None):
-    """``act_compact``: (w, nb) int64 device tensor, or the raw device-side address of a mapped host buffer."""
+def sample_actions(logits, u, branch_sizes, act_ptr, act_stride, logp_ptr, logp_stride, act_compact, w, forced=None, notify=None):
+    """``act_compact``: (w, nb) int64 device tensor, or the raw device-side address of a mapped host buffer.
+    ``notify`` = (device counter tensor, device-side address of a pinned host int64): completion flag for host polling."""
     compact = act_compact if isinstance(act_compact, int) else _p(act_compact)
+    if notify is not None:
+        _check(load().trxl_sample_actions_notify(_p(logits), _p(u), _p(forced), branch_array(branch_sizes), len(branch_sizes), act_ptr,
+                                                 act_stride, logp_ptr, logp_stride, compact, w, _p(notify[0]), notify[1], _stream()),
+               "trxl_sample_actions_notify")
+        return
     _check(load().trxl_sample_actions(_p(logits), _p(u), _p(forced), branch_array(branch_sizes), len(branch_sizes), act_ptr, act_stride,
                                       logp_ptr, logp_stride, compact, w, _stream()), "trxl_sample_actions")
 

@@ -210,6 +210,12 @@ int trxl_memory_scatter(float* table, const int64_t* ep, const int64_t* step, co
 int trxl_sample_actions(const float* logits, const float* u, const int64_t* forced_actions, const int32_t* branch_sizes,
                         int num_branches, int64_t* actions, int64_t act_stride, float* log_probs, int64_t logp_stride,
                         int64_t* actions_compact, int W, void* stream);
+/* Same, and once every action of the step is stored (e.g. in pinned host memory, see trxl_host_device_pointer) the kernel
+ * increments *done_counter (device memory) and publishes the new value to *done_flag (pinned host memory) behind a system-wide
+ * fence: the host learns that the step's actions are ready by polling plain memory, without a CUDA call.  W * num_branches <= 1024. */
+int trxl_sample_actions_notify(const float* logits, const float* u, const int64_t* forced_actions, const int32_t* branch_sizes,
+                               int num_branches, int64_t* actions, int64_t act_stride, float* log_probs, int64_t logp_stride,
+                               int64_t* actions_compact, int W, int64_t* done_counter, int64_t* done_flag, void* stream);
 /* {sum a, sum a^2, count} of the minibatch advantages as doubles (all-reduce these across ranks) */
 int trxl_adv_stats(const float* advantages, const int64_t* sample_index, int N, double* out3, void* stream);
 /* trainer.py:277-304,315-316 forward + backward: stats6 = [policy_loss, vf_loss, loss, entropy,
