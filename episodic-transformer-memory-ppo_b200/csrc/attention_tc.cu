@@ -164,6 +164,10 @@ GemmArgs grouped_args(const AttnTcArgs& a, const float* A, long long lda, int K,
     return g;
 }
 
+// N tile of a grouped GEMM: one 256-wide CTA per row tile when the output is wider than 128 (each CTA converts the tile's A
+// operand once instead of twice, and a c3 launch is 136 CTAs = one wave), else the narrowest tile that covers it
+int tile_n(int n) { return n > 128 ? 256 : (n > 64 ? 128 : (n > 32 ? 64 : 32)); }
+
 }  // namespace
 
 long long attn_tc_row_floats(long long slots) { return (slots + 3) / 4 * 4; }
@@ -208,11 +212,11 @@ int attn_tc_forward(const AttnTcArgs& a, const float* qk, float* P, float* ctx, 
     TRXL_CHECK_ARG(trxl_tc_gemm_eligible(g1), "attention_tc: operands not TMA-eligible");
     trxl_prof_begin(2, a.N, st);
     trxl_prof_aux(2, a.n_tiles);
-    TRXL_PROPAGATE(trxl_tc_gemm(g1, 128, st));
+    TRXL_PROPAGATE(trxl_tc_gemm(g1, tile_n((int)a.slots), st));
     attn_softmax_kernel<<<trxl_cdiv(rows, 8), 256, 0, st>>>(P, ld, (int)a.slots, a.ranges, a.H, rows, a.scale, a.L);
     TRXL_CHECK_LAUNCH("attention_softmax");
     GemmArgs g2 = grouped_args(a, P, ld, (int)a.slots, a.D, 0, ctx, a.D);               // ctx = P . Xpe      (B MN-major: k = slot)
-    TRXL_PROPAGATE(trxl_tc_gemm(g2, 128, st));
+    TRXL_PROPAGATE(trxl_tc_gemm(g2, tile_n(a.D), st));
     trxl_prof_end(2, st);
     return TRXL_OK;
 }
@@ -224,11 +228,11 @@ int attn_tc_backward(const AttnTcArgs& a, const float* P, const float* dctx, flo
     GemmArgs g1 = grouped_args(a, dctx, a.D, a.D, (int)a.slots, 1, scratch, ld);        // dP = dctx . Xpe^T
     trxl_prof_begin(3, a.N, st);
     trxl_prof_aux(3, a.n_tiles);
-    TRXL_PROPAGATE(trxl_tc_gemm(g1, 128, st));
+    TRXL_PROPAGATE(trxl_tc_gemm(g1, tile_n((int)a.slots), st));
     attn_dscore_kernel<<<trxl_cdiv(rows, 8), 256, 0, st>>>(scratch, P, ld, (int)a.slots, a.ranges, a.H, rows, 1.f / a.scale);
     TRXL_CHECK_LAUNCH("attention_dscore");
     GemmArgs g2 = grouped_args(a, scratch, ld, (int)a.slots, a.D, 0, dqk, a.D);         // dqk = dS . Xpe
-    TRXL_PROPAGATE(trxl_tc_gemm(g2, 128, st));
+    TRXL_PROPAGATE(trxl_tc_gemm(g2, tile_n(a.D), st));
     trxl_prof_end(3, st);
     return TRXL_OK;
 }

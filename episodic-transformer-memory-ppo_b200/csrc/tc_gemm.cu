@@ -45,8 +45,12 @@ constexpr int TM_CONV_WARPS = 8, TM_MMA_WARP = 8, TM_TMA_WARP = 9, TM_THREADS = 
 constexpr int A_TILE_BYTES = TM_BM * TM_BK * 4;      // 16 KB; K-major: 128 rows x 128 B; MN-major: 4 groups x (32 k-rows x 128 B)
 
 __host__ __device__ constexpr int tm_stage_bytes(int bn) { return 2 * A_TILE_BYTES + 2 * bn * TM_BK * 4; }
-__host__ __device__ constexpr int tm_stages(int bn) { return bn == 128 ? 3 : (bn == 64 ? 4 : 5); }
+__host__ __device__ constexpr int tm_stages(int bn) { return bn == 256 ? 2 : (bn == 128 ? 3 : (bn == 64 ? 4 : 5)); }
 __host__ __device__ constexpr int tm_tmem_cols(int bn) { return bn == 32 ? 128 : (bn == 64 ? 256 : 512); }
+// BN = 256 (the episode-grouped attention GEMMs: one CTA covers all 256 slots / all 256 embedding columns of a tile) leaves
+// room for two accumulators only: every hi*hi product goes to the first, the cross terms to the second.  The hi*hi chain
+// is then K/8 truncating additions long instead of K/16 (<= 32 at K = 256: ~2e-6 relative), which the attention tolerates.
+__host__ __device__ constexpr int tm_accumulators(int bn) { return bn == 256 ? 2 : 3; }
 
 struct TmaGemmParams {
     CUtensorMap ta, tb;          // rank 3: {inner, outer, batch}
@@ -60,6 +64,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// ask the TMA unit to pull a box into L2 (no shared-memory destination, no barrier): issued a few k-blocks ahead of the stage
+// ring so that the ring's own loads find their rows in L2 instead of paying the DRAM round trip with only 2-5 stages in flight
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -80,13 +90,20 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[3
 // v = (hi*hi even steps + hi*hi odd steps) + cross terms, for 32 accumulator columns of this warp's 32 lanes
 template <int BN>
 __device__ __forceinline__ void load_accumulators3(uint32_t taddr, float (&out)[32]) {
-    uint32_t v[32], u[32], x[32];
+    uint32_t v[32], u[32];
     tmem_ld32_nowait(taddr, v);
     tmem_ld32_nowait(taddr + BN, u);
-    tmem_ld32_nowait(taddr + 2 * BN, x);
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (tm_accumulators(BN) == 3) {
+        uint32_t x[32];
+        tmem_ld32_nowait(taddr + 2 * BN, x);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int i = 0; i < 32; ++i) out[i] = (__uint_as_float(v[i]) + __uint_as_float(u[i])) + __uint_as_float(x[i]);
+        for (int i = 0; i < 32; ++i) out[i] = (__uint_as_float(v[i]) + __uint_as_float(u[i])) + __uint_as_float(x[i]);
+    } else {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 32; ++i) out[i] = __uint_as_float(v[i]) + __uint_as_float(u[i]);
+    }
 }
 
 template <int BN, bool A_MN, bool B_MN>
@@ -132,8 +149,26 @@ __global__ void __launch_bounds__(TM_THREADS, 1) tma_gemm_kernel(const __grid_co
     if (warp == TM_TMA_WARP) {
         // ---------------- TMA producer ----------------
         if (lane == 0) {
+            constexpr int AHEAD = STAGES + 3;             // L2 prefetch distance in k-blocks
+            auto prefetch_kb = [&](int kb) {
+                const int k0 = k_begin + kb * TM_BK;
+                if (A_MN) {
+#pragma unroll
+                    for (int grp = 0; grp < TM_BM / 32; ++grp) tma_prefetch_3d(&p.ta, m0 + 32 * grp, k0, b);
+                } else {
+                    tma_prefetch_3d(&p.ta, k0, m0, b);
+                }
+                if (B_MN) {
+#pragma unroll
+                    for (int grp = 0; grp < BN / 32; ++grp) tma_prefetch_3d(&p.tb, n0 + 32 * grp, k0, b_of_B);
+                } else {
+                    tma_prefetch_3d(&p.tb, k0, n0, b_of_B);
+                }
+            };
+            for (int kb = STAGES; kb < min(kblocks, AHEAD); ++kb) prefetch_kb(kb);
             for (int kb = 0; kb < kblocks; ++kb) {
                 const int s = kb % STAGES;
+                if (kb + AHEAD < kblocks) prefetch_kb(kb + AHEAD);
                 mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
                 const int k0 = k_begin + kb * TM_BK;
                 const uint32_t a_dst = smem_base + s * STAGE_BYTES;
@@ -178,9 +213,15 @@ __global__ void __launch_bounds__(TM_THREADS, 1) tma_gemm_kernel(const __grid_co
                     const uint64_t dah = dah0 + k * A_KSTEP, dal = dal0 + k * A_KSTEP;
                     const uint64_t dbh = dbh0 + k * B_KSTEP, dbl = dbl0 + k * B_KSTEP;
                     const int step = kb * (TM_BK / 8) + k;
-                    umma_tf32(tmem_base + (uint32_t)((step & 1) * BN), dah, dbh, idesc, step >= 2 ? 1u : 0u);
-                    umma_tf32(tmem_base + 2 * BN, dal, dbh, idesc, step > 0 ? 1u : 0u);
-                    umma_tf32(tmem_base + 2 * BN, dah, dbl, idesc, 1u);
+                    if (tm_accumulators(BN) == 3) {
+                        umma_tf32(tmem_base + (uint32_t)((step & 1) * BN), dah, dbh, idesc, step >= 2 ? 1u : 0u);
+                        umma_tf32(tmem_base + 2 * BN, dal, dbh, idesc, step > 0 ? 1u : 0u);
+                        umma_tf32(tmem_base + 2 * BN, dah, dbl, idesc, 1u);
+                    } else {
+                        umma_tf32(tmem_base, dah, dbh, idesc, step > 0 ? 1u : 0u);
+                        umma_tf32(tmem_base + BN, dal, dbh, idesc, step > 0 ? 1u : 0u);
+                        umma_tf32(tmem_base + BN, dah, dbl, idesc, 1u);
+                    }
                 }
                 umma_commit(&empty[s]);                          // frees the stage once these MMAs have read it
                 if (kb == kblocks - 1) umma_commit(tmem_full);   // accumulators complete -> epilogue
@@ -427,6 +468,7 @@ int trxl_tc_gemm(const GemmArgs& g, int bn, cudaStream_t st) {
     if (g.b_kc) rc = get_map(g.B, g.K, g.N, nb, g.ldb, g.sB, bn, 0, &p.tb);                // (N, K) row-major: inner = k
     else rc = get_map(g.B, g.N, g.K, nb, g.ldb, g.sB, 32, 1, &p.tb);                       // (K, N) row-major: inner = n
     if (rc != TRXL_OK) return rc;
+    if (bn == 256) return launch_orient<256>(p, st);
     if (bn == 128) return launch_orient<128>(p, st);
     if (bn == 64) return launch_orient<64>(p, st);
     return launch_orient<32>(p, st);
