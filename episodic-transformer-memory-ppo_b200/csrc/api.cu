@@ -442,6 +442,17 @@ int trxl_memory_scatter(float* table, const int64_t* ep, const int64_t* step, co
     return ppo_memory_scatter(S(stream), table, (cll)ep, (cll)step, new_mem, W, slots, inner);
 }
 
+int trxl_rollout_store(float* table, float* table_pe, const float* pe_table, const int64_t* ep, const int64_t* step,
+                       const float* new_mem, int W, int64_t slots, int blocks, int dim, const float* value, float* value_dst,
+                       int64_t value_stride, void* stream) {
+    TRXL_CHECK_ARG(table && ep && step && new_mem, "rollout_store: null pointer");
+    TRXL_CHECK_ARG(!table_pe || pe_table, "rollout_store: table_pe given without pe_table");
+    TRXL_CHECK_ARG(!value_dst || value, "rollout_store: value_dst given without value");
+    TRXL_CHECK_ARG(blocks > 0 && dim > 0 && slots > 0, "rollout_store: bad shape");
+    return ppo_rollout_store(S(stream), table, table_pe, pe_table, (cll)ep, (cll)step, new_mem, W, slots, blocks, dim, value, value_dst,
+                             value_stride);
+}
+
 int trxl_sample_actions(const float* logits, const float* u, const int64_t* forced_actions, const int32_t* branch_sizes,
                         int num_branches, int64_t* actions, int64_t act_stride, float* log_probs, int64_t logp_stride,
                         int64_t* actions_compact, int W, void* stream) {

@@ -76,6 +76,24 @@ __global__ void memory_scatter_kernel(float* __restrict__ table, const long long
     const float* s = new_mem + w * inner;
     for (long long i = threadIdx.x; i < inner; i += blockDim.x) d[i] = s[i];
 }
+// The stores that end a rollout step, in one kernel: the memory scatter above; optionally the same rows plus their slot's
+// positional row into table_pe (a copy of the table that already carries the positional rows, which the fused rollout forward
+// prefetches window rows from); optionally value_dst[w * value_stride] = value[w] (trainer.py:186)
+__global__ void rollout_store_kernel(float* __restrict__ table, float* __restrict__ table_pe, const float* __restrict__ pe_table,
+                                     const long long* __restrict__ ep, const long long* __restrict__ step,
+                                     const float* __restrict__ new_mem, long long slots, int blocks, int D,
+                                     const float* __restrict__ value, float* __restrict__ value_dst, long long value_stride) {
+    const long long w = blockIdx.x, inner = (long long)blocks * D;
+    const long long s_ = step[w], off = (ep[w] * slots + s_) * inner;
+    const float* s = new_mem + w * inner;
+    const float* pe = table_pe ? pe_table + s_ * D : nullptr;
+    for (long long i = threadIdx.x; i < inner; i += blockDim.x) {
+        const float v = s[i];
+        table[off + i] = v;
+        if (table_pe) table_pe[off + i] = v + pe[i % D];
+    }
+    if (value_dst && threadIdx.x == 0) value_dst[w * value_stride] = value[w];
+}
 // mask_out[w, :] = mask_table[min(step, L-1), :]; idx_out[w, :] = index_table[step, :]; ep_out[w] = ep[w]
 // (reference trainer.py:165-166; tables are the bit-exact integer tables built on the host)
 __global__ void rollout_prepare_kernel(const long long* __restrict__ step, const long long* __restrict__ ep,
@@ -401,6 +419,15 @@ int ppo_memory_scatter(cudaStream_t st, float* table, const long long* ep, const
     if (W == 0) return TRXL_OK;
     memory_scatter_kernel<<<W, 128, 0, st>>>(table, ep, step, new_mem, slots, inner);
     TRXL_CHECK_LAUNCH("memory_scatter");
+    return TRXL_OK;
+}
+
+int ppo_rollout_store(cudaStream_t st, float* table, float* table_pe, const float* pe_table, const long long* ep, const long long* step,
+                      const float* new_mem, int W, long long slots, int blocks, int D, const float* value, float* value_dst,
+                      long long value_stride) {
+    if (W == 0) return TRXL_OK;
+    rollout_store_kernel<<<W, 256, 0, st>>>(table, table_pe, pe_table, ep, step, new_mem, slots, blocks, D, value, value_dst, value_stride);
+    TRXL_CHECK_LAUNCH("rollout_store");
     return TRXL_OK;
 }
 

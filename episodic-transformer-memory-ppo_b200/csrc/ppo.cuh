@@ -39,6 +39,9 @@ int ppo_gather_window(cudaStream_t st, const float* in, const long long* idx, fl
                       long long inner);
 int ppo_memory_scatter(cudaStream_t st, float* table, const long long* ep, const long long* step, const float* new_mem, int W,
                        long long slots, long long inner);
+int ppo_rollout_store(cudaStream_t st, float* table, float* table_pe, const float* pe_table, const long long* ep, const long long* step,
+                      const float* new_mem, int W, long long slots, int blocks, int D, const float* value, float* value_dst,
+                      long long value_stride);
 int ppo_rollout_prepare(cudaStream_t st, const long long* step, const long long* ep, const unsigned char* mask_table,
                         const long long* index_table, unsigned char* mask_out, long long mask_stride, long long* idx_out,
                         long long idx_stride, long long* ep_out, long long ep_stride, int W, int L);

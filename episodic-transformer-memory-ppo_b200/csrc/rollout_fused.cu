@@ -10,13 +10,22 @@
 //     one L2 round trip) and writes its quarter of the result into all four CTAs through distributed shared memory,
 //     followed by one cluster barrier;
 //   * attention heads are dealt to the CTAs (head h -> CTA h % 4): K-fold, the two passes over the episodic-memory
-//     window (read in place from the episode table) and the V-unfold of a head stay inside one CTA;
+//     window and the V-unfold of a head stay inside one CTA;
+//   * the window rows of a block depend only on the episode table, not on the activations, so when they need no
+//     positional add (no positional encoding, or a table that already carries it) every CTA pulls the NEXT block's L rows
+//     into shared memory with bulk async copies (cp.async.bulk, one per row, completion on an mbarrier) while the current
+//     block's projections run: the energies / context passes then read shared memory only (measured on B200 at c3: the
+//     energies pass was 4 dependent L2 round trips, 13.9 k of a block's 43 k clocks);
 //   * LayerNorms / gates' elementwise parts are recomputed by every CTA on its replicated vectors.
 // Same math and the same query-side fold as the layered kernels (attention.cu), fp32 throughout; inference only (nothing is
 // saved for a backward pass).  32 samples -> 128 CTAs on 128 SMs.
 #include "rollout_fused.cuh"
 
 #include <cooperative_groups.h>
+
+#include "tc_common.cuh"
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace cg = cooperative_groups;
 
@@ -41,6 +50,14 @@ __device__ __forceinline__ float dot4f(const float4& a, const float4& b) {
     return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
 }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// one row global -> shared through the bulk-copy engine; `bytes` (multiple of 16) are credited to the mbarrier on arrival
+__device__ __forceinline__ void bulk_row_g2s(float* dst, const float* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(tc::smem_u32(dst)), "l"(src), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
+}
 
 struct Cl {
     int rank, tid, warp, lane;
@@ -60,46 +77,55 @@ __device__ __forceinline__ void slice(const Cl& c, int n, int& j0, int& j1) {
     j1 = min(n, j0 + per);
 }
 
-// y[j] = act( W[j, :] . x + bias[j] ) + resid[j]   for j in [j0, j1).  W row-major (rows x K).  One warp per 8 rows; every
-// lane issues the 16 loads of its slice of the 8 rows before the first FMA.  The result goes to y[j] of this CTA, or of
-// every CTA in the cluster when bcast (the caller then runs a cluster barrier), and/or to y_global[j].
+// y[j] = act( W[j, :] . x + bias[j] ) + resid[j]   for j in [j0, j1).  W row-major (rows x K).  One warp per ROWS rows; every
+// lane issues the 2 * ROWS * KU 16-byte loads of its slice of those rows (KU chunks of 256 k) before the first FMA -- the
+// products are pure L2 latency, so the depth in flight is what sets their speed (8 x 1: the D x D layers, one round trip;
+// 8 x 2: lin_hidden's long rows; 16 x 1: the heads' 2 * hid rows).  The accumulation order per row does not depend on
+// ROWS / KU.  The result goes to y[j] of this CTA, or of every CTA in the cluster when bcast (the caller then runs a cluster
+// barrier), and/or to y_global[j].
+template <int ROWS = 8, int KU = 1>
 __device__ void gemv_range(const Cl& c, const float* __restrict__ W, int K, int j0, int j1, const float* x,
                            const float* __restrict__ bias, bool relu, const float* resid, float* y, float* y_global, bool bcast) {
     const bool vec = ((K & 3) == 0) && ((((uintptr_t)W) & 15) == 0) && ((((uintptr_t)x) & 15) == 0);
-    for (int jb = j0 + c.warp * 8; jb < j1; jb += RF_WARPS * 8) {
-        const int nrow = min(8, j1 - jb);
-        float acc[8];
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int jb = j0 + c.warp * ROWS; jb < j1; jb += RF_WARPS * ROWS) {
+        const int nrow = min(ROWS, j1 - jb);
+        float acc[ROWS];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) acc[r] = 0.f;
+        for (int r = 0; r < ROWS; ++r) acc[r] = 0.f;
         if (vec) {
-            for (int k0 = c.lane * 4; k0 < K; k0 += 256) {
-                const bool has2 = (k0 + 128) < K;
-                float4 w[8][2];
+            for (int k0 = c.lane * 4; k0 < K; k0 += 256 * KU) {
+                float4 w[ROWS][2 * KU];
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
+                for (int r = 0; r < ROWS; ++r) {
                     const float* wr = W + (long long)(jb + (r < nrow ? r : 0)) * K + k0;
-                    w[r][0] = ldg4(wr);
-                    w[r][1] = has2 ? ldg4(wr + 128) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                const float4 x0 = *reinterpret_cast<const float4*>(x + k0);
-                const float4 x1 = has2 ? *reinterpret_cast<const float4*>(x + k0 + 128) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int r = 0; r < 8; ++r) acc[r] += dot4f(w[r][0], x0) + dot4f(w[r][1], x1);
+                    for (int u = 0; u < 2 * KU; ++u) w[r][u] = (k0 + 128 * u < K) ? ldg4(wr + 128 * u) : zero4;
+                }
+                float4 xv[2 * KU];
+#pragma unroll
+                for (int u = 0; u < 2 * KU; ++u) xv[u] = (k0 + 128 * u < K) ? *reinterpret_cast<const float4*>(x + k0 + 128 * u) : zero4;
+#pragma unroll
+                for (int u = 0; u < KU; ++u) {
+                    if (u > 0 && k0 + 256 * u >= K) break;        // (a lane past the end of the row only holds zeros)
+#pragma unroll
+                    for (int r = 0; r < ROWS; ++r) acc[r] += dot4f(w[r][2 * u], xv[2 * u]) + dot4f(w[r][2 * u + 1], xv[2 * u + 1]);
+                }
             }
         } else {
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
+            for (int r = 0; r < ROWS; ++r) {
                 if (r >= nrow) continue;
                 const float* wr = W + (long long)(jb + r) * K;
                 for (int k = c.lane; k < K; k += 32) acc[r] = fmaf(__ldg(wr + k), x[k], acc[r]);
             }
         }
 #pragma unroll
-        for (int r = 0; r < 8; ++r) acc[r] = wsum(acc[r]);
+        for (int r = 0; r < ROWS; ++r) acc[r] = wsum(acc[r]);
         if (c.lane < nrow) {
             float v = acc[0];
 #pragma unroll
-            for (int r = 1; r < 8; ++r) if (c.lane == r) v = acc[r];
+            for (int r = 1; r < ROWS; ++r) if (c.lane == r) v = acc[r];
             const int j = jb + c.lane;
             if (bias) v += bias[j];
             if (relu) v = fmaxf(v, 0.f);
@@ -211,6 +237,18 @@ __device__ void gru_gate(cg::cluster_group& cluster, const Cl& c, const float* P
     cluster.sync();
 }
 
+// Start the bulk copies of one block's visible window rows into s_cache (whole CTA calls; the rows were last touched by
+// generic-proxy accesses that a __syncthreads has already ordered before this call).
+__device__ void window_prefetch(const Cl& c, const float* tab, const int* s_win, const int* s_vis, int L, int D, int nvis,
+                                float* s_cache, uint64_t* bar) {
+    tc::fence_async_proxy();
+    if (c.tid == 0) mbar_expect_tx(bar, (uint32_t)nvis * (uint32_t)D * 4u);
+    // a warp issues its lanes' bulk copies one after the other (~50 clocks each, measured), so the rows are dealt across the
+    // warps first: row l -> warp l % 8, lane l / 8
+    for (int l = c.warp + c.lane * RF_WARPS; l < L; l += RF_THREADS)
+        if (s_vis[l]) bulk_row_g2s(s_cache + (long long)l * D, tab + s_win[l], (uint32_t)D * 4u, bar);
+}
+
 __global__ void __cluster_dims__(RF_CL, 1, 1) __launch_bounds__(RF_THREADS, 1) rollout_fused_kernel(const RfArgs a) {
     extern __shared__ __align__(16) float sm[];
     cg::cluster_group cluster = cg::this_cluster();
@@ -239,7 +277,12 @@ __global__ void __cluster_dims__(RF_CL, 1, 1) __launch_bounds__(RF_THREADS, 1) r
     int* s_vis = s_pe + Lp;                           // [L]
     float* s_cache = reinterpret_cast<float*>(s_vis + Lp);   // [L][D] window rows (+PE) of the head in flight, if it fits
     __shared__ int s_any;
+    __shared__ int s_nvis;
+    __shared__ __align__(8) uint64_t s_wbar;          // completion of the window prefetch in flight
 
+    int mark_i = 0;
+#define RF_MARK() do { if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[mark_i] = clock64(); ++mark_i; } while (0)
+    RF_MARK();
     Cl c;
     c.rank = (int)cluster.block_rank();
     c.tid = threadIdx.x; c.warp = c.tid >> 5; c.lane = c.tid & 31;
@@ -265,22 +308,34 @@ __global__ void __cluster_dims__(RF_CL, 1, 1) __launch_bounds__(RF_THREADS, 1) r
         s_pe[l] = (int)((a.pe_index ? a.pe_index[row * L + l] : 0) * D);
     }
     if (any) s_any = 1;
+    if (tid == 0) { tc::mbar_init(&s_wbar, 1); tc::mbar_init_fence(); }
     __syncthreads();
     const bool all_masked = (s_any == 0);
     if (all_masked) {
         for (int l = tid; l < L; l += RF_THREADS) s_vis[l] = 1;
         __syncthreads();
     }
-    const float* pe = a.pe_mode == 1 ? a.pe_table : (a.pe_mode == 2 ? P + a.pos : nullptr);
+    const float* pe = (a.pe_mode == 1 && a.pe_index) ? a.pe_table : ((a.pe_mode == 2 && a.pe_index) ? P + a.pos : nullptr);
+    // window rows through the bulk-copy engine, one block ahead (only CTAs that own a head; rows must need no positional add)
+    const bool bulk = a.cache_window && pe == nullptr && c.rank < H;
+    if (bulk) {
+        int cnt = 0;
+        for (int l0 = 0; l0 < L; l0 += RF_THREADS) cnt += __syncthreads_count((l0 + tid < L) && s_vis[l0 + tid]);
+        if (tid == 0) s_nvis = cnt;
+        window_prefetch(c, a.table + (ep * a.slots) * a.B * (long long)D, s_win, s_vis, L, D, cnt, s_cache, &s_wbar);
+    }
     cluster.sync();                                   // every CTA's shared memory is live before the first remote store
+    RF_MARK();                                        // 1: inputs staged
 
     int j0, j1;
     // ---- lin_hidden + embedding ----
     slice(c, D, j0, j1);
-    gemv_range(c, P + a.Wh, a.feat, j0, j1, s_feat, P + a.bh, true, nullptr, s_a, nullptr, true);
+    gemv_range<8, 2>(c, P + a.Wh, a.feat, j0, j1, s_feat, P + a.bh, true, nullptr, s_a, nullptr, true);
     cluster.sync();
+    RF_MARK();                                        // 2: lin_hidden
     gemv_range(c, P + a.We, D, j0, j1, s_a, P + a.be, true, nullptr, s_h, nullptr, true);
     cluster.sync();
+    RF_MARK();                                        // 3: embedding
 
     const float scale = sqrtf((float)D);
     const int NC = (D + 127) / 128;                   // float4 chunks per lane per row (<= 4)
@@ -299,11 +354,13 @@ __global__ void __cluster_dims__(RF_CL, 1, 1) __launch_bounds__(RF_THREADS, 1) r
         slice(c, D, j0, j1);
         gemv_range(c, P + a.b0.Wq + bo, D, j0, j1, q_in, nullptr, false, nullptr, s_b, nullptr, true);
         cluster.sync();
+        RF_MARK();                                    // block + 0: Q
         const float* Wk = P + a.b0.Wk + bo;
         // ---- the heads dealt to this CTA ----
         for (int h = c.rank; h < H; h += RF_CL) {
             // folded query: qk[j] = sum_{d in head h} Q[d] Wk[d, j] (* gamma_kv[j]);  pre-LN extras: qkb, sum_j qk[j]
             fold_k(c, Wk + (long long)h * dh * D, D, dh, s_b + h * dh, pre ? P + a.b0.nkw + bo : nullptr, s_part, s_qk);
+            if (h == c.rank) RF_MARK();               // block + 1: K-fold
             float qkb = 0.f, sg = 0.f;
             if (pre) {
                 // kb[d] = Wk[d, :] . beta_kv for this head's rows -> s_d[h*dh ..]
@@ -326,8 +383,59 @@ __global__ void __cluster_dims__(RF_CL, 1, 1) __launch_bounds__(RF_THREADS, 1) r
                 const int col = cc * 128 + lane * 4;
                 qv[cc] = (cc < NC && col < D) ? *reinterpret_cast<const float4*>(s_qk + col) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            // ---- pass 1: energies (four window rows in flight per warp) ----
-            for (int l0 = warp * 4; l0 < L; l0 += RF_WARPS * 4) {
+            if (bulk && h == c.rank) tc::mbar_wait(&s_wbar, (uint32_t)(blk & 1));      // this block's window has landed
+            // ---- pass 1: energies ----
+            // prefetched window: rows are in shared memory; eight rows per warp and trip, their reductions interleaved, lane u
+            // finishes row l0 + u (same per-row arithmetic as the streaming form below)
+            if (bulk) {
+                for (int l0 = warp * 8; l0 < L; l0 += RF_WARPS * 8) {
+                    float d[8], s1[8], s2[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int l = l0 + u;
+                        d[u] = 0.f; s1[u] = 0.f; s2[u] = 0.f;
+                        if (l < L && s_vis[l]) {                        // warp-uniform
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc) {
+                                const int col = cc * 128 + lane * 4;
+                                if (cc < NC && col < D) {
+                                    const float4 xv = *reinterpret_cast<const float4*>(s_cache + l * D + col);
+                                    d[u] += dot4f(qv[cc], xv);
+                                    if (pre) { s1[u] += xv.x + xv.y + xv.z + xv.w; s2[u] += dot4f(xv, xv); }
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) d[u] += __shfl_xor_sync(FULL, d[u], o);
+                    }
+                    if (pre) {
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) { s1[u] += __shfl_xor_sync(FULL, s1[u], o); s2[u] += __shfl_xor_sync(FULL, s2[u], o); }
+                        }
+                    }
+                    float dv = d[0], s1v = s1[0], s2v = s2[0];
+#pragma unroll
+                    for (int u = 1; u < 8; ++u) if (lane == u) { dv = d[u]; s1v = s1[u]; s2v = s2[u]; }
+                    const int l = l0 + lane;
+                    if (lane < 8 && l < L && s_vis[l]) {
+                        float e = dv;
+                        if (pre) {
+                            const float mu = s1v / (float)D;
+                            const float rstd = rsqrtf(fmaxf(s2v / (float)D - mu * mu, 0.f) + LN_EPS);
+                            s_mu[l] = mu; s_rs[l] = rstd;
+                            e = fmaf(rstd, dv - mu * sg, qkb);
+                        }
+                        s_p[l] = all_masked ? 0.f : __fdiv_rn(e, scale);
+                    }
+                }
+            }
+            // streaming form: rows (+ positional rows) come from L2, four window rows in flight per warp
+            for (int l0 = warp * 4; l0 < L && !bulk; l0 += RF_WARPS * 4) {
                 float4 x[4][4];
                 bool vis[4];
 #pragma unroll
@@ -381,6 +489,7 @@ __global__ void __cluster_dims__(RF_CL, 1, 1) __launch_bounds__(RF_THREADS, 1) r
                 }
             }
             __syncthreads();
+            if (h == c.rank) RF_MARK();               // block + 2: energies
             // ---- softmax over the L energies (warp 0) ----
             if (warp == 0) {
                 float m = -INFINITY;
@@ -397,13 +506,43 @@ __global__ void __cluster_dims__(RF_CL, 1, 1) __launch_bounds__(RF_THREADS, 1) r
                 for (int l = lane; l < L; l += 32) s_p[l] *= inv;
             }
             __syncthreads();
+            if (h == c.rank) RF_MARK();               // block + 3: softmax
             // ---- pass 2: ctx = sum_l p[l] x_l (rows come back from L2), warps merged in warp order ----
             {
                 float4 acc[4];
                 float csum = 0.f;
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) acc[cc] = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int l0 = warp * 2; l0 < L; l0 += RF_WARPS * 2) {
+                // window in shared memory: two row pairs (l0, l0 + 1, l0 + 16, l0 + 17) per trip, accumulated in the order of the
+                // two-row loop below
+                for (int lb = warp * 2; lb < L && a.cache_window; lb += RF_WARPS * 4) {
+                    float4 x[4][4];
+                    bool vis[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int l = lb + (q >> 1) * (RF_WARPS * 2) + (q & 1);
+                        vis[q] = (l < L) && s_vis[l];
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) {
+                            const int col = cc * 128 + lane * 4;
+                            x[q][cc] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (vis[q] && cc < NC && col < D) x[q][cc] = *reinterpret_cast<const float4*>(s_cache + l * D + col);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (!vis[q]) continue;
+                        const int l = lb + (q >> 1) * (RF_WARPS * 2) + (q & 1);
+                        const float wgt = s_p[l] * (pre ? s_rs[l] : 1.f);
+                        if (pre) csum = fmaf(wgt, s_mu[l], csum);
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) {
+                            acc[cc].x = fmaf(wgt, x[q][cc].x, acc[cc].x); acc[cc].y = fmaf(wgt, x[q][cc].y, acc[cc].y);
+                            acc[cc].z = fmaf(wgt, x[q][cc].z, acc[cc].z); acc[cc].w = fmaf(wgt, x[q][cc].w, acc[cc].w);
+                        }
+                    }
+                }
+                for (int l0 = warp * 2; l0 < L && !a.cache_window; l0 += RF_WARPS * 2) {
                     float4 x[2][4];
                     bool vis[2];
 #pragma unroll
@@ -415,14 +554,10 @@ __global__ void __cluster_dims__(RF_CL, 1, 1) __launch_bounds__(RF_THREADS, 1) r
                             const int col = cc * 128 + lane * 4;
                             x[u][cc] = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (vis[u] && cc < NC && col < D) {
-                                if (a.cache_window) {
-                                    x[u][cc] = *reinterpret_cast<const float4*>(s_cache + l * D + col);
-                                } else {
-                                    x[u][cc] = ldg4(tab + s_win[l] + col);
-                                    if (pe) {
-                                        const float4 p4 = ldg4(pe + s_pe[l] + col);
-                                        x[u][cc].x += p4.x; x[u][cc].y += p4.y; x[u][cc].z += p4.z; x[u][cc].w += p4.w;
-                                    }
+                                x[u][cc] = ldg4(tab + s_win[l] + col);
+                                if (pe) {
+                                    const float4 p4 = ldg4(pe + s_pe[l] + col);
+                                    x[u][cc].x += p4.x; x[u][cc].y += p4.y; x[u][cc].z += p4.z; x[u][cc].w += p4.w;
                                 }
                             }
                         }
@@ -458,15 +593,19 @@ __global__ void __cluster_dims__(RF_CL, 1, 1) __launch_bounds__(RF_THREADS, 1) r
                 }
                 __syncthreads();
             }
+            if (h == c.rank) RF_MARK();               // block + 4: context
             // V-unfold of this head: att[d] = Wv[d, :] . ctx  for d in the head's rows -> s_c of every CTA
             gemv_range(c, P + a.b0.Wv + bo, D, h * dh, (h + 1) * dh, s_ctx, nullptr, false, nullptr, s_c, nullptr, true);
             __syncthreads();
         }
+        if (bulk && blk + 1 < a.B) window_prefetch(c, tab + D, s_win, s_vis, L, D, s_nvis, s_cache, &s_wbar);
         cluster.sync();
+        RF_MARK();                                    // block + 5: V-unfold
         // fc_out (+ residual when not gated) -> s_b
         slice(c, D, j0, j1);
         gemv_range(c, P + a.b0.Wo + bo, D, j0, j1, s_c, P + a.b0.bo + bo, false, a.gtrxl ? nullptr : s_h, s_b, nullptr, true);
         cluster.sync();
+        RF_MARK();                                    // block + 6: fc_out
         float* h1 = s_b;                               // h1pre
         if (a.gtrxl) {
             RfGate g1 = a.b0.g1; g1.Wr += bo; g1.Ur += bo; g1.Ug += bo; g1.bg += bo;
@@ -483,9 +622,11 @@ __global__ void __cluster_dims__(RF_CL, 1, 1) __launch_bounds__(RF_THREADS, 1) r
             layer_norm(c, h1, nullptr, P + a.b0.n2w + bo, P + a.b0.n2b + bo, s_f, D, s_red);
             h_ = s_f;
         }
+        RF_MARK();                                    // block + 7: gate / norms before the feed-forward
         slice(c, D, j0, j1);
         gemv_range(c, P + a.b0.Wff + bo, D, j0, j1, h_, P + a.b0.bff + bo, true, nullptr, s_g, nullptr, true);
         cluster.sync();
+        RF_MARK();                                    // block + 8: feed-forward
         if (a.gtrxl) {
             RfGate g2 = a.b0.g2; g2.Wr += bo; g2.Ur += bo; g2.Ug += bo; g2.bg += bo;
             float* pool[5] = {s_a, s_b, s_c, s_d, s_e};
@@ -508,16 +649,41 @@ __global__ void __cluster_dims__(RF_CL, 1, 1) __launch_bounds__(RF_THREADS, 1) r
         }
         // a faster CTA must not start the next block's broadcasts (Q -> s_b, ...) while a slower one still reads this block's
         cluster.sync();
+        RF_MARK();                                    // block + 9: gate / norm after the feed-forward
     }
     // ---- heads ----
     slice(c, hid, j0, j1);
-    gemv_range(c, P + a.Wp, D, j0, j1, s_h, P + a.bp, true, nullptr, s_hd, nullptr, true);
-    gemv_range(c, P + a.Wlv, D, j0, j1, s_h, P + a.blv, true, nullptr, s_hd + hid, nullptr, true);
+    gemv_range<16, 1>(c, P + a.Wp, D, j0, j1, s_h, P + a.bp, true, nullptr, s_hd, nullptr, true);
+    gemv_range<16, 1>(c, P + a.Wlv, D, j0, j1, s_h, P + a.blv, true, nullptr, s_hd + hid, nullptr, true);
     cluster.sync();
     if (c.rank == 0) {
-        gemv_range(c, P + a.Wbr, hid, 0, a.sumA, s_hd, P + a.bbr, false, nullptr, nullptr, a.logits + (long long)n * a.sumA, false);
-        gemv_range(c, P + a.wval, hid, 0, 1, s_hd + hid, P + a.bval, false, nullptr, nullptr, a.value + n, false);
+        // the sumA logit rows and the value row, one per warp, all in flight together (per-row arithmetic as in gemv_range)
+        const bool vec = ((hid & 3) == 0) && ((((uintptr_t)(P + a.Wbr)) & 15) == 0) && ((((uintptr_t)(P + a.wval)) & 15) == 0);
+        for (int j = warp; j <= a.sumA; j += RF_WARPS) {
+            const bool is_value = (j == a.sumA);
+            const float* wr = is_value ? P + a.wval : P + a.Wbr + (long long)j * hid;
+            const float* xv = is_value ? s_hd + hid : s_hd;
+            float acc = 0.f;
+            if (vec) {
+                for (int k0 = lane * 4; k0 < hid; k0 += 256) {
+                    const bool has2 = (k0 + 128) < hid;
+                    const float4 w0 = ldg4(wr + k0), w1 = has2 ? ldg4(wr + k0 + 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 x0 = *reinterpret_cast<const float4*>(xv + k0);
+                    const float4 x1 = has2 ? *reinterpret_cast<const float4*>(xv + k0 + 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    acc += dot4f(w0, x0) + dot4f(w1, x1);
+                }
+            } else {
+                for (int k = lane; k < hid; k += 32) acc = fmaf(__ldg(wr + k), xv[k], acc);
+            }
+            acc = wsum(acc);
+            if (lane == 0) {
+                if (is_value) a.value[n] = acc + P[a.bval];
+                else a.logits[(long long)n * a.sumA + j] = acc + P[a.bbr + j];
+            }
+        }
     }
+    RF_MARK();                                        // heads
+#undef RF_MARK
 }
 
 }  // namespace
@@ -549,7 +715,35 @@ int rollout_fused_forward(const RfArgs& a, cudaStream_t st) {
     }
     RfArgs b = a;
     b.cache_window = window_fits(a) ? 1 : 0;
+    // TRXL_RF_TRACE present at the first call: every later call whose current value is > 0 prints cluster 0's phase latencies
+    // (synchronises the stream; debugging only -- tools/rf_trace.py)
+    static int trace_armed = -1;
+    if (trace_armed < 0) trace_armed = getenv("TRXL_RF_TRACE") ? 1 : 0;
+    int trace = 0;
+    if (trace_armed) { const char* e = getenv("TRXL_RF_TRACE"); trace = (e && atoi(e) > 0) ? 1 : 0; }
+    static long long* trace_dev = nullptr;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (trace) cudaStreamIsCapturing(st, &cap);
+    const bool tracing = trace && cap == cudaStreamCaptureStatusNone;
+    if (tracing) {
+        if (!trace_dev) cudaMalloc(&trace_dev, 256 * sizeof(long long));
+        cudaMemsetAsync(trace_dev, 0, 256 * sizeof(long long), st);
+        b.trace = trace_dev;
+    }
     rollout_fused_kernel<<<a.N * RF_CL, RF_THREADS, smem, st>>>(b);
     TRXL_CHECK_LAUNCH("rollout_fused");
+    if (tracing) {
+        long long host[256];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(host, trace_dev, sizeof(host), cudaMemcpyDeviceToHost);
+        static const char* blk_names[10] = {"Q", "K-fold", "energies", "softmax", "context", "V-unfold", "fc_out", "pre-FF", "FF", "post-FF"};
+        const int marks = 4 + 10 * a.B + 1;
+        fprintf(stderr, "[rf-trace] N=%d D=%d H=%d L=%d B=%d feat=%d cache=%d total=%lld clk\n", a.N, a.D, a.H, a.L, a.B, a.feat, b.cache_window,
+                host[marks - 1] - host[0]);
+        for (int i = 1; i < marks && i < 256; ++i) {
+            const char* name = i == 1 ? "stage" : (i == 2 ? "lin_hidden" : (i == 3 ? "embedding" : (i == marks - 1 ? "heads" : blk_names[(i - 4) % 10])));
+            fprintf(stderr, "[rf-trace]  %2d %-10s %6lld clk\n", i, name, host[i] - host[i - 1]);
+        }
+    }
     return TRXL_OK;
 }

@@ -25,6 +25,7 @@ struct RfArgs {
     float* logits = nullptr;
     float* value = nullptr;
     float* out_mem = nullptr;
+    long long* trace = nullptr;    // debug (TRXL_RF_TRACE=1): SM clock of cluster 0 at every phase boundary
     int cache_window = 0;      // set by the launcher: the head's window (L x D floats) is kept in shared memory between the two passes
 };
 

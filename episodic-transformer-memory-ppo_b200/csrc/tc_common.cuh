@@ -32,10 +32,13 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return r;
 }
-// x = hi + lo with hi, lo representable in TF32 (lo carries the next 11 mantissa bits)
+// x = hi + lo: hi = x rounded to TF32 (nearest, ties away: add half an ulp of the 10-bit mantissa to the magnitude and clear the
+// low 13 bits -- what cvt.rna.tf32.f32 computes for finite values, in two integer operations instead of its ~10-instruction
+// expansion on sm_100a); lo = x - hi is exact in fp32 and left unrounded: the tensor core reads only its top 19 bits, an error of
+// 2^-11 |lo| <= 2^-22 |x|, the size of the lo*lo term 3xTF32 drops anyway.
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    hi = __uint_as_float(to_tf32(x));
-    lo = __uint_as_float(to_tf32(x - hi));
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+    lo = x - hi;
 }
 
 // SWIZZLE_NONE shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): bits [0,14) start>>4,

@@ -20,6 +20,9 @@
 // runs fence.proxy.async, issues the stage's MMAs and tcgen05.commit's the `empty` mbarrier.
 #include "tc_conv.cuh"
 
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace {
@@ -27,8 +30,10 @@ namespace {
 using namespace tc;
 
 constexpr int BM = 128, BK = TCG_BK, THREADS = 160;
-// STAGES = 2 (<= 48 KB per stage): two CTAs per SM for the training-sized grids; STAGES = 4: one CTA per SM with three
-// k-blocks in flight for rollout-sized grids (fewer CTAs than SMs, pure latency)
+// STAGES = 2 (<= 48 KB per stage): two CTAs of 4 producer warps per SM for the training-sized grids; STAGES = 4: one CTA per
+// SM with three k-blocks in flight and EIGHT producer / epilogue warps for rollout-sized grids (fewer CTAs than SMs, pure
+// latency: measured on B200, one producer warp per scheduler needs ~1.2 k clocks to issue a k-block's 24 copies per thread,
+// and the four-warp epilogue took 12-16 k clocks of a 36-41 k clock kernel)
 // The tensor core adds into the TMEM accumulator with truncation, so the rounding error grows with the length of the
 // accumulation chain.  Three accumulators keep it at fp32-SIMT level: hi*hi products alternate between two of them (halving
 // the chain that carries the magnitude), the ~2^-11 smaller cross terms go to the third, and the epilogue adds them (RN).
@@ -44,7 +49,9 @@ struct GatherArgs {
     int relu;
     const float* mask;                          // optional image with the output geometry: result kept where mask > 0
     float* out_hi; float* out_lo; float* out_plain;     // any may be null
+    float* out_feat; int feat_P;                        // optional: feat[n, c * P + p] = result[(n, p), c] (dense forward rows only)
     long long M;
+    long long* trace;                                   // debug (TRXL_CONV_TRACE): CTA 0's SM clock at phase boundaries
 };
 
 struct WgradArgs {
@@ -78,22 +85,48 @@ __device__ __forceinline__ void load_accumulators(uint32_t taddr, uint32_t (&v)[
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(THREADS, STAGES == 2 ? 2 : 1) tc_conv_gather_kernel(const __grid_constant__ GatherArgs a) {
+// cluster helpers (split-K: the CTAs of a cluster hold partial sums of the same 128-row tile)
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float4 ld_peer_f4(uint32_t local_addr, uint32_t cta) {
+    uint32_t remote;
+    float4 v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(cta));
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote) : "memory");
+    return v;
+}
+
+// grid (row tiles, KS); with KS > 1 the launch carries cluster dims (1, KS, 1): CTA (tile, kq) accumulates k-blocks
+// [kq nkb / KS, (kq + 1) nkb / KS) of the tile -- rollout-sized problems have fewer row tiles than SMs and are bound by one SM's
+// copy-issue rate (measured: ~1.3 k clocks per k-block whatever the number of producer warps), so the k-blocks are spread over
+// KS SMs.  Epilogue: every CTA parks its partial tile in its own (now idle) stage memory; after a cluster barrier CTA kq sums
+// the KS partials of rows [kq 128 / KS, (kq + 1) 128 / KS) in fixed order through distributed shared memory and finishes
+// them: thread = (row, 1/8 of the columns), so a row's 128 / 256 output bytes per plane leave as one coalesced run.
+template <int BN, int STAGES, int PW>
+__global__ void __launch_bounds__((PW + 1) * 32, STAGES == 2 ? 2 : 1) tc_conv_gather_kernel(const __grid_constant__ GatherArgs a) {
     extern __shared__ __align__(1024) unsigned char tcc_smem[];
     constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    constexpr int PSTRIDE = BN + 4;                          // floats per parked row (the pad keeps float4 accesses conflict-free)
+    static_assert(BM * PSTRIDE * 4 <= STAGE_BYTES, "a parked tile must fit one stage");
     unsigned char* tiles = tcc_smem + ((1024u - (smem_u32(tcc_smem) & 1023u)) & 1023u);      // swizzled layouts need an aligned base
     uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    float* park = reinterpret_cast<float*>(tiles);                           // [BM][PSTRIDE] partial tile (stage 0)
+    float* fin = reinterpret_cast<float*>(tiles + STAGE_BYTES);              // [rows][PSTRIDE] finished values (stage 1; out_feat only)
     __shared__ int s_tapoff[TCG_MAX_KB], s_dy[TCG_MAX_KB], s_dx[TCG_MAX_KB];
     __shared__ long long s_rowbase[BM], s_rowdst[BM];       // float offsets of a row's anchor pixel / output pixel (-1: past M)
     __shared__ int s_rowyx[BM];                             // anchor pixel (y << 16 | x)
+    __shared__ long long s_rowfeat[BM];                     // out_feat: offset of element (n, c = 0, p) of the row's sample
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long m0 = (long long)blockIdx.x * BM;
-    const int nkb = a.g.nkb;
+    const int KS = (int)gridDim.y, kq = (int)blockIdx.y;
+    const int kb0 = (kq * a.g.nkb) / KS, kb1 = ((kq + 1) * a.g.nkb) / KS, nkb = kb1 - kb0;
+    const bool tracing = a.trace != nullptr && blockIdx.x == 0 && kq == 0;
+    if (tracing && threadIdx.x == 0) a.trace[0] = clock64();
     stage_taps(a.g, s_tapoff, s_dy, s_dx);
     if (threadIdx.x < BM) {
         const long long m = m0 + threadIdx.x;
@@ -110,97 +143,88 @@ __global__ void __launch_bounds__(THREADS, STAGES == 2 ? 2 : 1) tc_conv_gather_k
         s_rowbase[threadIdx.x] = base;
         s_rowdst[threadIdx.x] = dst;
         s_rowyx[threadIdx.x] = (ay << 16) | ax;
+        if (a.out_feat && dst >= 0) {                   // dense forward rows: dst / BN = n * P + p
+            const long long np = dst / BN, fn = np / a.feat_P;
+            s_rowfeat[threadIdx.x] = fn * BN * a.feat_P + (np - fn * a.feat_P);
+        }
     }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], PW * 32); mbar_init(&empty[s], 1); }
         mbar_init(tmem_full, 1);
         mbar_init_fence();
     }
-    if (warp == 4) tmem_alloc(tmem_slot, tmem_cols(BN));
+    if (warp == PW) tmem_alloc(tmem_slot, tmem_cols(BN));
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t smem_base = smem_u32(tiles);
+    if (tracing && threadIdx.x == 0) a.trace[1] = clock64();
 
-    if (warp < 4) {
+    if (warp < PW) {
         // ---------------- producers ----------------
         // Eight consecutive lanes copy the eight 16-byte pieces of one row's 128-byte run (fully coalesced global reads);
-        // thread t owns piece t & 7 of rows (t >> 3) + 16 i.  Shared tiles are K-major SWIZZLE_128B: row r at
+        // thread t owns piece t & 7 of rows (t >> 3) + RSTEP i.  Shared tiles are K-major SWIZZLE_128B: row r at
         // (r / 8) * 1024 + (r % 8) * 128, piece c at position c ^ (r % 8), so the eight lanes of a row hit distinct banks.
+        constexpr int RSTEP = PW * 4, RPT = BM / RSTEP;      // rows a pass of all producers covers; rows per thread
         const int piece = threadIdx.x & 7, r0 = threadIdx.x >> 3;
-        long long rbase[8];
-        int ryx[8];
+        long long rbase[RPT];
+        int ryx[RPT];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { rbase[i] = s_rowbase[r0 + 16 * i]; ryx[i] = s_rowyx[r0 + 16 * i]; }
+        for (int i = 0; i < RPT; ++i) { rbase[i] = s_rowbase[r0 + RSTEP * i]; ryx[i] = s_rowyx[r0 + RSTEP * i]; }
         const uint32_t dst0 = (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128 + ((piece ^ (r0 & 7)) * 16));
-        const int K = nkb * BK;
+        const int K = a.g.nkb * BK;
         for (int it = 0; it < nkb; ++it) {
-            {
-                const int s = it % STAGES;
-                mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
-                const int tdy = s_dy[it], tdx = s_dx[it];
-                const long long toff = s_tapoff[it] + piece * 4;
-                const uint32_t dst = smem_base + s * STAGE_BYTES + dst0;
+            const int s = it % STAGES, kb = kb0 + it;
+            mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+            const int tdy = s_dy[kb], tdx = s_dx[kb];
+            const long long toff = s_tapoff[kb] + piece * 4;
+            const uint32_t dst = smem_base + s * STAGE_BYTES + dst0;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int sy = (ryx[i] >> 16) + tdy, sx = (ryx[i] & 0xffff) + tdx;
-                    const bool ok = rbase[i] >= 0 && sy >= 0 && sy < a.g.img_h && sx >= 0 && sx + a.g.run_px <= a.g.img_w;
-                    const long long off = ok ? rbase[i] + toff : 0;
-                    const uint32_t nbytes = ok ? 16u : 0u;
-                    cp_async16(dst + i * 2048, a.a_hi + off, nbytes);
-                    cp_async16(dst + A_BYTES + i * 2048, a.a_lo + off, nbytes);
-                }
-                const long long boff = (long long)r0 * K + it * BK + piece * 4;
-                const uint32_t dstb = smem_base + s * STAGE_BYTES + 2 * A_BYTES + dst0;
-#pragma unroll
-                for (int i = 0; i < BN / 16; ++i) {
-                    cp_async16(dstb + i * 2048, a.b_hi + boff + (long long)i * 16 * K, 16u);
-                    cp_async16(dstb + B_BYTES + i * 2048, a.b_lo + boff + (long long)i * 16 * K, 16u);
-                }
-                cp_async_arrive(&full[s]);           // fires when this thread's copies of the stage have landed; nobody waits
+            for (int i = 0; i < RPT; ++i) {
+                const int sy = (ryx[i] >> 16) + tdy, sx = (ryx[i] & 0xffff) + tdx;
+                const bool ok = rbase[i] >= 0 && sy >= 0 && sy < a.g.img_h && sx >= 0 && sx + a.g.run_px <= a.g.img_w;
+                const long long off = ok ? rbase[i] + toff : 0;
+                const uint32_t nbytes = ok ? 16u : 0u;
+                cp_async16(dst + i * (RSTEP * 128), a.a_hi + off, nbytes);
+                cp_async16(dst + A_BYTES + i * (RSTEP * 128), a.a_lo + off, nbytes);
             }
+            const long long boff = (long long)r0 * K + kb * BK + piece * 4;
+            const uint32_t dstb = smem_base + s * STAGE_BYTES + 2 * A_BYTES + dst0;
+#pragma unroll
+            for (int i = 0; i < BN / RSTEP; ++i) {
+                cp_async16(dstb + i * (RSTEP * 128), a.b_hi + boff + (long long)i * RSTEP * K, 16u);
+                cp_async16(dstb + B_BYTES + i * (RSTEP * 128), a.b_lo + boff + (long long)i * RSTEP * K, 16u);
+            }
+            cp_async_arrive(&full[s]);           // fires when this thread's copies of the stage have landed; nobody waits
+            if (tracing && threadIdx.x == 0 && it < 36) a.trace[2 + it] = clock64();
         }
-        // ---------------- epilogue: TMEM -> registers -> bias / ReLU / mask -> pre-split NHWC stores ----------------
+        // ---------------- epilogue, part 1: TMEM -> registers -> this CTA's partial tile, parked in stage 0 ----------------
+        // warp w reads TMEM lanes 32 (w % 4) .. +31 (rows of the tile); with eight warps, w / 4 picks the 32-column chunks
         mbar_wait(tmem_full, 0);
         fence_after_sync();
-        const long long dst = s_rowdst[threadIdx.x];
-        const bool row_ok = dst >= 0;
+        if (tracing && threadIdx.x == 0) a.trace[80] = clock64();
+        const int quarter = warp & 3;
+        float* prow = park + (quarter * 32 + lane) * PSTRIDE;
 #pragma unroll 1
-        for (int j = 0; j < BN / 32; ++j) {
+        for (int j = warp >> 2; j < BN / 32; j += PW / 4) {
             uint32_t v[32];
-            load_accumulators<BN>(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * 32), v);
-            if (!row_ok) continue;
+            load_accumulators<BN>(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * 32), v);
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                const int col = j * 32 + i;
-                float x[4], hi[4], lo[4];
-                float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (a.mask) mk = *reinterpret_cast<const float4*>(a.mask + dst + col);
-                const float mkv[4] = {mk.x, mk.y, mk.z, mk.w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float t = __uint_as_float(v[i + q]);
-                    if (a.bias) t += __ldg(a.bias + col + q);
-                    if (a.relu) t = fmaxf(t, 0.f);
-                    if (!(mkv[q] > 0.f)) t = 0.f;
-                    x[q] = t;
-                    split_tf32(t, hi[q], lo[q]);
-                }
-                if (a.out_hi) *reinterpret_cast<float4*>(a.out_hi + dst + col) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                if (a.out_lo) *reinterpret_cast<float4*>(a.out_lo + dst + col) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                if (a.out_plain) *reinterpret_cast<float4*>(a.out_plain + dst + col) = make_float4(x[0], x[1], x[2], x[3]);
-            }
+            for (int i = 0; i < 32; i += 4)
+                *reinterpret_cast<float4*>(prow + j * 32 + i) = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
+                                                                            __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
         }
     } else {
         // ---------------- MMA issuer ----------------
         constexpr uint32_t idesc = idesc_tf32(BM, BN, false, false);
         constexpr uint32_t SBO = 1024;
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % STAGES;
-            mbar_wait(&full[s], (kb / STAGES) & 1);
+        for (int it = 0; it < nkb; ++it) {
+            const int s = it % STAGES;
+            mbar_wait(&full[s], (it / STAGES) & 1);
             fence_async_proxy();                     // the landed copies (generic proxy) -> visible to the MMAs this warp issues
             fence_after_sync();
+            if (tracing && lane == 0 && it < 36) a.trace[40 + it] = clock64();
             if (lane == 0) {
                 const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_BYTES;
                 const uint32_t b_hi = a_lo + A_BYTES, b_lo = b_hi + B_BYTES;
@@ -210,20 +234,104 @@ __global__ void __launch_bounds__(THREADS, STAGES == 2 ? 2 : 1) tc_conv_gather_k
                     const uint64_t dal = make_desc(a_lo + k * 32, 16, SBO, LAYOUT_SW128);
                     const uint64_t dbh = make_desc(b_hi + k * 32, 16, SBO, LAYOUT_SW128);
                     const uint64_t dbl = make_desc(b_lo + k * 32, 16, SBO, LAYOUT_SW128);
-                    const int step = kb * (BK / 8) + k;
+                    const int step = it * (BK / 8) + k;
                     umma_tf32(tmem_base + (uint32_t)((step & 1) * BN), dah, dbh, idesc, step >= 2 ? 1u : 0u);
                     umma_tf32(tmem_base + 2 * BN, dal, dbh, idesc, step > 0 ? 1u : 0u);
                     umma_tf32(tmem_base + 2 * BN, dah, dbl, idesc, 1u);
                 }
                 umma_commit(&empty[s]);
-                if (kb == nkb - 1) umma_commit(tmem_full);
+                if (it == nkb - 1) umma_commit(tmem_full);
             }
             __syncwarp();
         }
     }
     fence_before_sync();
-    __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, tmem_cols(BN));
+    __syncthreads();                                 // partial tile parked, TMEM drained
+    if (warp == PW) tmem_dealloc(tmem_base, tmem_cols(BN));
+    if (KS > 1) cluster_sync_all();                  // every CTA's partial is visible cluster-wide
+    if (warp < PW) {
+        // ---------------- epilogue, part 2: sum the partials of this CTA's rows, bias / ReLU / mask, pre-split NHWC stores ----------------
+        constexpr int NT = PW * 32, CPT = BN / 8;    // a row's columns are shared by 8 threads
+        const int rows_mine = BM / KS, row_lo = kq * rows_mine;
+        const int g8 = threadIdx.x & 7, c0 = g8 * CPT;
+        const bool bias_vec = (((uintptr_t)a.bias) & 15) == 0;
+        float bv[CPT];
+#pragma unroll
+        for (int q = 0; q < CPT; ++q) bv[q] = 0.f;
+        if (a.bias) {
+            if (bias_vec) {
+#pragma unroll
+                for (int q = 0; q < CPT; q += 4) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + c0 + q));
+                    bv[q] = b4.x; bv[q + 1] = b4.y; bv[q + 2] = b4.z; bv[q + 3] = b4.w;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < CPT; ++q) bv[q] = __ldg(a.bias + c0 + q);
+            }
+        }
+        const uint32_t park_addr = smem_u32(park);
+        for (int rl = threadIdx.x >> 3; rl < rows_mine; rl += NT / 8) {
+            const int r = row_lo + rl;
+            const long long dst = s_rowdst[r];
+            float x[CPT];
+#pragma unroll
+            for (int q = 0; q < CPT; ++q) x[q] = 0.f;
+            // all peers' loads in flight together; summed in CTA order (the result does not depend on which CTA finishes first)
+            float4 p4[4][CPT / 4];
+#pragma unroll
+            for (int src = 0; src < 4; ++src) {
+#pragma unroll
+                for (int q = 0; q < CPT; q += 4) {
+                    const uint32_t off = (uint32_t)((r * PSTRIDE + c0 + q) * 4);
+                    p4[src][q / 4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (KS > 1) { if (src < KS) p4[src][q / 4] = ld_peer_f4(park_addr + off, (uint32_t)src); }
+                    else if (src == 0) p4[src][q / 4] = *reinterpret_cast<const float4*>(park + r * PSTRIDE + c0 + q);
+                }
+            }
+#pragma unroll
+            for (int src = 0; src < 4; ++src) {
+                if (src >= KS) break;
+#pragma unroll
+                for (int q = 0; q < CPT; q += 4) {
+                    x[q] += p4[src][q / 4].x; x[q + 1] += p4[src][q / 4].y; x[q + 2] += p4[src][q / 4].z; x[q + 3] += p4[src][q / 4].w;
+                }
+            }
+            float hi[CPT], lo[CPT];
+#pragma unroll
+            for (int q = 0; q < CPT; q += 4) {
+                float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (a.mask && dst >= 0) mk = *reinterpret_cast<const float4*>(a.mask + dst + c0 + q);
+                const float mkv[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float t = x[q + e] + bv[q + e];
+                    if (a.relu) t = fmaxf(t, 0.f);
+                    if (!(mkv[e] > 0.f)) t = 0.f;
+                    x[q + e] = t;
+                    split_tf32(t, hi[q + e], lo[q + e]);
+                }
+                if (dst >= 0) {
+                    if (a.out_hi) *reinterpret_cast<float4*>(a.out_hi + dst + c0 + q) = make_float4(hi[q], hi[q + 1], hi[q + 2], hi[q + 3]);
+                    if (a.out_lo) *reinterpret_cast<float4*>(a.out_lo + dst + c0 + q) = make_float4(lo[q], lo[q + 1], lo[q + 2], lo[q + 3]);
+                    if (a.out_plain) *reinterpret_cast<float4*>(a.out_plain + dst + c0 + q) = make_float4(x[q], x[q + 1], x[q + 2], x[q + 3]);
+                }
+                if (a.out_feat) *reinterpret_cast<float4*>(fin + rl * PSTRIDE + c0 + q) = make_float4(x[q], x[q + 1], x[q + 2], x[q + 3]);
+            }
+        }
+        if (a.out_feat) {
+            // the reference flattens NCHW (model.py:94): feat[n, c * P + p] = result[(n, p), c]; consecutive lanes take consecutive
+            // rows (= consecutive p within a sample), so every store instruction writes runs of the feature row
+            asm volatile("bar.sync 1, %0;" ::"n"(PW * 32) : "memory");       // the producer / epilogue warps only
+            for (int idx = threadIdx.x; idx < rows_mine * BN; idx += NT) {
+                const int rl = idx % rows_mine, c = idx / rows_mine;
+                if (s_rowdst[row_lo + rl] < 0) continue;
+                a.out_feat[s_rowfeat[row_lo + rl] + (long long)c * a.feat_P] = fin[rl * PSTRIDE + c];
+            }
+        }
+    }
+    if (tracing && threadIdx.x == 0) a.trace[81] = clock64();
+    if (KS > 1) cluster_sync_all();                  // nobody leaves while a peer may still read its parked tile
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -402,15 +510,6 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int kind, int l
         lo[i] = l;
     }
 }
-// feat[n, c*P + p] = y3[(n, p), c]                                  (the reference flattens NCHW, model.py:94)
-__global__ void nhwc_to_feat_kernel(const float* __restrict__ y, float* __restrict__ feat, long long n, int P) {
-    const long long total = n * P * 64;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int p = (int)(i % P), c = (int)((i / P) % 64);
-        const long long img = i / ((long long)P * 64);
-        feat[i] = y[(img * P + p) * 64 + c];
-    }
-}
 // dy3[(n, p), c] = dfeat[n, c*P + p] where the conv3 output was positive (ReLU backward), pre-split
 __global__ void dfeat_to_dy3_kernel(const float* __restrict__ dfeat, const float* __restrict__ y3_hi, long long n, int P,
                                     float* __restrict__ hi, float* __restrict__ lo) {
@@ -474,7 +573,7 @@ long long align64(long long v) { return (v + 63) / 64 * 64; }
 constexpr int COLSUM_BLOCKS = 592;
 
 struct Ws {
-    float *x0[2], *y1[2], *y2[2], *y3[2], *y3p, *d3[2], *d2[2], *d1[2];
+    float *x0[2], *y1[2], *y2[2], *y3[2], *d3[2], *d2[2], *d1[2];
     float *wp1[2], *wp2[2], *wp3[2], *wd3[2], *wd2[2];
     float *partial, *colpart;
     long long partial_floats, total;
@@ -497,7 +596,6 @@ void carve(const TcgEncoder& e, long long n, float* base, Ws& w) {
     for (int i = 0; i < 2; ++i) w.y1[i] = take(m1 * 32);
     for (int i = 0; i < 2; ++i) w.y2[i] = take(m2 * 64);
     for (int i = 0; i < 2; ++i) w.y3[i] = take(m3 * 64);
-    w.y3p = take(m3 * 64);
     for (int i = 0; i < 2; ++i) w.d3[i] = take(m3 * 64);
     for (int i = 0; i < 2; ++i) w.d2[i] = take(m2 * 64);
     for (int i = 0; i < 2; ++i) w.d1[i] = take(m1 * 32);
@@ -524,14 +622,65 @@ void carve(const TcgEncoder& e, long long n, float* base, Ws& w) {
 template <int BN, int STAGES>
 int launch_gather_stages(cudaStream_t st, const GatherArgs& a) {
     constexpr size_t smem = (size_t)STAGES * (2 * BM * BK * 4 + 2 * BN * BK * 4) + (2 * STAGES + 1) * 8 + 16 + 1024;
+    constexpr int PW = STAGES == 2 ? 4 : 8;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_conv_gather_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(tc_conv_gather_kernel<BN, STAGES, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { trxl_set_error("tc_conv: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e)); return TRXL_ERR_CUDA; }
         attr_set = true;
     }
-    tc_conv_gather_kernel<BN, STAGES><<<trxl_cdiv(a.M, BM), THREADS, smem, st>>>(a);
+    // TRXL_CONV_TRACE present at the first call: later launches of at most one wave whose current value is > 0 print CTA 0's
+    // phase clocks (synchronises the stream; debugging only)
+    static int trace_armed = -1;
+    static long long* trace_dev = nullptr;
+    if (trace_armed < 0) trace_armed = getenv("TRXL_CONV_TRACE") ? 1 : 0;
+    bool tracing = false;
+    if (trace_armed && trxl_cdiv(a.M, BM) <= 148) {
+        const char* e = getenv("TRXL_CONV_TRACE");
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cap);
+        tracing = e && atoi(e) > 0 && cap == cudaStreamCaptureStatusNone;
+    }
+    GatherArgs b = a;
+    if (tracing) {
+        if (!trace_dev) cudaMalloc(&trace_dev, 96 * sizeof(long long));
+        cudaMemsetAsync(trace_dev, 0, 96 * sizeof(long long), st);
+        b.trace = trace_dev;
+    }
+    // rollout-sized grids: spread a tile's k-blocks over a cluster of KS CTAs so that ~half the SMs or more pull operands
+    const int tiles_m = (int)trxl_cdiv(a.M, BM);
+    int KS = 1;
+    if (STAGES == 4) {
+        static int forced = -1;                  // TRXL_CONV_KSPLIT=1|2|4 pins the split (tuning experiments)
+        if (forced < 0) { const char* e = getenv("TRXL_CONV_KSPLIT"); forced = e ? atoi(e) : 0; }
+        if (forced == 1 || forced == 2 || forced == 4) KS = forced;       // (the kernel sums at most 4 partials)
+        else KS = (tiles_m * 4 <= 148 && a.g.nkb >= 8) ? 4 : ((tiles_m * 2 <= 148 && a.g.nkb >= 4) ? 2 : 1);
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(tiles_m, KS, 1);
+    cfg.blockDim = dim3((PW + 1) * 32, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = KS; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = KS > 1 ? 1 : 0;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, tc_conv_gather_kernel<BN, STAGES, PW>, b);
+    if (le != cudaSuccess) { trxl_set_error("tc_conv_gather: launch failed: %s", cudaGetErrorString(le)); return TRXL_ERR_CUDA; }
     TRXL_CHECK_LAUNCH("tc_conv_gather");
+    if (tracing) {
+        long long h[96];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[conv-trace] BN=%d stages=%d M=%lld nkb=%d ctas=%d ksplit=%d: setup %lld, epilogue at %lld, end %lld clk\n", BN, STAGES,
+                a.M, a.g.nkb, tiles_m, KS, h[1] - h[0], h[80] - h[0], h[81] - h[0]);
+        fprintf(stderr, "[conv-trace]   producer issue:");
+        for (int i = 0; i < a.g.nkb && i < 36; ++i) fprintf(stderr, " %lld", h[2 + i] - h[0]);
+        fprintf(stderr, "\n[conv-trace]   stage landed: ");
+        for (int i = 0; i < a.g.nkb && i < 36; ++i) fprintf(stderr, " %lld", h[40 + i] - h[0]);
+        fprintf(stderr, "\n");
+    }
     return TRXL_OK;
 }
 template <int BN>
@@ -636,10 +785,8 @@ int tc_conv_forward(cudaStream_t st, const float* const* p, const float* obs, co
     a = GatherArgs{};
     tcg_plan_forward(e, 3, a.g, a.s);
     a.a_hi = w.y2[0]; a.a_lo = w.y2[1]; a.b_hi = w.wp3[0]; a.b_lo = w.wp3[1]; a.bias = p[5]; a.relu = 1;
-    a.out_hi = w.y3[0]; a.out_lo = w.y3[1]; a.out_plain = w.y3p; a.M = m3;
+    a.out_hi = w.y3[0]; a.out_lo = w.y3[1]; a.out_feat = feat; a.feat_P = e.h3 * e.w3; a.M = m3;     // flatten in the epilogue
     TRXL_PROPAGATE(launch_gather<64>(st, a));
-    nhwc_to_feat_kernel<<<grid_for(m3 * 64), 256, 0, st>>>(w.y3p, feat, N, e.h3 * e.w3);
-    TRXL_CHECK_LAUNCH("nhwc_to_feat");
     return TRXL_OK;
 }
 

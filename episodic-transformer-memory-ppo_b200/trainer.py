@@ -153,8 +153,12 @@ class PPOTrainer:
         self._obs_slab = None
         self._yield_when_idle = False
         self._control = None          # shared-memory stepping arrays (own workers only)
-        n_groups = int(os.environ.get("TRXL_ROLLOUT_GROUPS", "2" if (workers is None and self.num_workers >= 8 and
-                                                                      os.environ.get("TRXL_PIPE_STEPPING", "0") != "1") else "1"))
+        # worker groups overlap one group's env stepping with the others' forwards; the forwards are latency-bound (a group's
+        # kernels occupy a fraction of the GPU), so several groups' device work overlaps too (measured at c3, W = 32 on 16 host
+        # CPUs: rollout 215 ms with 2 groups, 161 with 3, 158 with 4)
+        own_stepping = workers is None and os.environ.get("TRXL_PIPE_STEPPING", "0") != "1"
+        default_groups = 1 if not own_stepping or self.num_workers < 8 else (2 if self.num_workers < 32 else 4)
+        n_groups = int(os.environ.get("TRXL_ROLLOUT_GROUPS", str(default_groups)))
         n_groups = max(1, min(n_groups, self.num_workers, 64))
         self._group_bounds = [round(i * self.num_workers / n_groups) for i in range(n_groups + 1)]
         group_of = [max(g for g in range(n_groups) if self._group_bounds[g] <= w) for w in range(self.num_workers)]
@@ -204,6 +208,7 @@ class PPOTrainer:
 
         # episode table + per-worker cursors
         self._table = None
+        self._table_roll = None         # rollout: table + positional rows, kept in step by memory_scatter_pe (fused forward only)
         self._table_cap = 0
         self._ep_host = torch.arange(W, dtype=torch.long).pin_memory()      # table row of each worker's live episode
         self._step_host = self.worker_current_episode_step.pin_memory()
@@ -283,6 +288,15 @@ class PPOTrainer:
             new[:self._table.shape[0]].copy_(self._table)
             torch.cuda.synchronize(self.device)
         self._table, self._table_cap = new, capacity
+        # the fused rollout forward prefetches window rows with bulk copies, which cannot add positional rows on the way: with a
+        # (parameter-free) positional table the rollout keeps a second table that already carries them
+        model = getattr(self, "model", None)
+        if model is not None and model._fused_ok and self.num_workers <= model.FUSED_MAX_BATCH and model._pe_table() is not None \
+                and os.environ.get("TRXL_ROLLOUT_TABLE_PE", "1") != "0":
+            # (rows no step has written yet must read as 0 + positional row: an episode's first step attends uniformly over them)
+            self._table_roll = torch.empty_like(new)
+            native.table_add_pe(new, model._pe_table(), self._table_roll, capacity)
+            torch.cuda.synchronize(self.device)
 
     @property
     def memory(self):
@@ -305,6 +319,8 @@ class PPOTrainer:
         self._ep_dev.copy_(self._ep_host, non_blocking=True)
         self._n_rows = W
         self._n_episodes = W
+        if self._table_roll is not None:                 # every row with its positional row (fresh rows: 0 + pe); the rollout
+            native.table_add_pe(self._table, self.model._pe_table(), self._table_roll, self._table_cap)     # then writes slot by slot
 
     # ------------------------------------------------------------------------------------------ training loop
     def run_training(self):
@@ -386,7 +402,8 @@ class PPOTrainer:
     #    replayed, which removes the host launch overhead that otherwise dominates a W=32 forward.
     def _graph_key(self, mode):
         forced = self._forced_buf.data_ptr() if self._forced_on else 0
-        return (mode, self._table.data_ptr(), self.model.flat_parameters().data_ptr(), forced)
+        roll = 0 if self._table_roll is None else self._table_roll.data_ptr()
+        return (mode, self._table.data_ptr(), roll, self.model.flat_parameters().data_ptr(), forced)
 
     def _step_via_graph(self, mode, grp, t, src):
         """Enqueue step t of worker group ``grp`` on the current stream, as a CUDA-graph replay when possible."""
@@ -464,15 +481,20 @@ class PPOTrainer:
                                ctx["flat_mask"].data_ptr() + row0 * L, T * L, ctx["flat_idx"].data_ptr() + row0 * L * 8, T * L,
                                ctx["flat_ep"].data_ptr() + row0 * 8, T, n, L)
         feat = model.encode(obs_dev, weights_packed=grp.enc_packed, slot=grp.index)
-        logits, value, new_mem = model.forward_table(feat, self._table, ctx["flat_ep"], ctx["flat_idx"], ctx["flat_mask"],
-                                                     ctx["flat_idx"], sample_index=grp.rows[t], n=n, ws=grp.ws, out=grp.outs)
-        native.memory_scatter(self._table, ep_dev, step_dev, new_mem, self.max_episode_length, ctx["inner"])
+        roll = self._table_roll       # with it, window rows come from the table that already carries the positional rows
+        logits, value, new_mem = model.forward_table(feat, self._table if roll is None else roll, ctx["flat_ep"], ctx["flat_idx"],
+                                                     ctx["flat_mask"], ctx["flat_idx"] if roll is None else None,
+                                                     sample_index=grp.rows[t], n=n, ws=grp.ws, out=grp.outs,
+                                                     fused=None if roll is None else True)
+        # table[ep, step] = new memory (trainer.py:174), the same into `roll`, buffer.values[:, t] = value (trainer.py:186)
+        native.rollout_store(self._table, roll, None if roll is None else model._pe_table(), ep_dev, step_dev, new_mem,
+                             self.max_episode_length, self.num_blocks, self.embed_dim, value=value,
+                             value_dst=buf.values.data_ptr() + row0 * 4, value_stride=T)
         forced = None if self._forced_actions is None else self._forced_actions[t, lo:grp.hi]
         native.sample_actions(logits, ctx["uniforms"][t, lo:grp.hi], self.action_space_shape,
                               buf.actions.data_ptr() + row0 * nb * 8, T * nb, buf.log_probs.data_ptr() + row0 * nb * 4, T * nb,
                               grp.act_host_dptr if on_host else grp.act_dev, n, forced=forced,      # actions land in host memory
                               notify=(grp.done_counter, grp.done_flag_dptr) if (on_host and grp.use_flag) else None)
-        native.copy_rows(value.data_ptr(), buf.values.data_ptr() + row0 * 4, n, 4, 4, T * 4)
 
     def _host_src(self, grp, host_obs):
         """Device-side addresses of this group's slices of the pinned host buffers (observations, cursors)."""

@@ -88,6 +88,7 @@ SIGNATURES = {
     "trxl_gae": (i32, [vp, vp, vp, vp, vp, i32, i32, f64, f64, vp]),
     "trxl_rollout_prepare": (i32, [vp, vp, vp, vp, vp, i64, vp, i64, vp, i64, i32, i32, vp]),
     "trxl_memory_scatter": (i32, [vp, vp, vp, vp, i32, i64, i64, vp]),
+    "trxl_rollout_store": (i32, [vp, vp, vp, vp, vp, vp, i32, i64, i32, i32, vp, vp, i64, vp]),
     "trxl_rollout_fetch": (i32, [vp, i64, vp, vp, vp, vp, i64, vp, vp, i32, vp]),
     "trxl_host_device_pointer": (i32, [vp, C.POINTER(C.c_void_p)]),
     "trxl_sample_actions": (i32, [vp, vp, vp, C.POINTER(C.c_int32), i32, vp, i64, vp, i64, vp, i32, vp]),
@@ -432,6 +433,14 @@ def host_device_pointer(host_ptr):
 def memory_scatter(table, ep, step, new_mem, slots, inner):
     _check(load().trxl_memory_scatter(_p(table), _p(ep), _p(step), _p(new_mem), ep.shape[0], int(slots), int(inner), _stream()),
            "trxl_memory_scatter")
+
+
+def rollout_store(table, table_pe, pe_table, ep, step, new_mem, slots, blocks, dim, value=None, value_dst=0, value_stride=0):
+    """End-of-step stores in one kernel: memory rows into `table` (and, with their positional rows, into `table_pe` if given) and
+    `value` into the rollout buffer (`value_dst`: raw device address of the first worker's slot, stride in floats)."""
+    _check(load().trxl_rollout_store(_p(table), _p(table_pe), _p(pe_table), _p(ep), _p(step), _p(new_mem), ep.shape[0], int(slots),
+                                     int(blocks), int(dim), _p(value), int(value_dst) or None, int(value_stride),
+                                     _stream()), "trxl_rollout_store")
 
 
 def sample_actions(logits, u, branch_sizes, act_ptr, act_stride, logp_ptr, logp_stride, act_compact, w, forced=None, notify=None):

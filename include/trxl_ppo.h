@@ -110,7 +110,8 @@ int trxl_fused_forward_supported(const trxl_model_config* cfg);
  *   pe_table    (max_episode_steps, D) for TRXL_PE_RELATIVE (host-built sinusoid), else NULL
  * Outputs: logits (N, sum A) raw, value (N,), out_mem (N, B, D) = inputs of every block.
  * workspace == NULL selects the fused inference path (see trxl_fused_forward_supported); it saves no
- * activations, so trxl_model_backward cannot follow it. */
+ * activations, so trxl_model_backward cannot follow it.  On that path pe_index == NULL means that `table` already carries
+ * the positional rows (see trxl_rollout_store): no positional add, and the window rows are prefetched block by block. */
 int trxl_model_forward(const trxl_model_config* cfg, const float* params, const float* feat, const float* table,
                        int64_t slots, const int64_t* ep_index, const int64_t* win_index, const uint8_t* mask,
                        const int64_t* pe_index, const int64_t* sample_index, const float* pe_table, int N,
@@ -204,6 +205,14 @@ int trxl_host_device_pointer(const void* host_ptr, void** device_ptr_out);
 /* trainer.py:174: table[ep[w], step[w]] = new_mem[w] (inner = B*D floats) */
 int trxl_memory_scatter(float* table, const int64_t* ep, const int64_t* step, const float* new_mem, int W, int64_t slots,
                         int64_t inner, void* stream);
+/* The stores that end a rollout step in ONE kernel: the scatter above (trainer.py:174); if table_pe != NULL also
+ * table_pe[ep[w], step[w], b, :] = new_mem[w, b, :] + pe_table[step[w], :] -- a second table that already carries the positional
+ * rows (transformer.py:213-214 adds them to every window row of every forward), kept in step with the first, which
+ * trxl_model_forward's inference path reads with pe_index == NULL (its window rows then come in by bulk async copies); and if
+ * value_dst != NULL value_dst[w * value_stride] = value[w] (trainer.py:186: buffer.values[:, t] = value). */
+int trxl_rollout_store(float* table, float* table_pe, const float* pe_table, const int64_t* ep, const int64_t* step,
+                       const float* new_mem, int W, int64_t slots, int blocks, int dim, const float* value, float* value_dst,
+                       int64_t value_stride, void* stream);
 /* trainer.py:177-186: sample each branch from softmax(logits) with caller-supplied uniforms u (W, nb)
  * (inverse CDF); if forced_actions (W, nb) != NULL those actions are taken instead (trajectory replay)
  * and only their log-probabilities are computed. */

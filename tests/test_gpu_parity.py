@@ -300,6 +300,14 @@ def test_forward_backward_c3_dims_vs_oracle(n, ln, pe, gtrxl, dims):
             np.testing.assert_allclose(fval.cpu().numpy(), value.detach().numpy(), atol=1e-4)
             np.testing.assert_allclose(fmem.cpu().numpy(), new_mem.detach().numpy(), atol=1e-4)
             np.testing.assert_allclose(flg.cpu().numpy(), logits[0].detach().numpy(), atol=1e-4)
+            # the rollout's form: window rows prefetched by bulk copies from a table that already carries the positional rows
+            # (pe_index = None) -- the same fp32 additions in a different kernel, so the result is bit-identical
+            if model._pe_table() is not None:
+                import trxl_native as native
+                table_pe = torch.empty_like(dev(table))
+                native.table_add_pe(dev(table), model._pe_table(), table_pe, n_eps)
+                plg, pval, pmem = model.forward_table(dev(obs), table_pe, dev(ep), dev(idx), dev(mask.to(torch.uint8)), None, fused=True)
+                assert torch.equal(plg, flg) and torch.equal(pval, fval) and torch.equal(pmem, fmem)
         # layered path (saves activations for the backward below)
         lg, val, mem = model.forward_table(dev(obs), dev(table), dev(ep), dev(idx), dev(mask.to(torch.uint8)), dev(idx), fused=False)
     np.testing.assert_allclose(val.cpu().numpy(), value.detach().numpy(), atol=1e-4)
@@ -397,3 +405,34 @@ def test_learns_the_memory_task(tmp_path, monkeypatch):
     # 10-update window, far above the ~0.4 success of the untrained policy
     best = max(np.mean(success[i:i + 10]) for i in range(len(success) - 9))
     assert np.mean(success[:2]) < 0.7 and best >= 0.95, [round(float(x), 2) for x in success]
+
+
+@pytest.mark.gpu
+def test_rollout_store_keeps_both_tables_in_step():
+    """trxl_rollout_store writes the new memory rows into the table (trainer.py:174), the same rows plus their slot's positional
+    row into the second table the fused rollout forward reads (bit-exact: one fp32 add), and the values into column t of the
+    rollout buffer (trainer.py:186)."""
+    import trxl_native as native
+    torch.manual_seed(3)
+    E, M, B, D, W, T = 9, 20, 3, 64, 5, 7
+    table = torch.randn(E, M, B, D, device=DEV)
+    table_pe = torch.randn(E, M, B, D, device=DEV)
+    pe = torch.randn(M, D, device=DEV)
+    ep = torch.tensor([4, 0, 8, 2, 6], device=DEV)
+    step = torch.tensor([0, 19, 7, 7, 3], device=DEV)
+    new_mem = torch.randn(W, B, D, device=DEV)
+    value = torch.randn(W, device=DEV)
+    values = torch.zeros(W, T, device=DEV)
+    want, want_pe, want_values = table.clone(), table_pe.clone(), values.clone()
+    want[ep, step] = new_mem
+    want_pe[ep, step] = new_mem + pe[step].unsqueeze(1)
+    want_values[:, 4] = value
+    native.rollout_store(table, table_pe, pe, ep, step, new_mem, M, B, D, value=value, value_dst=values.data_ptr() + 4 * 4, value_stride=T)
+    torch.cuda.synchronize()
+    assert torch.equal(table, want) and torch.equal(table_pe, want_pe) and torch.equal(values, want_values)
+    table2 = torch.randn(E, M, B, D, device=DEV)
+    want2 = table2.clone()
+    want2[ep, step] = new_mem
+    native.rollout_store(table2, None, None, ep, step, new_mem, M, B, D)
+    torch.cuda.synchronize()
+    assert torch.equal(table2, want2)
