@@ -22,6 +22,8 @@
 // tables (gradients flow into the rows) stay on the per-sample kernel (attention.cu).
 #include "attention_tc.cuh"
 
+#include <stdlib.h>
+
 #include "gemm.cuh"
 
 int trxl_tc_gemm(const GemmArgs& g, int bn, cudaStream_t st);      // tc_gemm.cu
@@ -213,6 +215,9 @@ int attn_tc_forward(const AttnTcArgs& a, const float* qk, float* P, float* ctx, 
     trxl_prof_begin(2, a.N, st);
     trxl_prof_aux(2, a.n_tiles);
     TRXL_PROPAGATE(trxl_tc_gemm(g1, tile_n((int)a.slots), st));
+    // (a masked softmax fused into this GEMM's epilogue -- straight from the TMEM accumulators, row halves exchanged between the two
+    // warps of a lane quarter -- was measured SLOWER, 83.5 vs 76.3 us per forward on the same box: a CTA's 8 epilogue warps
+    // serialise what this kernel spreads over the whole GPU; likewise for the dscore pass, 108 vs 71 us)
     attn_softmax_kernel<<<trxl_cdiv(rows, 8), 256, 0, st>>>(P, ld, (int)a.slots, a.ranges, a.H, rows, a.scale, a.L);
     TRXL_CHECK_LAUNCH("attention_softmax");
     GemmArgs g2 = grouped_args(a, P, ld, (int)a.slots, a.D, 0, ctx, a.D);               // ctx = P . Xpe      (B MN-major: k = slot)

@@ -440,9 +440,22 @@ int trxl_gemm(GemmArgs g, cudaStream_t st) {
                 t.ksplit = (t.K + t.k_per_split - 1) / t.k_per_split;
             }
         }
+        // up to 8 splits: the CTAs of a tile form a cluster and reduce through distributed shared memory -- no workspace round
+        // trip and no reduce kernel (TRXL_TC_CLUSTER_SPLITK=0: workspace + splitk_reduce_kernel as for the SIMT path)
+        static int cluster_off = -1;
+        if (cluster_off < 0) { const char* e = getenv("TRXL_TC_CLUSTER_SPLITK"); cluster_off = (e && atoi(e) == 0) ? 1 : 0; }
+        if (!cluster_off && t.K >= 256 && tc_tiles * 2 <= 148 && bn <= 128) {
+            int s = (int)((148 + tc_tiles - 1) / tc_tiles);
+            s = s >= 8 ? 8 : (s >= 4 ? 4 : 2);
+            while (s > 1 && t.K / s < 64) s >>= 1;
+            if (s > 1) {
+                t.k_per_split = ((t.K + s - 1) / s + 31) / 32 * 32;
+                if ((t.K + t.k_per_split - 1) / t.k_per_split == s) { t.ksplit = s; t.cluster_reduce = 1; }
+            }
+        }
         rc = trxl_tc_gemm(t, bn, st);
         if (rc != TRXL_ERR_UNSUPPORTED) {
-            if (rc != TRXL_OK || t.ksplit == 1) return rc;
+            if (rc != TRXL_OK || t.ksplit == 1 || t.cluster_reduce) return rc;
             const long long total_t = (long long)t.M * t.N * t.batch;
             splitk_reduce_kernel<<<trxl_cdiv(total_t, 256), 256, 0, st>>>(t);
             TRXL_CHECK_LAUNCH("splitk_reduce");

@@ -15,6 +15,8 @@ struct GemmArgs {
     float* ws = nullptr; long long ws_floats = 0;   // optional split-K workspace
     int vecA = 0, vecB = 0, ksplit = 1, k_per_split = 0;   // filled by trxl_gemm
     int debug = 0;                        // TRXL_TC_DEBUG bitmask (timing experiments only; results are wrong when set)
+    int cluster_reduce = 0;               // tensor-core path: the ksplit (2, 4 or 8) CTAs of a tile form a cluster and sum their
+                                          // partials through distributed shared memory (no workspace, no reduce kernel)
     // grouped mode (tensor-core path only): output row tile t covers rows [tiles[t].x, +tiles[t].y) of A / C and multiplies
     // with batch element tiles[t].z of B (b_batch of them, stride sB).  grid.y = n_tiles; batch must be 1.
     const int4* tiles = nullptr; int n_tiles = 0; int b_batch = 1;

@@ -1,6 +1,14 @@
 // tcgen05 / TMEM / mbarrier / cp.async primitives shared by the sm_100a tensor-core kernels (inline PTX).
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
+
+// Cached rank-3 tensor map {inner (contiguous), outer (stride ld floats), batch (stride sb floats)} over a row-major fp32 operand,
+// box {32, box_outer, 1}; mn = 1: MN-major operand (SWIZZLE_128B_ATOM_32B), else K-major (SWIZZLE_128B).  Defined in tc_gemm.cu;
+// TRXL_ERR_UNSUPPORTED when the driver entry point is missing or the encoder refuses the shape.
+int trxl_tensor_map(const float* base, long long inner, long long outer, long long batch, long long ld, long long sb, int box_outer,
+                    int mn, CUtensorMap* out);
 
 namespace tc {
 
@@ -115,5 +123,31 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---- thread-block clusters ----
+__device__ __forceinline__ void cluster_sync_all() {     // every thread of every CTA of the cluster
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 16 bytes from the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ float4 ld_peer_f4(uint32_t local_addr, uint32_t cta) {
+    uint32_t remote;
+    float4 v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(cta));
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote) : "memory");
+    return v;
+}
+
+// ---- TMA (bulk tensor copies) ----
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
 
 }  // namespace tc

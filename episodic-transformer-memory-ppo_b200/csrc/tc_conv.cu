@@ -45,6 +45,8 @@ struct GatherArgs {
     const float* a_hi; const float* a_lo;       // gathered image, pre-split
     const long long* sample_index;              // optional: image n of the row grid reads image sample_index[n]
     const float* b_hi; const float* b_lo;       // weights [BN][K], pre-split
+    CUtensorMap tb_hi, tb_lo;                   // ... and their tensor maps (box {32 k, BN rows}, SWIZZLE_128B) when use_tma
+    int use_tma;
     const float* bias;                          // [BN] or null
     int relu;
     const float* mask;                          // optional image with the output geometry: result kept where mask > 0
@@ -85,18 +87,6 @@ __device__ __forceinline__ void load_accumulators(uint32_t taddr, uint32_t (&v)[
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// cluster helpers (split-K: the CTAs of a cluster hold partial sums of the same 128-row tile)
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ float4 ld_peer_f4(uint32_t local_addr, uint32_t cta) {
-    uint32_t remote;
-    float4 v;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(cta));
-    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote) : "memory");
-    return v;
-}
-
 // grid (row tiles, KS); with KS > 1 the launch carries cluster dims (1, KS, 1): CTA (tile, kq) accumulates k-blocks
 // [kq nkb / KS, (kq + 1) nkb / KS) of the tile -- rollout-sized problems have fewer row tiles than SMs and are bound by one SM's
 // copy-issue rate (measured: ~1.3 k clocks per k-block whatever the number of producer warps), so the k-blocks are spread over
@@ -149,9 +139,11 @@ __global__ void __launch_bounds__((PW + 1) * 32, STAGES == 2 ? 2 : 1) tc_conv_ga
         }
     }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], PW * 32); mbar_init(&empty[s], 1); }
+        // `full`: one cp.async arrival per producer thread, plus (TMA weights) the arrive that announces the tile bytes
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], PW * 32 + (a.use_tma ? 1 : 0)); mbar_init(&empty[s], 1); }
         mbar_init(tmem_full, 1);
         mbar_init_fence();
+        if (a.use_tma) { prefetch_tmap(&a.tb_hi); prefetch_tmap(&a.tb_lo); }
     }
     if (warp == PW) tmem_alloc(tmem_slot, tmem_cols(BN));
     fence_before_sync();
@@ -189,12 +181,23 @@ __global__ void __launch_bounds__((PW + 1) * 32, STAGES == 2 ? 2 : 1) tc_conv_ga
                 cp_async16(dst + i * (RSTEP * 128), a.a_hi + off, nbytes);
                 cp_async16(dst + A_BYTES + i * (RSTEP * 128), a.a_lo + off, nbytes);
             }
-            const long long boff = (long long)r0 * K + kb * BK + piece * 4;
-            const uint32_t dstb = smem_base + s * STAGE_BYTES + 2 * A_BYTES + dst0;
+            if (a.use_tma) {
+                // the weight tile is a plain 2-D box: one elected thread hands it to the TMA unit (no LSU copy slots -- the
+                // gathered rows are bound by the 16-byte copy-issue rate, measured ~13 clocks per warp instruction)
+                if (threadIdx.x == 0) {
+                    const uint32_t bdst = smem_base + s * STAGE_BYTES + 2 * A_BYTES;
+                    mbar_arrive_expect_tx(&full[s], 2 * B_BYTES);
+                    tma_load_3d(bdst, &a.tb_hi, &full[s], kb * BK, 0, 0);
+                    tma_load_3d(bdst + B_BYTES, &a.tb_lo, &full[s], kb * BK, 0, 0);
+                }
+            } else {
+                const long long boff = (long long)r0 * K + kb * BK + piece * 4;
+                const uint32_t dstb = smem_base + s * STAGE_BYTES + 2 * A_BYTES + dst0;
 #pragma unroll
-            for (int i = 0; i < BN / RSTEP; ++i) {
-                cp_async16(dstb + i * (RSTEP * 128), a.b_hi + boff + (long long)i * RSTEP * K, 16u);
-                cp_async16(dstb + B_BYTES + i * (RSTEP * 128), a.b_lo + boff + (long long)i * RSTEP * K, 16u);
+                for (int i = 0; i < BN / RSTEP; ++i) {
+                    cp_async16(dstb + i * (RSTEP * 128), a.b_hi + boff + (long long)i * RSTEP * K, 16u);
+                    cp_async16(dstb + B_BYTES + i * (RSTEP * 128), a.b_lo + boff + (long long)i * RSTEP * K, 16u);
+                }
             }
             cp_async_arrive(&full[s]);           // fires when this thread's copies of the stage have landed; nobody waits
             if (tracing && threadIdx.x == 0 && it < 36) a.trace[2 + it] = clock64();
@@ -642,6 +645,13 @@ int launch_gather_stages(cudaStream_t st, const GatherArgs& a) {
         tracing = e && atoi(e) > 0 && cap == cudaStreamCaptureStatusNone;
     }
     GatherArgs b = a;
+    {
+        static int tma_off = -1;                 // TRXL_CONV_TMA=0: weight tiles through cp.async like the gathered rows
+        if (tma_off < 0) { const char* e = getenv("TRXL_CONV_TMA"); tma_off = (e && atoi(e) == 0) ? 1 : 0; }
+        const long long K = (long long)a.g.nkb * BK;
+        b.use_tma = !tma_off && trxl_tensor_map(a.b_hi, K, BN, 1, K, 0, BN, 0, &b.tb_hi) == TRXL_OK &&
+                    trxl_tensor_map(a.b_lo, K, BN, 1, K, 0, BN, 0, &b.tb_lo) == TRXL_OK;
+    }
     if (tracing) {
         if (!trace_dev) cudaMalloc(&trace_dev, 96 * sizeof(long long));
         cudaMemsetAsync(trace_dev, 0, 96 * sizeof(long long), st);

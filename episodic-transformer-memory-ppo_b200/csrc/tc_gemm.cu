@@ -57,24 +57,12 @@ struct TmaGemmParams {
     GemmArgs g;
 };
 
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
 // ask the TMA unit to pull a box into L2 (no shared-memory destination, no barrier): issued a few k-blocks ahead of the stage
 // ring so that the ring's own loads find their rows in L2 instead of paying the DRAM round trip with only 2-5 stages in flight
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
                  ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-
 // 32 lanes x 32 consecutive fp32 accumulator columns, no wait (the caller waits once for all three accumulators)
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -274,6 +262,19 @@ __global__ void __launch_bounds__(TM_THREADS, 1) tma_gemm_kernel(const __grid_co
         fence_after_sync();
         const int quarter = warp & 3;
         const int m = m0 + quarter * 32 + lane;
+        if (BN <= 128 && g.cluster_reduce) {
+            // ---- split-K inside a cluster, part 1: this CTA's partial tile parked in its (now idle) stage ring ----
+            constexpr int PSTRIDE = BN + 4;
+            static_assert(TM_BM * PSTRIDE * 4 <= STAGES * STAGE_BYTES, "a parked tile must fit the stage ring");
+            float* prow = reinterpret_cast<float*>(tiles) + (quarter * 32 + lane) * PSTRIDE;
+#pragma unroll 1
+            for (int j = warp >> 2; j < BN / 32; j += TM_CONV_WARPS / 4) {
+                float v[32];
+                load_accumulators3<BN>(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * 32), v);
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(prow + j * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+        } else {
         float* __restrict__ C = g.C + (long long)b * g.sC;
         const float* __restrict__ bias = g.bias ? g.bias + (long long)b * g.sBias : nullptr;
         const float* __restrict__ R = g.R ? g.R + (long long)b * g.sR : nullptr;
@@ -325,10 +326,65 @@ __global__ void __launch_bounds__(TM_THREADS, 1) tma_gemm_kernel(const __grid_co
                 }
             }
         }
+        }
     }
     fence_before_sync();
     __syncthreads();
     if (warp == TM_MMA_WARP) tmem_dealloc(tmem_base, tm_tmem_cols(BN));
+    if constexpr (BN <= 128) if (g.cluster_reduce) {
+        // ---- part 2: CTA `split` sums the ksplit partials of rows [split 128 / ksplit, ...) in split order through distributed
+        //      shared memory and runs the epilogue on them; thread = (row, 1/8 of the columns): coalesced row stores ----
+        cluster_sync_all();
+        if (warp < TM_CONV_WARPS) {
+            constexpr int PSTRIDE = BN + 4, CPT = BN / 8;
+            const int ks = g.ksplit, rows_mine = TM_BM / ks, row_lo = split * rows_mine;
+            const int c0 = (threadIdx.x & 7) * CPT;
+            const uint32_t park_addr = smem_u32(tiles);
+            float* __restrict__ C = g.C + (long long)b * g.sC;
+            const float* __restrict__ bias = g.bias ? g.bias + (long long)b * g.sBias : nullptr;
+            const float* __restrict__ R = g.R ? g.R + (long long)b * g.sR : nullptr;
+            for (int rl = threadIdx.x >> 3; rl < rows_mine; rl += TM_CONV_WARPS * 4) {
+                const int r = row_lo + rl, m = m0 + r;
+                float x[CPT];
+#pragma unroll
+                for (int q = 0; q < CPT; ++q) x[q] = 0.f;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {             // four peers' loads in flight at a time
+                    float4 p4[4][CPT / 4];
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; ++s4) {
+                        const int src = half * 4 + s4;
+#pragma unroll
+                        for (int q = 0; q < CPT; q += 4) {
+                            p4[s4][q / 4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (src < ks) p4[s4][q / 4] = ld_peer_f4(park_addr + (uint32_t)((r * PSTRIDE + c0 + q) * 4), (uint32_t)src);
+                        }
+                    }
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; ++s4) {
+                        if (half * 4 + s4 >= ks) break;
+#pragma unroll
+                        for (int q = 0; q < CPT; q += 4) {
+                            x[q] += p4[s4][q / 4].x; x[q + 1] += p4[s4][q / 4].y; x[q + 2] += p4[s4][q / 4].z; x[q + 3] += p4[s4][q / 4].w;
+                        }
+                    }
+                }
+                if (m >= m_end) continue;
+#pragma unroll
+                for (int q = 0; q < CPT; ++q) {
+                    const int n = n0 + c0 + q;
+                    if (n >= g.N) continue;
+                    float v = x[q] * g.alpha;
+                    if (bias) v += __ldg(bias + n);
+                    if (g.relu) v = fmaxf(v, 0.f);
+                    if (R) v += R[(long long)m * g.ldr + n];
+                    if (g.accumulate) v += C[(long long)m * g.ldc + n];
+                    C[(long long)m * g.ldc + n] = v;
+                }
+            }
+        }
+        cluster_sync_all();                      // nobody leaves while a peer may still read its parked tile
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -412,7 +468,18 @@ int launch_tma(const TmaGemmParams& p, cudaStream_t st) {
     }
     const GemmArgs& g = p.g;
     dim3 grid(trxl_cdiv(g.N, BN), g.tiles ? g.n_tiles : trxl_cdiv(g.M, TM_BM), g.batch * g.ksplit);
-    tma_gemm_kernel<BN, A_MN, B_MN><<<grid, TM_THREADS, smem, st>>>(p);
+    if (g.cluster_reduce) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = dim3(TM_THREADS, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = g.ksplit;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t le = cudaLaunchKernelEx(&cfg, tma_gemm_kernel<BN, A_MN, B_MN>, p);
+        if (le != cudaSuccess) { trxl_set_error("tma_gemm: cluster launch failed: %s", cudaGetErrorString(le)); return TRXL_ERR_CUDA; }
+    } else {
+        tma_gemm_kernel<BN, A_MN, B_MN><<<grid, TM_THREADS, smem, st>>>(p);
+    }
     ++g_trxl_tc_launches;
     TRXL_CHECK_LAUNCH("tma_gemm");
     return TRXL_OK;
@@ -428,6 +495,11 @@ int launch_orient(const TmaGemmParams& p, cudaStream_t st) {
 }
 
 }  // namespace
+
+int trxl_tensor_map(const float* base, long long inner, long long outer, long long batch, long long ld, long long sb, int box_outer,
+                    int mn, CUtensorMap* out) {
+    return get_map(base, inner, outer, batch, ld, sb, box_outer, mn, out);
+}
 
 // Can the TMA path take these operands?  (16-byte aligned bases, leading dimensions / batch strides in whole 16-byte units)
 bool trxl_tc_gemm_eligible(const GemmArgs& g) {
@@ -455,6 +527,8 @@ int trxl_tc_gemm_tile_n(const GemmArgs& g) {
 
 // Returns TRXL_ERR_UNSUPPORTED (without launching anything) if a tensor map cannot be encoded; the caller then uses the SIMT path.
 int trxl_tc_gemm(const GemmArgs& g, int bn, cudaStream_t st) {
+    TRXL_CHECK_ARG(!g.cluster_reduce || ((g.ksplit == 2 || g.ksplit == 4 || g.ksplit == 8) && bn <= 128 && !g.tiles),
+                   "tc_gemm: cluster split-K takes 2, 4 or 8 splits of a plain GEMM with tiles up to 128 wide");
     TmaGemmParams p;
     p.g = g;
     static int debug = -1;

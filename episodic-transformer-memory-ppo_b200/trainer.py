@@ -155,9 +155,9 @@ class PPOTrainer:
         self._control = None          # shared-memory stepping arrays (own workers only)
         # worker groups overlap one group's env stepping with the others' forwards; the forwards are latency-bound (a group's
         # kernels occupy a fraction of the GPU), so several groups' device work overlaps too (measured at c3, W = 32 on 16 host
-        # CPUs: rollout 215 ms with 2 groups, 161 with 3, 158 with 4)
+        # CPUs: rollout 215 ms with 2 groups, 161 with 3, 158 with 4, 146 with 6, 149 with 8)
         own_stepping = workers is None and os.environ.get("TRXL_PIPE_STEPPING", "0") != "1"
-        default_groups = 1 if not own_stepping or self.num_workers < 8 else (2 if self.num_workers < 32 else 4)
+        default_groups = 1 if not own_stepping or self.num_workers < 8 else min(6, self.num_workers // 4)
         n_groups = int(os.environ.get("TRXL_ROLLOUT_GROUPS", str(default_groups)))
         n_groups = max(1, min(n_groups, self.num_workers, 64))
         self._group_bounds = [round(i * self.num_workers / n_groups) for i in range(n_groups + 1)]
