@@ -466,7 +466,7 @@ int trxl_sample_actions(const float* logits, const float* u, const int64_t* forc
 int trxl_sample_actions_notify(const float* logits, const float* u, const int64_t* forced_actions, const int32_t* branch_sizes,
                                int num_branches, int64_t* actions, int64_t act_stride, float* log_probs, int64_t logp_stride,
                                int64_t* actions_compact, int W, int64_t* done_counter, int64_t* done_flag, void* stream) {
-    TRXL_CHECK_ARG(logits && (u || forced_actions) && actions && log_probs && done_counter && done_flag, "sample_actions_notify: null pointer");
+    TRXL_CHECK_ARG(logits && (u || forced_actions) && actions && log_probs && done_counter && actions_compact, "sample_actions_notify: null pointer");
     BranchSpec bs;
     int sumA = 0;
     TRXL_PROPAGATE(branch_spec(branch_sizes, num_branches, bs, &sumA));

@@ -167,7 +167,7 @@ __global__ void rollout_fetch_scalar_kernel(const float* __restrict__ obs_src, l
 __device__ __forceinline__ void sample_one(const float* __restrict__ logits, int sumA, const float* __restrict__ u,
                                            const long long* __restrict__ forced, const BranchSpec& bs, long long* __restrict__ act_out,
                                            long long act_stride, float* __restrict__ logp_out, long long logp_stride,
-                                           long long* __restrict__ act_compact, int W, int i) {
+                                           long long* __restrict__ act_compact, int W, int i, long long tag = 0) {
     if (i >= W * bs.n) return;
     const int w = i / bs.n, k = i % bs.n;
     const float* z = logits + (long long)w * sumA + bs.off[k];
@@ -190,7 +190,7 @@ __device__ __forceinline__ void sample_one(const float* __restrict__ logits, int
     }
     act_out[w * act_stride + k] = a;
     logp_out[w * logp_stride + k] = z[a] - lse;
-    if (act_compact) act_compact[i] = a;
+    if (act_compact) act_compact[i] = tag | (long long)a;
 }
 
 __global__ void sample_actions_kernel(const float* __restrict__ logits, int sumA, const float* __restrict__ u,
@@ -198,17 +198,21 @@ __global__ void sample_actions_kernel(const float* __restrict__ logits, int sumA
                                       long long logp_stride, long long* __restrict__ act_compact, int W,
                                       long long* __restrict__ done_counter, volatile long long* __restrict__ done_flag) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (done_flag) {
-        // single-block launches only (checked by the host wrapper): once every action of the step is in (pinned host) memory,
-        // publish a launch sequence number the host can poll without a CUDA call
-        sample_one(logits, sumA, u, forced, bs, act_out, act_stride, logp_out, logp_stride, act_compact, W, i);
-        __threadfence_system();
-        __syncthreads();
+    if (done_counter) {
+        // single-block launches only (checked by the host wrapper).  Every compact action word carries the launch sequence number
+        // in its upper half: word = seq << 32 | action.  A host that polls the words themselves (8-byte stores are single-copy
+        // atomic) needs no flag behind a system-wide fence -- two of those cost ~12 us of a 17 us kernel when the words live in
+        // pinned host memory (measured).  done_flag, if given, is still published behind fences.
+        const long long seq = *done_counter + 1;
+        sample_one(logits, sumA, u, forced, bs, act_out, act_stride, logp_out, logp_stride, act_compact, W, i, seq << 32);
+        if (done_flag) __threadfence_system();
+        __syncthreads();                          // every thread has read the counter
         if (threadIdx.x == 0) {
-            const long long seq = *done_counter + 1;
             *done_counter = seq;
-            __threadfence_system();
-            *done_flag = seq;
+            if (done_flag) {
+                __threadfence_system();
+                *done_flag = seq;
+            }
         }
         return;
     }
@@ -471,9 +475,10 @@ int ppo_sample_actions(cudaStream_t st, const float* logits, int sumA, const flo
                        long long act_stride, float* logp_out, long long logp_stride, long long* act_compact, int W,
                        long long* done_counter, long long* done_flag) {
     if (W == 0) return TRXL_OK;
-    TRXL_CHECK_ARG(!done_flag || (done_counter && W * bs.n <= 1024), "sample_actions: the completion flag needs a counter and W * branches <= 1024");
-    const int threads = done_flag ? ((W * bs.n + 31) / 32 * 32) : 128;
-    sample_actions_kernel<<<done_flag ? 1 : trxl_cdiv(W * bs.n, 128), threads, 0, st>>>(logits, sumA, u, forced, bs, act_out, act_stride, logp_out,
+    TRXL_CHECK_ARG(!done_flag || done_counter, "sample_actions: the completion flag needs a counter");
+    TRXL_CHECK_ARG(!done_counter || W * bs.n <= 1024, "sample_actions: sequence-tagged actions need W * branches <= 1024");
+    const int threads = done_counter ? ((W * bs.n + 31) / 32 * 32) : 128;
+    sample_actions_kernel<<<done_counter ? 1 : trxl_cdiv(W * bs.n, 128), threads, 0, st>>>(logits, sumA, u, forced, bs, act_out, act_stride, logp_out,
                                                                    logp_stride, act_compact, W, done_counter, done_flag);
     TRXL_CHECK_LAUNCH("sample_actions");
     return TRXL_OK;

@@ -553,15 +553,25 @@ __global__ void colsum_final_kernel(const float* __restrict__ partial, int block
     for (int b = 0; b < blocks; ++b) t += partial[(long long)b * BN + col];
     out[col] = t;
 }
-// dW (reference layout) = sum over the row splits of the partial [K][BN] tiles
+// dW (reference layout) = sum over the row splits of the partial [K][BN] tiles.  A block owns 32 consecutive outputs; its eight
+// warps sum splits w, w + 8, ... (coalesced rows of the partial tiles) and the eight partial sums are added in warp order
+// (deterministic; conv1 has ~800 splits, which a single thread per output used to walk alone)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int K, int BN, int layer, int C, float* __restrict__ dw) {
-    const int total = K * BN;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    __shared__ float s_part[8][32];
+    const int total = K * BN, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 32 + lane;
+    float t = 0.f;
+    if (i < total)
+        for (int s = warp; s < splits; s += 8) t += partial[(long long)s * total + i];
+    s_part[warp][lane] = t;
+    __syncthreads();
+    if (warp == 0 && i < total) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += s_part[w][lane];
         const int k = i / BN, oc = i - k * BN;
-        float t = 0.f;
-        for (int s = 0; s < splits; ++s) t += partial[(long long)s * total + i];
         const int idx = tcg_wfwd_index(layer, C, oc, k);
-        if (idx >= 0) dw[idx] = t;
+        if (idx >= 0) dw[idx] = v;
     }
 }
 
@@ -715,7 +725,7 @@ int launch_wgrad(cudaStream_t st, WgradArgs a, int layer, int C, float* dw, cons
     a.partial = w.partial;
     tc_conv_wgrad_kernel<BN, STAGES><<<dim3(ktiles, splits), THREADS, smem, st>>>(a);
     TRXL_CHECK_LAUNCH("tc_conv_wgrad");
-    wgrad_reduce_kernel<<<grid_for((long long)K * BN), 256, 0, st>>>(w.partial, splits, K, BN, layer, C, dw);
+    wgrad_reduce_kernel<<<trxl_cdiv(K * BN, 32), 256, 0, st>>>(w.partial, splits, K, BN, layer, C, dw);
     TRXL_CHECK_LAUNCH("wgrad_reduce");
     return TRXL_OK;
 }

@@ -77,12 +77,11 @@ class _WorkerGroup:
         self.act_dev = torch.zeros((self.n, nb), dtype=torch.long, device=dev)
         self.act_pinned = torch.zeros((self.n, nb), dtype=torch.long).pin_memory()
         self.act_host_dptr = native.host_device_pointer(self.act_pinned.data_ptr())     # kernels write the actions here
-        # completion flag: the sampling kernel publishes a launch sequence number into pinned host memory, so the host polls a
-        # plain int64 instead of a CUDA event (W * branches <= 1024 per group, else the event is used)
+        self.act_np = self.act_pinned.numpy()
+        # completion signal: the sampling kernel tags every action word it writes into pinned host memory with a launch sequence
+        # number (word = seq << 32 | action), so the host polls plain int64s instead of a CUDA event and no system-wide fence sits
+        # on the step's critical path (W * branches <= 1024 per group, else the event is used)
         self.done_counter = torch.zeros(1, dtype=torch.long, device=dev)
-        self.done_flag = torch.zeros(1, dtype=torch.long).pin_memory()
-        self.done_flag_np = self.done_flag.numpy()
-        self.done_flag_dptr = native.host_device_pointer(self.done_flag.data_ptr())
         self.use_flag = self.n * nb <= 1024
         self.expected = 0
         self.stream_handle = self.stream.cuda_stream
@@ -494,7 +493,7 @@ class PPOTrainer:
         native.sample_actions(logits, ctx["uniforms"][t, lo:grp.hi], self.action_space_shape,
                               buf.actions.data_ptr() + row0 * nb * 8, T * nb, buf.log_probs.data_ptr() + row0 * nb * 4, T * nb,
                               grp.act_host_dptr if on_host else grp.act_dev, n, forced=forced,      # actions land in host memory
-                              notify=(grp.done_counter, grp.done_flag_dptr) if (on_host and grp.use_flag) else None)
+                              notify=(grp.done_counter, None) if (on_host and grp.use_flag) else None)    # seq-tagged action words
 
     def _host_src(self, grp, host_obs):
         """Device-side addresses of this group's slices of the pinned host buffers (observations, cursors)."""
@@ -541,7 +540,7 @@ class PPOTrainer:
             src = self._host_src(grp, self._stage_host_obs())
             self._step_via_graph("pipes", grp, t, src)
             stream.synchronize()
-            actions = grp.act_pinned.numpy()
+            actions = grp.act_np & 0xffffffff              # (the words carry a sequence tag in their upper half)
             te = time.perf_counter()
             for w, worker in enumerate(self.workers):
                 worker.child.send(("step", actions[w].copy()))
@@ -646,13 +645,16 @@ class PPOTrainer:
             for grp in groups:
                 lo, hi = grp.lo, grp.hi
                 if grp.phase == grp.GPU:
-                    if grp.use_flag:
-                        if grp.done_flag_np[0] < grp.expected:
+                    if grp.use_flag:         # every action word of the group carries this launch's sequence number
+                        if grp.act_np.min() < (grp.expected << 32):
                             continue
+                        now = time.perf_counter()
+                        acts[lo:hi] = grp.act_np & 0xffffffff
                     elif not grp.event.query():
                         continue
-                    now = time.perf_counter()
-                    acts[lo:hi] = grp.act_pinned.numpy()
+                    else:
+                        now = time.perf_counter()
+                        acts[lo:hi] = grp.act_np
                     cmd[lo:hi] += 1                       # publish last: the actions above are visible before the command
                     if futex_words is not None:           # one system call wakes the whole group
                         fwords[FUTEX_WORD_STRIDE * grp.index] += 1

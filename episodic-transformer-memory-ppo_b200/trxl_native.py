@@ -445,7 +445,8 @@ def rollout_store(table, table_pe, pe_table, ep, step, new_mem, slots, blocks, d
 
 def sample_actions(logits, u, branch_sizes, act_ptr, act_stride, logp_ptr, logp_stride, act_compact, w, forced=None, notify=None):
     """``act_compact``: (w, nb) int64 device tensor, or the raw device-side address of a mapped host buffer.
-    ``notify`` = (device counter tensor, device-side address of a pinned host int64): completion flag for host polling."""
+    ``notify`` = (device counter tensor, device-side address of a pinned host int64 or None): the compact action words are
+    written as ``seq << 32 | action`` for host polling; the optional flag is published behind system-wide fences."""
     compact = act_compact if isinstance(act_compact, int) else _p(act_compact)
     if notify is not None:
         _check(load().trxl_sample_actions_notify(_p(logits), _p(u), _p(forced), branch_array(branch_sizes), len(branch_sizes), act_ptr,

@@ -219,9 +219,11 @@ int trxl_rollout_store(float* table, float* table_pe, const float* pe_table, con
 int trxl_sample_actions(const float* logits, const float* u, const int64_t* forced_actions, const int32_t* branch_sizes,
                         int num_branches, int64_t* actions, int64_t act_stride, float* log_probs, int64_t logp_stride,
                         int64_t* actions_compact, int W, void* stream);
-/* Same, and once every action of the step is stored (e.g. in pinned host memory, see trxl_host_device_pointer) the kernel
- * increments *done_counter (device memory) and publishes the new value to *done_flag (pinned host memory) behind a system-wide
- * fence: the host learns that the step's actions are ready by polling plain memory, without a CUDA call.  W * num_branches <= 1024. */
+/* Same, with a completion signal the host can poll in plain memory, without a CUDA call: the kernel takes the launch sequence
+ * number seq = *done_counter + 1 (device memory; stored back), and every word of actions_compact (e.g. pinned host memory, see
+ * trxl_host_device_pointer) is written as seq << 32 | action -- when all W * num_branches words carry seq, the step's actions are
+ * there (8-byte stores are single-copy atomic; no system-wide fence on the step's critical path).  If done_flag != NULL (pinned
+ * host memory) seq is additionally published there behind system-wide fences.  W * num_branches <= 1024. */
 int trxl_sample_actions_notify(const float* logits, const float* u, const int64_t* forced_actions, const int32_t* branch_sizes,
                                int num_branches, int64_t* actions, int64_t act_stride, float* log_probs, int64_t logp_stride,
                                int64_t* actions_compact, int W, int64_t* done_counter, int64_t* done_flag, void* stream);
