@@ -242,7 +242,13 @@ def run_b200(args, cfg, name):
 
     # ---------------- e2e arm first (forks env processes before the big allocations) ----------------
     e2e = None
-    if not args.no_e2e:
+    e2e_skipped = None
+    # one Python process per env: beyond ~16 processes per host CPU (or the host's free memory at ~0.4 GB each) the arm measures
+    # the box, not the engine -- and c5's 512 processes got the whole bench OOM-killed on a 16-CPU box
+    n_procs = cfg["n_workers"] * max(1, world)
+    if not args.no_e2e and (n_procs > 16 * (os.cpu_count() or 1) or n_procs * 0.4 > 0.8 * _host_mem_gb()):
+        e2e_skipped = "%d env processes on %d host CPUs / %.0f GB free: e2e arm skipped" % (n_procs, os.cpu_count() or 1, _host_mem_gb())
+    if not args.no_e2e and e2e_skipped is None:
         tr = PPOTrainer(cfg, run_id="bench_e2e", device=device, summary_writer=False)
         sched = lambda u: (polynomial_decay(**_s(cfg["learning_rate_schedule"]), current_step=u),   # noqa: E731
                            polynomial_decay(**_s(cfg["clip_range_schedule"]), current_step=u),
@@ -331,6 +337,8 @@ def run_b200(args, cfg, name):
             "roofline": roofline, "e2e": e2e,
             "breakdown_s_per_update": {"rollout": tr.timers["rollout"] / args.steps, "train": tr.timers["train"] / args.steps},
             "last_stats": [float(x) for x in np.mean(np.array(stats, dtype=np.float64), axis=0)]}
+    if e2e_skipped:
+        line["e2e_skipped"] = e2e_skipped
     if world == 1 and not args.no_cpu_baseline:
         mb_full = W * T // cfg["n_mini_batch"]
         window_gb = mb_full * (env_cfg["max_episode_steps"] + t["memory_length"]) * t["num_blocks"] * t["embed_dim"] * 4 / 1e9
@@ -392,8 +400,8 @@ def attention_roofline(cfg, mb, prof, tiles, peaks, step_ms_total):
         exec_flops = tiles[2] / fwd_n * 128.0 * M * D * 2.0 * 2.0 * 3.0
         achieved = exec_flops / (avg * 1e-3) / 1e12
         peak = bf16_peak / 2.0
-        return {"kernel": "episode-grouped attention forward of one block (N=%d): tma_gemm_kernel<128> S=QK.X^T, attn_softmax_kernel, "
-                          "tma_gemm_kernel<128> ctx=P.X" % mb,
+        return {"kernel": "episode-grouped attention forward of one block (N=%d): grouped tma_gemm_kernel (256-wide tiles at M > 128) S=QK.X^T, "
+                          "attn_softmax_kernel, grouped tma_gemm_kernel ctx=P.X" % mb,
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": src + ": sustained dense bf16 / 2 (TF32 rate)",
                 "executed_flops_per_launch": exec_flops, "tiles_per_launch": tiles[2] / fwd_n, "avg_launch_ms": avg,

@@ -485,15 +485,16 @@ class PPOTrainer:
                                                      ctx["flat_mask"], ctx["flat_idx"] if roll is None else None,
                                                      sample_index=grp.rows[t], n=n, ws=grp.ws, out=grp.outs,
                                                      fused=None if roll is None else True)
-        # table[ep, step] = new memory (trainer.py:174), the same into `roll`, buffer.values[:, t] = value (trainer.py:186)
-        native.rollout_store(self._table, roll, None if roll is None else model._pe_table(), ep_dev, step_dev, new_mem,
-                             self.max_episode_length, self.num_blocks, self.embed_dim, value=value,
-                             value_dst=buf.values.data_ptr() + row0 * 4, value_stride=T)
         forced = None if self._forced_actions is None else self._forced_actions[t, lo:grp.hi]
         native.sample_actions(logits, ctx["uniforms"][t, lo:grp.hi], self.action_space_shape,
                               buf.actions.data_ptr() + row0 * nb * 8, T * nb, buf.log_probs.data_ptr() + row0 * nb * 4, T * nb,
                               grp.act_host_dptr if on_host else grp.act_dev, n, forced=forced,      # actions land in host memory
                               notify=(grp.done_counter, None) if (on_host and grp.use_flag) else None)    # seq-tagged action words
+        # (after the sampling kernel: the host waits for the actions only, so these stores overlap the env phase)
+        # table[ep, step] = new memory (trainer.py:174), the same into `roll`, buffer.values[:, t] = value (trainer.py:186)
+        native.rollout_store(self._table, roll, None if roll is None else model._pe_table(), ep_dev, step_dev, new_mem,
+                             self.max_episode_length, self.num_blocks, self.embed_dim, value=value,
+                             value_dst=buf.values.data_ptr() + row0 * 4, value_stride=T)
 
     def _host_src(self, grp, host_obs):
         """Device-side addresses of this group's slices of the pinned host buffers (observations, cursors)."""

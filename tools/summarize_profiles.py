@@ -94,7 +94,7 @@ def main():
         print("wrote kineto table")
     for rep, title in (("attn_%s" % args.round, "fused window attention fwd/bwd, training minibatch (N=2048, L=128, D=256, H=4)") if args.round == "r1" else
                        ("attn_%s" % args.round, "episode-grouped attention forward of block 0, c3 minibatch (N=2048, H=4, D=256, M=256): grouped "
-                                                "tma_gemm_kernel<128> S = QK.Xpe^T (K-major B from the strided table), then ctx = P.Xpe (MN-major B)"),
+                                                "tma_gemm_kernel<256> S = QK.Xpe^T (K-major B from the strided table), then ctx = P.Xpe (MN-major B)"),
                        ("tmagemm_%s" % args.round, "TMA + tcgen05 3xTF32 trunk GEMMs of one c3 minibatch step, in launch order: lin_hidden "
                                                    "(2048x256x3136), embedding (2048x256x256), Q projection, per-head K fold (batch 4, K=64)"),
                        ("sgemm_%s" % args.round, "SIMT sgemm launches: 1 rollout step (M=32) + 1 minibatch step (M=2048)"),
