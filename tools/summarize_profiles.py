@@ -99,8 +99,10 @@ def main():
                                                    "(2048x256x3136), embedding (2048x256x256), Q projection, per-head K fold (batch 4, K=64)"),
                        ("sgemm_%s" % args.round, "SIMT sgemm launches: 1 rollout step (M=32) + 1 minibatch step (M=2048)"),
                        ("tcgemm_%s" % args.round, "tcgen05 3xTF32 GEMM (opt-in), linear forward M=2048 N=256 K=256"),
-                       ("rollout_%s" % args.round, "one rollout step (W=32): tcgen05 conv1/2/3 forward + the cluster-per-sample fused trunk kernel "
-                                                   "(captured before the producers became fully asynchronous; two steps)"),
+                       ("rollout_%s" % args.round, "one rollout step (W=32, c3): tcgen05 conv1 / conv2 / conv3 forward (conv2, conv3 with cluster "
+                                                   "split-K 4) + the cluster-per-sample fused trunk kernel.  Cold caches under the profiler: the "
+                                                   "fused kernel reads its 23 MB of weights from DRAM here (148 us) and from L2 in the replayed "
+                                                   "graph (99 us, profiles/%s_kineto_update_c3.txt)" % args.round),
                        ("tcconv_%s" % args.round, "tcgen05 3xTF32 implicit-GEMM CNN encoder, one training minibatch (N=2048, 4x84x84): conv1/2/3 "
                                                   "forward, wgrad3, dgrad3, wgrad2, dgrad2 x4 parity classes, wgrad1 (launch order)")):
         p = os.path.join(args.src, rep + ".ncu-rep")
