@@ -59,7 +59,9 @@ __global__ void attn_ranges_kernel(const unsigned char* __restrict__ mask, const
     }
 }
 
-// in place: S (rows, ld) energies over all slots -> P: softmax over [lo, lo+cnt) of S / scale, zero elsewhere.  One warp per row.
+// in place: S (rows, ld) energies over all slots -> P: softmax over [lo, lo+cnt) of S / scale, zero elsewhere.  One warp per row;
+// the row lives in registers between the passes (PL values per lane, M <= 32 PL): one read and one write of the matrix.
+template <int PL>
 __global__ void attn_softmax_kernel(float* __restrict__ S, long long ld, int M, const int4* __restrict__ ranges, int H, int rows,
                                     float scale, int L) {
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -73,27 +75,34 @@ __global__ void attn_softmax_kernel(float* __restrict__ S, long long ld, int M, 
         for (int t = lane; t < M; t += 32) row[t] = (t >= lo && t < hi) ? u : 0.f;
         return;
     }
+    float e[PL];
     float m = -INFINITY;
-    for (int t = lo + lane; t < hi; t += 32) {
-        const float e = __fdiv_rn(row[t], scale);
-        row[t] = e;
-        m = fmaxf(m, e);
+#pragma unroll
+    for (int i = 0; i < PL; ++i) {
+        const int t = lane + 32 * i;
+        e[i] = (t >= lo && t < hi) ? __fdiv_rn(row[t], scale) : -INFINITY;
+        m = fmaxf(m, e[i]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
     float s = 0.f;
-    for (int t = lo + lane; t < hi; t += 32) {
-        const float p = __expf(row[t] - m);
-        row[t] = p;
-        s += p;
+#pragma unroll
+    for (int i = 0; i < PL; ++i) {
+        e[i] = __expf(e[i] - m);                  // slots outside the window hold -inf -> 0
+        s += e[i];
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
     const float inv = 1.f / s;
-    for (int t = lane; t < M; t += 32) row[t] = (t >= lo && t < hi) ? row[t] * inv : 0.f;
+#pragma unroll
+    for (int i = 0; i < PL; ++i) {
+        const int t = lane + 32 * i;
+        if (t < M) row[t] = e[i] * inv;
+    }
 }
 
 // in place: dP (rows, ld) -> dS = P (dP - sum_t P dP) / scale on the window, zero elsewhere (and everywhere for uniform rows)
+template <int PL>
 __global__ void attn_dscore_kernel(float* __restrict__ dP, const float* __restrict__ P, long long ld, int M,
                                    const int4* __restrict__ ranges, int H, int rows, float inv_scale) {
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -103,14 +112,27 @@ __global__ void attn_dscore_kernel(float* __restrict__ dP, const float* __restri
     float* d = dP + (long long)r * ld;
     const float* p = P + (long long)r * ld;
     const int lo = rg.x, hi = rg.x + rg.y;
-    float dot = 0.f;
-    if (!rg.z) {
-        for (int t = lo + lane; t < hi; t += 32) dot = fmaf(p[t], d[t], dot);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL, dot, o);
+    if (rg.z) {
+        for (int t = lane; t < M; t += 32) d[t] = 0.f;
+        return;
     }
-    for (int t = lane; t < M; t += 32)
-        d[t] = (!rg.z && t >= lo && t < hi) ? p[t] * (d[t] - dot) * inv_scale : 0.f;
+    float pv[PL], dv[PL];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < PL; ++i) {
+        const int t = lane + 32 * i;
+        const bool in = t >= lo && t < hi;
+        pv[i] = in ? p[t] : 0.f;
+        dv[i] = in ? d[t] : 0.f;
+        dot = fmaf(pv[i], dv[i], dot);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL, dot, o);
+#pragma unroll
+    for (int i = 0; i < PL; ++i) {
+        const int t = lane + 32 * i;
+        if (t < M) d[t] = pv[i] * (dv[i] - dot) * inv_scale;      // pv = 0 outside the window
+    }
 }
 
 // out[e, m, b, :] = table[e, m, b, :] + pe[m, :]
@@ -175,7 +197,8 @@ int tile_n(int n) { return n > 128 ? 256 : (n > 64 ? 128 : (n > 32 ? 64 : 32)); 
 long long attn_tc_row_floats(long long slots) { return (slots + 3) / 4 * 4; }
 
 bool attn_tc_supported(int D, int H, long long slots, int B) {
-    return H > 0 && 128 % H == 0 && D % 4 == 0 && D >= 4 && slots >= 1 && ((long long)B * D) % 4 == 0;
+    // (slots <= 1024: the row kernels keep a row of energies in registers, 32 values per lane)
+    return H > 0 && 128 % H == 0 && D % 4 == 0 && D >= 4 && slots >= 1 && slots <= 1024 && ((long long)B * D) % 4 == 0;
 }
 
 int attn_tc_ranges(const unsigned char* mask, const long long* win_index, const long long* ep_index, const long long* sample_index,
@@ -218,7 +241,8 @@ int attn_tc_forward(const AttnTcArgs& a, const float* qk, float* P, float* ctx, 
     // (a masked softmax fused into this GEMM's epilogue -- straight from the TMEM accumulators, row halves exchanged between the two
     // warps of a lane quarter -- was measured SLOWER, 83.5 vs 76.3 us per forward on the same box: a CTA's 8 epilogue warps
     // serialise what this kernel spreads over the whole GPU; likewise for the dscore pass, 108 vs 71 us)
-    attn_softmax_kernel<<<trxl_cdiv(rows, 8), 256, 0, st>>>(P, ld, (int)a.slots, a.ranges, a.H, rows, a.scale, a.L);
+    if (a.slots <= 256) attn_softmax_kernel<8><<<trxl_cdiv(rows, 8), 256, 0, st>>>(P, ld, (int)a.slots, a.ranges, a.H, rows, a.scale, a.L);
+    else attn_softmax_kernel<32><<<trxl_cdiv(rows, 8), 256, 0, st>>>(P, ld, (int)a.slots, a.ranges, a.H, rows, a.scale, a.L);
     TRXL_CHECK_LAUNCH("attention_softmax");
     GemmArgs g2 = grouped_args(a, P, ld, (int)a.slots, a.D, 0, ctx, a.D);               // ctx = P . Xpe      (B MN-major: k = slot)
     TRXL_PROPAGATE(trxl_tc_gemm(g2, tile_n(a.D), st));
@@ -234,7 +258,8 @@ int attn_tc_backward(const AttnTcArgs& a, const float* P, const float* dctx, flo
     trxl_prof_begin(3, a.N, st);
     trxl_prof_aux(3, a.n_tiles);
     TRXL_PROPAGATE(trxl_tc_gemm(g1, tile_n((int)a.slots), st));
-    attn_dscore_kernel<<<trxl_cdiv(rows, 8), 256, 0, st>>>(scratch, P, ld, (int)a.slots, a.ranges, a.H, rows, 1.f / a.scale);
+    if (a.slots <= 256) attn_dscore_kernel<8><<<trxl_cdiv(rows, 8), 256, 0, st>>>(scratch, P, ld, (int)a.slots, a.ranges, a.H, rows, 1.f / a.scale);
+    else attn_dscore_kernel<32><<<trxl_cdiv(rows, 8), 256, 0, st>>>(scratch, P, ld, (int)a.slots, a.ranges, a.H, rows, 1.f / a.scale);
     TRXL_CHECK_LAUNCH("attention_dscore");
     GemmArgs g2 = grouped_args(a, scratch, ld, (int)a.slots, a.D, 0, dqk, a.D);         // dqk = dS . Xpe
     TRXL_PROPAGATE(trxl_tc_gemm(g2, tile_n(a.D), st));

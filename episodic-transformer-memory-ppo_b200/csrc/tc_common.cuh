@@ -60,7 +60,7 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 // K-major SWIZZLE_128B (layout type 2): atom = 8 rows x 128 bytes (32 tf32 along K), the 16-byte chunk c of row r stored at
 //   chunk position c ^ (r & 7) (Swizzle<3,4,3>; 1024-byte aligned base); SBO = distance between 8-row groups; one tf32 MMA
 //   (K = 8 = 32 bytes) starts 32*k bytes into the 128-byte span.
-constexpr uint32_t LAYOUT_NONE = 0, LAYOUT_SW128_BASE32B = 1, LAYOUT_SW128 = 2;
+constexpr uint32_t LAYOUT_NONE = 0, LAYOUT_SW128_BASE32B = 1, LAYOUT_SW128 = 2, LAYOUT_SW64 = 4;
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = LAYOUT_NONE) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);

@@ -40,12 +40,16 @@ namespace {
 
 using namespace tc;
 
-constexpr int TM_BM = 128, TM_BK = 32;
+constexpr int TM_BM = 128;
 constexpr int TM_CONV_WARPS = 8, TM_MMA_WARP = 8, TM_TMA_WARP = 9, TM_THREADS = 320;
-constexpr int A_TILE_BYTES = TM_BM * TM_BK * 4;      // 16 KB; K-major: 128 rows x 128 B; MN-major: 4 groups x (32 k-rows x 128 B)
-
-__host__ __device__ constexpr int tm_stage_bytes(int bn) { return 2 * A_TILE_BYTES + 2 * bn * TM_BK * 4; }
-__host__ __device__ constexpr int tm_stages(int bn) { return bn == 256 ? 2 : (bn == 128 ? 3 : (bn == 64 ? 4 : 5)); }
+// k-block depth BK (floats): 32 everywhere except the 256-wide tiles of the episode-grouped attention GEMMs, which use 16 -- at
+// BN = 256 a 32-deep stage is 96 KB, i.e. a ring of two, and the kernel ran at 4.8 k clocks per k-block against the 2.6 k of its
+// shared-memory traffic (TMA latency + conversion + MMAs of one stage serialised); 16-deep stages make it a ring of four.
+__host__ __device__ constexpr int tm_bk(int bn) { return bn == 256 ? 16 : 32; }
+// A tile: K-major 128 rows x (4 BK) bytes (SWIZZLE_128B at BK = 32, SWIZZLE_64B at BK = 16); MN-major: 4 groups x (BK k-rows x 128 B)
+__host__ __device__ constexpr int tm_a_bytes(int bk) { return TM_BM * bk * 4; }
+__host__ __device__ constexpr int tm_stage_bytes(int bn) { return 2 * tm_a_bytes(tm_bk(bn)) + 2 * bn * tm_bk(bn) * 4; }
+__host__ __device__ constexpr int tm_stages(int bn) { return bn == 256 ? 4 : (bn == 128 ? 3 : (bn == 64 ? 4 : 5)); }
 __host__ __device__ constexpr int tm_tmem_cols(int bn) { return bn == 32 ? 128 : (bn == 64 ? 256 : 512); }
 // BN = 256 (the episode-grouped attention GEMMs: one CTA covers all 256 slots / all 256 embedding columns of a tile) leaves
 // room for two accumulators only: every hi*hi product goes to the first, the cross terms to the second.  The hi*hi chain
@@ -98,6 +102,7 @@ template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(TM_THREADS, 1) tma_gemm_kernel(const __grid_constant__ TmaGemmParams p) {
     extern __shared__ __align__(1024) unsigned char tm_smem[];
     constexpr int STAGES = tm_stages(BN);
+    constexpr int TM_BK = tm_bk(BN), A_TILE_BYTES = tm_a_bytes(TM_BK), GRP_BYTES = TM_BK * 128;    // GRP: 32 m/n x BK k, MN-major
     constexpr int B_TILE_BYTES = BN * TM_BK * 4;
     constexpr int STAGE_BYTES = tm_stage_bytes(BN);
     unsigned char* tiles = tm_smem + ((1024u - (smem_u32(tm_smem) & 1023u)) & 1023u);       // swizzled layouts need an aligned base
@@ -165,13 +170,13 @@ __global__ void __launch_bounds__(TM_THREADS, 1) tma_gemm_kernel(const __grid_co
                 mbar_arrive_expect_tx(&full[s], A_TILE_BYTES + B_TILE_BYTES);
                 if (A_MN) {
 #pragma unroll
-                    for (int grp = 0; grp < TM_BM / 32; ++grp) tma_load_3d(a_dst + grp * 4096, &p.ta, &full[s], m0 + 32 * grp, k0, b);
+                    for (int grp = 0; grp < TM_BM / 32; ++grp) tma_load_3d(a_dst + grp * GRP_BYTES, &p.ta, &full[s], m0 + 32 * grp, k0, b);
                 } else {
                     tma_load_3d(a_dst, &p.ta, &full[s], k0, m0, b);
                 }
                 if (B_MN) {
 #pragma unroll
-                    for (int grp = 0; grp < BN / 32; ++grp) tma_load_3d(b_dst + grp * 4096, &p.tb, &full[s], n0 + 32 * grp, k0, b_of_B);
+                    for (int grp = 0; grp < BN / 32; ++grp) tma_load_3d(b_dst + grp * GRP_BYTES, &p.tb, &full[s], n0 + 32 * grp, k0, b_of_B);
                 } else {
                     tma_load_3d(b_dst, &p.tb, &full[s], k0, n0, b_of_B);
                 }
@@ -183,9 +188,11 @@ __global__ void __launch_bounds__(TM_THREADS, 1) tma_gemm_kernel(const __grid_co
         // K-major SW128: a k-step is 32 bytes further along the 128-byte span; MN-major SW128_BASE32B: 8 k-rows = 1024 bytes.
         constexpr uint32_t idesc = idesc_tf32(TM_BM, BN, A_MN, B_MN);
         constexpr uint32_t A_KSTEP = (A_MN ? 1024 : 32) >> 4, B_KSTEP = (B_MN ? 1024 : 32) >> 4;
-        const uint64_t da0 = A_MN ? make_desc(smem_base, 4096, 512, LAYOUT_SW128_BASE32B) : make_desc(smem_base, 16, 1024, LAYOUT_SW128);
-        const uint64_t db0 = B_MN ? make_desc(smem_base + 2 * A_TILE_BYTES, 4096, 512, LAYOUT_SW128_BASE32B)
-                                  : make_desc(smem_base + 2 * A_TILE_BYTES, 16, 1024, LAYOUT_SW128);
+        // K-major rows are 4 BK bytes wide: SWIZZLE_128B (8-row groups 1024 B apart) at BK = 32, SWIZZLE_64B (512 B apart) at BK = 16
+        constexpr uint32_t KM_LAYOUT = TM_BK == 32 ? LAYOUT_SW128 : LAYOUT_SW64, KM_SBO = TM_BK == 32 ? 1024 : 512;
+        const uint64_t da0 = A_MN ? make_desc(smem_base, GRP_BYTES, 512, LAYOUT_SW128_BASE32B) : make_desc(smem_base, 16, KM_SBO, KM_LAYOUT);
+        const uint64_t db0 = B_MN ? make_desc(smem_base + 2 * A_TILE_BYTES, GRP_BYTES, 512, LAYOUT_SW128_BASE32B)
+                                  : make_desc(smem_base + 2 * A_TILE_BYTES, 16, KM_SBO, KM_LAYOUT);
         for (int kb = 0; kb < kblocks; ++kb) {
             const int s = kb % STAGES;
             mbar_wait(&ready[s], (kb / STAGES) & 1);
@@ -262,8 +269,12 @@ __global__ void __launch_bounds__(TM_THREADS, 1) tma_gemm_kernel(const __grid_co
         fence_after_sync();
         const int quarter = warp & 3;
         const int m = m0 + quarter * 32 + lane;
-        if (BN <= 128 && g.cluster_reduce) {
-            // ---- split-K inside a cluster, part 1: this CTA's partial tile parked in its (now idle) stage ring ----
+        // wide tiles without split-K leave through shared memory as well: the direct epilogue below stores thread-per-row (a warp
+        // instruction touches 32 different rows, 16 bytes each), which for a 128 x 256 tile is ~8 k sector writes per CTA
+        const bool coalesced = BN == 256 && g.ksplit == 1 && g.batch == 1 && !g.accumulate && !g.R && g.ldc % 4 == 0 &&
+                               ((((uintptr_t)g.C) & 15) == 0);
+        if ((BN <= 128 && g.cluster_reduce) || coalesced) {
+            // ---- split-K inside a cluster, part 1 / coalesced epilogue: the tile parked in the (now idle) stage ring ----
             constexpr int PSTRIDE = BN + 4;
             static_assert(TM_BM * PSTRIDE * 4 <= STAGES * STAGE_BYTES, "a parked tile must fit the stage ring");
             float* prow = reinterpret_cast<float*>(tiles) + (quarter * 32 + lane) * PSTRIDE;
@@ -273,6 +284,35 @@ __global__ void __launch_bounds__(TM_THREADS, 1) tma_gemm_kernel(const __grid_co
                 load_accumulators3<BN>(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(j * 32), v);
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(prow + j * 32 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+            if (coalesced) {
+                // 64 threads per row, four rows per pass: every warp instruction writes 512 contiguous bytes of one row
+                asm volatile("bar.sync 1, %0;" ::"n"(TM_CONV_WARPS * 32) : "memory");       // the eight epilogue warps only
+                const float* park = reinterpret_cast<const float*>(tiles);
+                const int c4 = (threadIdx.x & (BN / 4 - 1)) * 4, n = n0 + c4;
+                float bv[4] = {0.f, 0.f, 0.f, 0.f};
+                if (g.bias) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) if (n + q < g.N) bv[q] = __ldg(g.bias + n + q);
+                }
+                for (int r = threadIdx.x / (BN / 4); r < TM_BM; r += TM_CONV_WARPS * 32 / (BN / 4)) {
+                    const int mr = m0 + r;
+                    if (mr >= m_end) break;
+                    const float4 pv = *reinterpret_cast<const float4*>(park + r * PSTRIDE + c4);
+                    float x[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        x[q] = fmaf(x[q], g.alpha, bv[q]);
+                        if (g.relu) x[q] = fmaxf(x[q], 0.f);
+                    }
+                    float* dst = g.C + (long long)mr * g.ldc + n;
+                    if (n + 3 < g.N) {
+                        *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) if (n + q < g.N) dst[q] = x[q];
+                    }
+                }
             }
         } else {
         float* __restrict__ C = g.C + (long long)b * g.sC;
@@ -410,16 +450,16 @@ EncodeTiledFn encode_fn() {
 }
 
 struct MapKey {
-    const void* base; long long inner, outer, batch, ld, sb; int box_outer, mn;
+    const void* base; long long inner, outer, batch, ld, sb; int box_inner, box_outer, mn;
     bool operator==(const MapKey& o) const {
         return base == o.base && inner == o.inner && outer == o.outer && batch == o.batch && ld == o.ld && sb == o.sb &&
-               box_outer == o.box_outer && mn == o.mn;
+               box_inner == o.box_inner && box_outer == o.box_outer && mn == o.mn;
     }
 };
 struct MapKeyHash {
     size_t operator()(const MapKey& k) const {
         size_t h = reinterpret_cast<size_t>(k.base);
-        for (long long v : {k.inner, k.outer, k.batch, k.ld, k.sb, (long long)k.box_outer, (long long)k.mn})
+        for (long long v : {k.inner, k.outer, k.batch, k.ld, k.sb, (long long)k.box_inner, (long long)k.box_outer, (long long)k.mn})
             h = h * 1000003u ^ (size_t)v;
         return h;
     }
@@ -428,12 +468,13 @@ std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 std::mutex g_maps_mutex;
 
 // rank-3 map over a row-major operand: {inner (contiguous), outer (stride ld floats), batch (stride sb floats)};
-// box {32, box_outer, 1}.  mn = 1: MN-major operand (SWIZZLE_128B_ATOM_32B), else K-major (SWIZZLE_128B).
-int get_map(const float* base, long long inner, long long outer, long long batch, long long ld, long long sb, int box_outer, int mn,
-            CUtensorMap* out) {
+// box {box_inner, box_outer, 1}.  mn = 1: MN-major operand (32-wide boxes, SWIZZLE_128B_ATOM_32B), else K-major: SWIZZLE_128B for
+// 32-deep k-blocks (128-byte rows), SWIZZLE_64B for 16-deep ones.
+int get_map(const float* base, long long inner, long long outer, long long batch, long long ld, long long sb, int box_inner,
+            int box_outer, int mn, CUtensorMap* out) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return TRXL_ERR_UNSUPPORTED;
-    MapKey key{base, inner, outer, batch, ld, sb, box_outer, mn};
+    MapKey key{base, inner, outer, batch, ld, sb, box_inner, box_outer, mn};
     {
         std::lock_guard<std::mutex> lock(g_maps_mutex);
         auto it = g_maps.find(key);
@@ -441,11 +482,12 @@ int get_map(const float* base, long long inner, long long outer, long long batch
     }
     cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)(batch > 0 ? batch : 1)};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 4, batch > 1 ? (cuuint64_t)sb * 4 : (cuuint64_t)ld * 4 * (cuuint64_t)outer};
-    cuuint32_t box[3] = {32, (cuuint32_t)box_outer, 1};
+    cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUtensorMap m;
     CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : (box_inner == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B),
                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return TRXL_ERR_UNSUPPORTED;
     {
@@ -498,7 +540,7 @@ int launch_orient(const TmaGemmParams& p, cudaStream_t st) {
 
 int trxl_tensor_map(const float* base, long long inner, long long outer, long long batch, long long ld, long long sb, int box_outer,
                     int mn, CUtensorMap* out) {
-    return get_map(base, inner, outer, batch, ld, sb, box_outer, mn, out);
+    return get_map(base, inner, outer, batch, ld, sb, 32, box_outer, mn, out);
 }
 
 // Can the TMA path take these operands?  (16-byte aligned bases, leading dimensions / batch strides in whole 16-byte units)
@@ -535,12 +577,13 @@ int trxl_tc_gemm(const GemmArgs& g, int bn, cudaStream_t st) {
     if (debug < 0) { const char* e = getenv("TRXL_TC_DEBUG"); debug = e ? atoi(e) : 0; }
     p.g.debug = debug;
     int rc;
-    if (g.a_kc) rc = get_map(g.A, g.K, g.M, g.batch, g.lda, g.sA, TM_BM, 0, &p.ta);       // (M, K) row-major: inner = k
-    else rc = get_map(g.A, g.M, g.K, g.batch, g.lda, g.sA, 32, 1, &p.ta);                  // (K, M) row-major: inner = m
+    const int bk = tm_bk(bn);
+    if (g.a_kc) rc = get_map(g.A, g.K, g.M, g.batch, g.lda, g.sA, bk, TM_BM, 0, &p.ta);   // (M, K) row-major: inner = k
+    else rc = get_map(g.A, g.M, g.K, g.batch, g.lda, g.sA, 32, bk, 1, &p.ta);              // (K, M) row-major: inner = m
     if (rc != TRXL_OK) return rc;
     const long long nb = g.tiles ? g.b_batch : g.batch;
-    if (g.b_kc) rc = get_map(g.B, g.K, g.N, nb, g.ldb, g.sB, bn, 0, &p.tb);                // (N, K) row-major: inner = k
-    else rc = get_map(g.B, g.N, g.K, nb, g.ldb, g.sB, 32, 1, &p.tb);                       // (K, N) row-major: inner = n
+    if (g.b_kc) rc = get_map(g.B, g.K, g.N, nb, g.ldb, g.sB, bk, bn, 0, &p.tb);            // (N, K) row-major: inner = k
+    else rc = get_map(g.B, g.N, g.K, nb, g.ldb, g.sB, 32, bk, 1, &p.tb);                   // (K, N) row-major: inner = n
     if (rc != TRXL_OK) return rc;
     if (bn == 256) return launch_orient<256>(p, st);
     if (bn == 128) return launch_orient<128>(p, st);
