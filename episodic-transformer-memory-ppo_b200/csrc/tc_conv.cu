@@ -37,7 +37,7 @@ constexpr int BM = 128, BK = TCG_BK, THREADS = 160;
 // The tensor core adds into the TMEM accumulator with truncation, so the rounding error grows with the length of the
 // accumulation chain.  Three accumulators keep it at fp32-SIMT level: hi*hi products alternate between two of them (halving
 // the chain that carries the magnitude), the ~2^-11 smaller cross terms go to the third, and the epilogue adds them (RN).
-__host__ __device__ constexpr int tmem_cols(int bn) { return bn == 32 ? 128 : 256; }
+__host__ __device__ constexpr int tmem_cols(int bn) { return bn == 32 ? 128 : (bn == 64 ? 256 : 512); }
 
 struct GatherArgs {
     TcgGather g;
@@ -52,6 +52,7 @@ struct GatherArgs {
     const float* mask;                          // optional image with the output geometry: result kept where mask > 0
     float* out_hi; float* out_lo; float* out_plain;     // any may be null
     float* out_feat; int feat_P;                        // optional: feat[n, c * P + p] = result[(n, p), c] (dense forward rows only)
+    int classes;                                        // 1: the N columns are 2x2 parity classes x 32 channels (tcg_plan_dgrad2_merged)
     long long M;
     long long* trace;                                   // debug (TRXL_CONV_TRACE): CTA 0's SM clock at phase boundaries
 };
@@ -98,14 +99,14 @@ __global__ void __launch_bounds__((PW + 1) * 32, STAGES == 2 ? 2 : 1) tc_conv_ga
     extern __shared__ __align__(1024) unsigned char tcc_smem[];
     constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     constexpr int PSTRIDE = BN + 4;                          // floats per parked row (the pad keeps float4 accesses conflict-free)
-    static_assert(BM * PSTRIDE * 4 <= STAGE_BYTES, "a parked tile must fit one stage");
+    static_assert(2 * BM * PSTRIDE * 4 <= STAGES * STAGE_BYTES, "a parked tile and the finished copy must fit the stage ring");
     unsigned char* tiles = tcc_smem + ((1024u - (smem_u32(tcc_smem) & 1023u)) & 1023u);      // swizzled layouts need an aligned base
     uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-    float* park = reinterpret_cast<float*>(tiles);                           // [BM][PSTRIDE] partial tile (stage 0)
-    float* fin = reinterpret_cast<float*>(tiles + STAGE_BYTES);              // [rows][PSTRIDE] finished values (stage 1; out_feat only)
+    float* park = reinterpret_cast<float*>(tiles);                           // [BM][PSTRIDE] partial tile (the idle stage ring)
+    float* fin = park + BM * PSTRIDE;                                        // [rows][PSTRIDE] finished values (out_feat only)
     __shared__ int s_tapoff[TCG_MAX_KB], s_dy[TCG_MAX_KB], s_dx[TCG_MAX_KB];
     __shared__ long long s_rowbase[BM], s_rowdst[BM];       // float offsets of a row's anchor pixel / output pixel (-1: past M)
     __shared__ int s_rowyx[BM];                             // anchor pixel (y << 16 | x)
@@ -276,7 +277,23 @@ __global__ void __launch_bounds__((PW + 1) * 32, STAGES == 2 ? 2 : 1) tc_conv_ga
         const uint32_t park_addr = smem_u32(park);
         for (int rl = threadIdx.x >> 3; rl < rows_mine; rl += NT / 8) {
             const int r = row_lo + rl;
-            const long long dst = s_rowdst[r];
+            long long dst = s_rowdst[r];
+            int oc0 = c0;                                      // first output channel of this thread's columns
+            if (a.classes && dst >= 0) {                       // columns = (py, px, channel): the pixel of this thread's class
+                const int cls = c0 >> 5, py = cls >> 1, px = cls & 1;
+                const int yx = s_rowyx[r];
+                if (2 * (yx >> 16) + py >= a.s.out_h || 2 * (yx & 0xffff) + px >= a.s.out_w) dst = -1;
+                else dst += ((long long)py * a.s.out_w + px) * a.s.out_c;
+                oc0 = c0 & 31;
+            }
+            // the ReLU-mask values of the row first: their global-memory latency overlaps the partial sums below (issued inside the
+            // store loop they serialised into CPT / 4 round trips per row, which a lone CTA per SM cannot hide)
+            float4 mk4[CPT / 4];
+#pragma unroll
+            for (int q = 0; q < CPT; q += 4) {
+                mk4[q / 4] = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (a.mask && dst >= 0) mk4[q / 4] = __ldg(reinterpret_cast<const float4*>(a.mask + dst + oc0 + q));
+            }
             float x[CPT];
 #pragma unroll
             for (int q = 0; q < CPT; ++q) x[q] = 0.f;
@@ -303,8 +320,7 @@ __global__ void __launch_bounds__((PW + 1) * 32, STAGES == 2 ? 2 : 1) tc_conv_ga
             float hi[CPT], lo[CPT];
 #pragma unroll
             for (int q = 0; q < CPT; q += 4) {
-                float4 mk = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (a.mask && dst >= 0) mk = *reinterpret_cast<const float4*>(a.mask + dst + c0 + q);
+                const float4 mk = mk4[q / 4];
                 const float mkv[4] = {mk.x, mk.y, mk.z, mk.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -315,9 +331,9 @@ __global__ void __launch_bounds__((PW + 1) * 32, STAGES == 2 ? 2 : 1) tc_conv_ga
                     split_tf32(t, hi[q + e], lo[q + e]);
                 }
                 if (dst >= 0) {
-                    if (a.out_hi) *reinterpret_cast<float4*>(a.out_hi + dst + c0 + q) = make_float4(hi[q], hi[q + 1], hi[q + 2], hi[q + 3]);
-                    if (a.out_lo) *reinterpret_cast<float4*>(a.out_lo + dst + c0 + q) = make_float4(lo[q], lo[q + 1], lo[q + 2], lo[q + 3]);
-                    if (a.out_plain) *reinterpret_cast<float4*>(a.out_plain + dst + c0 + q) = make_float4(x[q], x[q + 1], x[q + 2], x[q + 3]);
+                    if (a.out_hi) *reinterpret_cast<float4*>(a.out_hi + dst + oc0 + q) = make_float4(hi[q], hi[q + 1], hi[q + 2], hi[q + 3]);
+                    if (a.out_lo) *reinterpret_cast<float4*>(a.out_lo + dst + oc0 + q) = make_float4(lo[q], lo[q + 1], lo[q + 2], lo[q + 3]);
+                    if (a.out_plain) *reinterpret_cast<float4*>(a.out_plain + dst + oc0 + q) = make_float4(x[q], x[q + 1], x[q + 2], x[q + 3]);
                 }
                 if (a.out_feat) *reinterpret_cast<float4*>(fin + rl * PSTRIDE + c0 + q) = make_float4(x[q], x[q + 1], x[q + 2], x[q + 3]);
             }
@@ -706,7 +722,8 @@ int launch_gather_stages(cudaStream_t st, const GatherArgs& a) {
 template <int BN>
 int launch_gather(cudaStream_t st, const GatherArgs& a) {
     if (a.M <= 0) return TRXL_OK;
-    return trxl_cdiv(a.M, BM) <= 148 ? launch_gather_stages<BN, 4>(st, a) : launch_gather_stages<BN, 2>(st, a);
+    if constexpr (BN == 128) return launch_gather_stages<BN, 3>(st, a);      // 64 KB stages: one CTA per SM, ring of three
+    else return trxl_cdiv(a.M, BM) <= 148 ? launch_gather_stages<BN, 4>(st, a) : launch_gather_stages<BN, 2>(st, a);
 }
 template <int BN>
 int launch_wgrad(cudaStream_t st, WgradArgs a, int layer, int C, float* dw, const Ws& w) {
@@ -837,7 +854,18 @@ int tc_conv_backward(cudaStream_t st, float* const* g, int N, int C, int H, int 
     tcg_plan_forward(e, 2, wa.g, unused);
     wa.a_hi = w.y1[0]; wa.a_lo = w.y1[1]; wa.dy_hi = w.d2[0]; wa.dy_lo = w.d2[1]; wa.M = m2;
     TRXL_PROPAGATE(launch_wgrad<64>(st, wa, 2, C, g[2], w));
-    for (int cls = 0; cls < 4; ++cls) {
+    static int per_class = -1;                  // TRXL_CONV_DGRAD2_CLASSES=1: one launch per parity class (A/B timing)
+    if (per_class < 0) { const char* ev = getenv("TRXL_CONV_DGRAD2_CLASSES"); per_class = (ev && atoi(ev) > 0) ? 1 : 0; }
+    if (!per_class) {
+        // the four parity classes gather the same 2x2 neighbourhood: one GEMM, weights stacked along N (4 x 32 columns)
+        a = GatherArgs{};
+        tcg_plan_dgrad2_merged(e, a.g, a.s);
+        a.classes = 1;
+        a.a_hi = w.d2[0]; a.a_lo = w.d2[1]; a.b_hi = w.wd2[0]; a.b_lo = w.wd2[1]; a.mask = w.y1[0];
+        a.out_hi = w.d1[0]; a.out_lo = w.d1[1]; a.M = (long long)N * a.g.rh * a.g.rw;
+        TRXL_PROPAGATE(launch_gather<128>(st, a));
+    }
+    for (int cls = 0; cls < 4 && per_class; ++cls) {
         a = GatherArgs{};
         tcg_plan_dgrad2(e, cls >> 1, cls & 1, a.g, a.s);
         a.a_hi = w.d2[0]; a.a_lo = w.d2[1]; a.b_hi = w.wd2[0] + cls * 32 * 256; a.b_lo = w.wd2[1] + cls * 32 * 256; a.mask = w.y1[0];

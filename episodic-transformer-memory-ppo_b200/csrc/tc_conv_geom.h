@@ -106,6 +106,15 @@ inline void tcg_plan_dgrad2(const TcgEncoder& e, int py, int px, TcgGather& g, T
     s.out_h = e.h1; s.out_w = e.w1; s.out_c = 32; s.ostride = 2; s.oy0 = py; s.ox0 = px;
 }
 
+// All four parity classes at once: the pixels (2a + py, 2b + px), py, px in {0, 1}, gather the SAME 2x2 neighbourhood
+// {a - 1, a} x {b - 1, b} of dL/d(conv2 output) -- only the weights differ.  One GEMM with the four classes' weight matrices
+// stacked along N (4 x 32 columns): the gathered operand is fetched once instead of four times and the MMAs are 128 wide.
+// The scatter's (oy0, ox0) are those of class (0, 0); the epilogue adds the class offset and drops pixels outside the image.
+inline void tcg_plan_dgrad2_merged(const TcgEncoder& e, TcgGather& g, TcgScatter& s) {
+    tcg_plan_dgrad2(e, 0, 0, g, s);
+    g.rh = (e.h1 + 1) / 2; g.rw = (e.w1 + 1) / 2;
+}
+
 // ---- packed K-major weight matrices: element (row, k) -> index into the reference (oc, c, ky, kx) tensor, -1 = zero ----
 TCG_HD int tcg_wfwd_index(int layer, int C, int oc, int k) {
     if (layer == 1) {
