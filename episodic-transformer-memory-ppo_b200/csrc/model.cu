@@ -343,7 +343,7 @@ int model_forward(const trxl_model_config* c, const float* P, const ModelIO& io,
     TRXL_CHECK_ARG(P && io.feat && io.table && logits && value && out_mem, "model_forward: null pointer");
     if (ws == nullptr) {        // no workspace: inference-only fused path
         TRXL_CHECK_ARG(io.N > 0, "model_forward: N must be positive");
-        // pe_index == NULL on this path: the table's rows already carry their positional rows (trxl_memory_scatter_pe)
+        // pe_index == NULL on this path: the table's rows already carry their positional rows (trxl_rollout_store)
         TRXL_CHECK_ARG(c->pos_enc != TRXL_PE_RELATIVE || io.pe_table || !io.pe_index, "model_forward: relative PE needs pe_table");
         return model_forward_fused(c, L, P, io, logits, value, out_mem, st);
     }

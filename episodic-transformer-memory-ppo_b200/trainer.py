@@ -207,7 +207,7 @@ class PPOTrainer:
 
         # episode table + per-worker cursors
         self._table = None
-        self._table_roll = None         # rollout: table + positional rows, kept in step by memory_scatter_pe (fused forward only)
+        self._table_roll = None         # rollout: table + positional rows, kept in step by trxl_rollout_store (fused forward only)
         self._table_cap = 0
         self._ep_host = torch.arange(W, dtype=torch.long).pin_memory()      # table row of each worker's live episode
         self._step_host = self.worker_current_episode_step.pin_memory()
