@@ -1,4 +1,6 @@
 // extern "C" surface of libtrxlppo (declared in include/trxl_ppo.h).  Thin argument marshalling only.
+#include <mutex>
+#include <unordered_map>
 #include <math.h>
 #include <stdarg.h>
 #include <string.h>
@@ -23,6 +25,8 @@ void trxl_set_error(const char* fmt, ...) {
 }
 
 long long g_trxl_launches = 0;
+static std::unordered_map<void*, long long> g_graph_nodes;      // kernel / copy nodes of every instantiated graph
+static std::mutex g_graph_nodes_mutex;
 
 // ---- optional launch timing of the two attention kernels (bench.py roofline) ----
 namespace {
@@ -98,10 +102,17 @@ int trxl_graph_end(void* stream, void** graph_exec_out) {
         trxl_set_error("graph_end: capture failed: %s", cudaGetErrorString(e));
         return TRXL_ERR_CUDA;
     }
+    size_t nodes = 0;
+    cudaGraphGetNodes(graph, nullptr, &nodes);
     cudaGraphExec_t exec = nullptr;
     e = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) { trxl_set_error("graph_end: instantiate failed: %s", cudaGetErrorString(e)); return TRXL_ERR_CUDA; }
+    {
+        // trxl_launch_count() counted the captured launches once, at capture time; every replay adds the graph's node count
+        std::lock_guard<std::mutex> lock(g_graph_nodes_mutex);
+        g_graph_nodes[exec] = (long long)nodes;
+    }
     *graph_exec_out = exec;
     return TRXL_OK;
 }
@@ -109,10 +120,21 @@ int trxl_graph_launch(void* graph_exec, void* stream) {
     TRXL_CHECK_ARG(graph_exec, "graph_launch: null graph");
     cudaError_t e = cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(graph_exec), S(stream));
     if (e != cudaSuccess) { trxl_set_error("graph_launch: %s", cudaGetErrorString(e)); return TRXL_ERR_CUDA; }
+    {
+        std::lock_guard<std::mutex> lock(g_graph_nodes_mutex);
+        auto it = g_graph_nodes.find(graph_exec);
+        if (it != g_graph_nodes.end()) g_trxl_launches += it->second;
+    }
     return TRXL_OK;
 }
 int trxl_graph_destroy(void* graph_exec) {
-    if (graph_exec) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(graph_exec));
+    if (graph_exec) {
+        {
+            std::lock_guard<std::mutex> lock(g_graph_nodes_mutex);
+            g_graph_nodes.erase(graph_exec);
+        }
+        cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(graph_exec));
+    }
     return TRXL_OK;
 }
 // dst[r, :row_bytes] = src[r, :row_bytes] for strided rows (buffer[:, t] = x without a torch op inside a capture)

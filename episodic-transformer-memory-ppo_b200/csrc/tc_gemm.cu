@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) tma_gemm_kernel(const __grid_co
     int b_of_B = b;
     if (g.tiles) {                                    // grouped mode: this CTA's rows and B batch element come from the tile table
         const int4 t = g.tiles[blockIdx.y];
+        if (t.y == 0) return;                         // padding entry (tables padded to a fixed length for CUDA-graph replay)
         m0 = t.x; m_end = min(g.M, t.x + t.y); b_of_B = t.z;
     }
     const int k_begin = split * g.k_per_split;

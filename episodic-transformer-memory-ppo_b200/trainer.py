@@ -236,6 +236,10 @@ class PPOTrainer:
         for grp in self._groups + [self._whole]:
             grp.rows = self._rollout_rows[:, grp.lo:grp.hi].contiguous()
         self.use_cuda_graphs = os.environ.get("TRXL_NO_GRAPHS", "0") != "1"
+        # the optimiser step's two launch-dense segments (encoder + trunk forward; trunk + encoder backward: ~250 launches of
+        # 3-30 us) replayed as CUDA graphs: eager stream launches leave ~2.6 us between kernels, graph replays ~0.4 us
+        self.use_train_graphs = self.use_cuda_graphs and os.environ.get("TRXL_TRAIN_GRAPHS", "1") != "0"
+        self._train_graphs = {}
         self._capture_stream = None
         self._mapped = {}
         self._futex = None
@@ -901,15 +905,20 @@ class PPOTrainer:
             tiles.append(np.asarray(rows, dtype=np.int32).reshape(-1, 4))
             n_tiles.append(len(rows))
         idx_dev = torch.from_numpy(np.concatenate(sorted_idx)).to(self.device)
-        tiles_dev = torch.from_numpy(np.concatenate(tiles, axis=0)).to(self.device)
-        i0 = t0 = 0
-        for mb, idx, nt in zip(batches, sorted_idx, n_tiles):
+        # every minibatch's tile table padded with empty entries (rows = 0: the CTA exits) to one length that is stable across
+        # minibatches and updates, so that a captured optimiser step can be replayed: tiles <= rows / 128 + episodes
+        max_tiles = max(len(b.sample_index_cpu) for b in batches) * H // 128 + 1 + (grouping["n_episodes"] + 63) // 64 * 64
+        padded = np.zeros((len(batches), max_tiles, 4), dtype=np.int32)
+        for j, t in enumerate(tiles):
+            padded[j, :len(t)] = t
+        tiles_dev = torch.from_numpy(padded).to(self.device)
+        i0 = 0
+        for j, (mb, idx, nt) in enumerate(zip(batches, sorted_idx, n_tiles)):
             mb.sample_index = idx_dev[i0:i0 + len(idx)]
             mb.sample_index_cpu = torch.from_numpy(idx)
-            mb.groups = {"tiles": tiles_dev[t0:t0 + nt], "n_tiles": nt, "table_pe": grouping["table_pe"],
-                         "n_episodes": grouping["n_episodes"]}
+            mb.groups = {"tiles": tiles_dev[j, :nt], "n_tiles": nt, "table_pe": grouping["table_pe"],
+                         "n_episodes": grouping["n_episodes"], "tiles_padded": tiles_dev[j], "max_tiles": max_tiles, "slot": j}
             i0 += len(idx)
-            t0 += nt
 
     def _train_mini_batch(self, samples, learning_rate, clip_range, beta):
         """One optimiser step on one minibatch (trainer.py:258-323).  ``samples`` is either a ``MiniBatch``
@@ -937,6 +946,43 @@ class PPOTrainer:
             }
             self._train_state = {n: st}          # keep one size resident
         return st
+
+    def _train_segment(self, gstate, name, fn):
+        """Run one launch-dense segment of the optimiser step: eagerly (``gstate`` None, or the first step with a new key),
+        or as a CUDA-graph replay captured through the library's own graph API (the segment consists of libtrxlppo calls
+        only: no torch op, no allocation).  Returns what ``fn`` returned when it last ran on the host."""
+        if gstate is None:
+            return fn()
+        if gstate["warm"] < 2:                     # both segments of one step run eagerly before anything is captured
+            gstate["warm"] += 1
+            out = fn()
+            gstate.setdefault("ret", {})[name] = out
+            return out
+        g = gstate["graphs"].get(name)
+        if g is None:
+            cur = torch.cuda.current_stream()
+            if self._capture_stream is None:
+                self._capture_stream = torch.cuda.Stream(device=self.device)
+            cs = self._capture_stream
+            cs.wait_stream(cur)
+            try:
+                with torch.cuda.stream(cs):
+                    native.graph_begin(cs.cuda_stream)
+                    try:
+                        gstate.setdefault("ret", {})[name] = fn()
+                        g = native.graph_end(cs.cuda_stream)
+                    except Exception:
+                        native.graph_abort(cs.cuda_stream)
+                        raise
+                cur.wait_stream(cs)
+                gstate["graphs"][name] = g
+            except Exception as e:  # noqa: BLE001 -- capture is an optimisation; the eager path is the same kernels
+                torch.cuda.synchronize()
+                print("[trxl] CUDA-graph capture of the training step failed (%s); continuing with eager launches" % e)
+                self.use_train_graphs = False
+                return fn()
+        native.graph_launch(g)
+        return gstate["ret"][name]
 
     def _ppo_step(self, samples, learning_rate, clip_range, beta, stats_out, norms_out, advstats=None):
         """One optimiser step.  ``advstats`` = the (already all-reduced) {sum, sum of squares, count} of the minibatch's
@@ -979,7 +1025,7 @@ class PPOTrainer:
         # encoder (cuDNN) with autograd so its backward can be driven by d loss / d features
         tc_enc = model._visual and model._tc_encoder
         if tc_enc:
-            feat_g, feat = None, model.encode_train(obs, sidx, n)
+            feat_g, feat = None, None              # computed inside the forward segment below
         elif model._visual:
             with torch.enable_grad():
                 feat_g = model.encode(obs)
@@ -988,14 +1034,53 @@ class PPOTrainer:
             feat_g, feat = None, obs.reshape(n, -1)
         logits, value, out_mem = st["out"]
         groups = None
-        if isinstance(samples, MiniBatch) and samples.groups is not None:
+        grouped = isinstance(samples, MiniBatch) and samples.groups is not None
+        # CUDA-graph replay of the two launch-dense segments: needs every address in them to be the same from one minibatch
+        # to the next, so the row indices and the (padded) tile table are copied to fixed staging buffers first.  While the
+        # library's event timers are on (bench.py's attention timing) the first minibatch of every epoch stays eager: events
+        # cannot be recorded inside a captured graph.
+        gstate = None
+        if getattr(self, "use_train_graphs", False) and grouped and tc_enc and \
+                not (native.profiling() and samples.groups.get("slot") == 0):
+            gr = samples.groups
+            if st.get("sidx_stage") is None or st["tiles_stage"].shape[0] != gr["max_tiles"]:
+                st["sidx_stage"] = torch.empty(n, dtype=torch.long, device=self.device)
+                st["tiles_stage"] = torch.empty((gr["max_tiles"], 4), dtype=torch.int32, device=self.device)
+            key = (n, gr["max_tiles"], gr["table_pe"].data_ptr(), table.data_ptr(), self._table_cap, model.flat_parameters().data_ptr(),
+                   obs.data_ptr(), st["ws"].data_ptr(), st["sidx_stage"].data_ptr(), st["tiles_stage"].data_ptr())
+            gstate = self._train_graphs.get(n)               # one state per minibatch size (a ragged last minibatch keeps its own)
+            if gstate is None or gstate["key"] != key:
+                for old in (gstate or {}).get("graphs", {}).values():
+                    native.graph_destroy(old)
+                gstate = self._train_graphs[n] = {"key": key, "warm": 0, "graphs": {}}
+            native.copy_async(sidx.data_ptr(), st["sidx_stage"].data_ptr(), n * 8)
+            native.copy_async(gr["tiles_padded"].data_ptr(), st["tiles_stage"].data_ptr(), gr["max_tiles"] * 16)
+            sidx = st["sidx_stage"]
+        if grouped:
             if st.get("ranges") is None:
                 st["ranges"] = torch.empty((n, 4), dtype=torch.int32, device=self.device)
-            native.attention_ranges(mask, win_index, ep_index, sidx, n, self.memory_length, st["ranges"])
             gr = samples.groups
-            groups = native.attn_groups(gr["table_pe"], gr["n_episodes"], gr["tiles"], gr["n_tiles"], st["ranges"])
-        native.model_forward(model._cfg, model.flat_parameters(), feat, table, table.shape[1], ep_index, win_index, mask,
-                             pe_index, sidx, model._pe_table(), n, st["ws"], logits, value, out_mem, groups=groups)
+            if gstate is not None:        # staged, padded table; the table's capacity as the (stable) episode bound
+                groups = native.attn_groups(gr["table_pe"], self._table_cap, st["tiles_stage"], gr["max_tiles"], st["ranges"])
+            else:
+                groups = native.attn_groups(gr["table_pe"], gr["n_episodes"], gr["tiles"], gr["n_tiles"], st["ranges"])
+
+        def forward_segment():
+            if grouped:
+                native.attention_ranges(mask, win_index, ep_index, sidx, n, self.memory_length, st["ranges"])
+            f = model.encode_train(obs, sidx, n) if tc_enc else feat
+            native.model_forward(model._cfg, model.flat_parameters(), f, table, table.shape[1], ep_index, win_index, mask,
+                                 pe_index, sidx, model._pe_table(), n, st["ws"], logits, value, out_mem, groups=groups)
+            return f
+
+        def backward_segment():
+            native.model_backward(model._cfg, model.flat_parameters(), model.flat_grads(), feat, table, table.shape[1], ep_index,
+                                  win_index, mask, pe_index, sidx, model._pe_table(), n, st["ws"], out_mem, st["dlogits"],
+                                  st["dvalue"], st["dfeat"], groups=groups)
+            if tc_enc:
+                model.encode_backward(n, obs.shape[-2], obs.shape[-1], st["dfeat"])
+
+        feat = self._train_segment(gstate, "fwd", forward_segment)
         if advstats is None:
             advstats = st["advstats"]
             native.adv_stats(adv, sidx, n, advstats)
@@ -1007,12 +1092,8 @@ class PPOTrainer:
         native.ppo_loss(logits, value, actions, old_logp, old_values, adv, sidx, advstats, self.action_space_shape, n,
                         clip_range, beta, cfg["value_loss_coefficient"], st["dlogits"], st["dvalue"], stats_dst,
                         st["loss_scratch"])
-        native.model_backward(model._cfg, model.flat_parameters(), model.flat_grads(), feat, table, table.shape[1], ep_index,
-                              win_index, mask, pe_index, sidx, model._pe_table(), n, st["ws"], out_mem, st["dlogits"],
-                              st["dvalue"], st["dfeat"], groups=groups)
-        if tc_enc:
-            model.encode_backward(n, obs.shape[-2], obs.shape[-1], st["dfeat"])
-        elif feat_g is not None:
+        self._train_segment(gstate, "bwd", backward_segment)
+        if not tc_enc and feat_g is not None:
             feat_g.backward(st["dfeat"])           # accumulates into the conv slices of the gradient arena
         if multi:
             self.dp.all_reduce_(model.flat_grads_with_tail())     # ONE collective per optimiser step: gradient arena + stats tail

@@ -235,8 +235,18 @@ def tc_gemm_launches():
     return int(load().trxl_tc_gemm_launches())
 
 
+_profiling = False
+
+
 def profile_enable(on):
+    global _profiling
     _check(load().trxl_profile_enable(int(bool(on))), "trxl_profile_enable")
+    _profiling = bool(on)
+
+
+def profiling():
+    """True while the library's event timers are on (they cannot record inside a captured graph)."""
+    return _profiling
 
 
 def profile_read(kind, min_samples=0):

@@ -120,6 +120,42 @@ def test_graph_replay_rollout_is_bit_identical_to_eager(ln, pe, gtrxl, tmp_path,
         tr.close(exit_process=False)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("ln", ["post", "pre"])
+def test_graph_replay_of_the_optimiser_step_is_bit_identical_to_eager(ln, tmp_path, monkeypatch):
+    """TRXL_TRAIN_GRAPHS: the optimiser step's forward and backward segments replayed as CUDA graphs (row indices and the
+    padded tile table staged at fixed addresses) against eager launches with the real tile counts: the parameters after
+    every update are bit-identical, and the graphs were actually captured and replayed."""
+    import trainer as trainer_mod
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setenv("TRXL_GROUPED_ATTENTION", "1")          # the small test minibatches would otherwise take the per-sample kernel
+    cfg = _cfg(transformer={"layer_norm": ln, "positional_encoding": "relative", "gtrxl": False})
+    trainers = []
+    for graphs in (True, False):
+        torch.manual_seed(7)
+        tr = trainer_mod.PPOTrainer(cfg, run_id="tg", device=torch.device(DEV), workers=_synthetic_workers(cfg), summary_writer=False)
+        tr.use_train_graphs = graphs
+        trainers.append(tr)
+    trainers[1].model.load_state_dict(trainers[0].model.state_dict())
+    for upd in range(3):
+        for tr in trainers:
+            torch.manual_seed(100 + upd)
+            tr._sample_training_data()
+            tr.buffer.prepare_batch_dict()
+        stats = []
+        for tr in trainers:
+            torch.manual_seed(200 + upd)
+            stats.append(tr._train_epochs(3e-4, 0.2, 1e-3)[0])
+        assert torch.equal(trainers[0].model.flat_parameters(), trainers[1].model.flat_parameters()), "update %d params" % upd
+        assert np.array_equal(np.asarray(stats[0]), np.asarray(stats[1])), "update %d statistics" % upd
+    states = list(trainers[0]._train_graphs.values())
+    assert trainers[0].use_train_graphs and states and all(set(st["graphs"]) == {"fwd", "bwd"} for st in states), \
+        "the graph path did not run"
+    assert not trainers[1]._train_graphs
+    for tr in trainers:
+        tr.close(exit_process=False)
+
+
 # ------------------------------------------------------------------------------------------------ (c) device feed vs workers
 class _ReplayEnv:
     """Environment that replays a SyntheticDeviceFeed's schedule (observations, rewards, episode ends) for one worker."""
