@@ -826,10 +826,10 @@ class PPOTrainer:
         norms = torch.zeros((n_steps, g + 2), dtype=torch.float32, device=self.device)
         i = 0
         grouping = self._begin_grouped_attention()
-        for _ in range(self.config["epochs"]):
+        for epoch in range(self.config["epochs"]):
             batches = list(self.buffer.mini_batch_generator())
             if grouping is not None:
-                self._group_epoch(batches, grouping)
+                self._group_epoch(batches, grouping, epoch)
             # advantage statistics of every minibatch of the epoch (the permutation is known up front): one small
             # all-reduce per epoch instead of one per optimiser step
             advstats = torch.zeros((len(batches), 3), dtype=torch.float64, device=self.device)
@@ -882,7 +882,7 @@ class PPOTrainer:
         return {"table_pe": table_pe, "n_episodes": int(table.shape[0]), "episode_of_row": episode_of_row,
                 "rows_per_tile": 128 // self.model.transformer.num_heads * self.model.transformer.num_heads}
 
-    def _group_epoch(self, batches, grouping):
+    def _group_epoch(self, batches, grouping, epoch=0):
         """Sort every minibatch of the epoch by episode (a minibatch is a set: the loss and its gradient do not depend on the
         order) and build its tile table {first (sample, head) row, rows, episode, 0}; one upload for the whole epoch."""
         H = self.model.transformer.num_heads
@@ -917,7 +917,7 @@ class PPOTrainer:
             mb.sample_index = idx_dev[i0:i0 + len(idx)]
             mb.sample_index_cpu = torch.from_numpy(idx)
             mb.groups = {"tiles": tiles_dev[j, :nt], "n_tiles": nt, "table_pe": grouping["table_pe"],
-                         "n_episodes": grouping["n_episodes"], "tiles_padded": tiles_dev[j], "max_tiles": max_tiles, "slot": j}
+                         "n_episodes": grouping["n_episodes"], "tiles_padded": tiles_dev[j], "max_tiles": max_tiles, "slot": j + epoch * len(batches)}
             i0 += len(idx)
 
     def _train_mini_batch(self, samples, learning_rate, clip_range, beta):
@@ -1037,7 +1037,7 @@ class PPOTrainer:
         grouped = isinstance(samples, MiniBatch) and samples.groups is not None
         # CUDA-graph replay of the two launch-dense segments: needs every address in them to be the same from one minibatch
         # to the next, so the row indices and the (padded) tile table are copied to fixed staging buffers first.  While the
-        # library's event timers are on (bench.py's attention timing) the first minibatch of every epoch stays eager: events
+        # library's event timers are on (bench.py's attention timing) the first minibatch of every update stays eager: events
         # cannot be recorded inside a captured graph.
         gstate = None
         if getattr(self, "use_train_graphs", False) and grouped and tc_enc and \
