@@ -98,6 +98,32 @@ def build_mask_table(memory_length):
     return torch.tril(torch.ones((memory_length, memory_length)), diagonal=-1)
 
 
+def group_minibatch_by_episode(sample_index, episode_of_row, num_heads):
+    """Host side of the episode-grouped attention: sort a minibatch's buffer rows by episode (stable) and cut them into tiles of at
+    most 128 (sample, head) rows that belong to ONE episode.  Returns (sorted rows (n,) int64, tiles (n_tiles, 4) int32 with
+    entries {first (sample, head) row, number of rows, episode, 0})."""
+    spt = 128 // num_heads                                           # samples per 128-row tile
+    ep = episode_of_row[sample_index]
+    order = np.argsort(ep, kind="stable")
+    idx, ep = sample_index[order], ep[order]
+    bounds = np.flatnonzero(np.diff(ep)) + 1
+    starts = np.concatenate(([0], bounds)).tolist() if len(ep) else []
+    ends = np.concatenate((bounds, [len(ep)])).tolist() if len(ep) else []
+    rows = []
+    for s0, s1 in zip(starts, ends):
+        e = int(ep[s0])
+        for r in range(s0, s1, spt):
+            rows.append((r * num_heads, (min(s1, r + spt) - r) * num_heads, e, 0))
+    return idx, np.asarray(rows, dtype=np.int32).reshape(-1, 4)
+
+
+def tile_table_length(rows, num_heads, n_episodes):
+    """Length every minibatch's tile table is padded to (empty entries have zero rows): an upper bound of the tile count --
+    an episode with r rows makes at most r * H / 128 + 1 tiles -- that only changes when the episode count crosses a multiple
+    of 64, so that a captured optimiser step stays replayable across minibatches and updates."""
+    return rows * num_heads // 128 + 1 + (n_episodes + 63) // 64 * 64
+
+
 def build_window_index_table(max_episode_length, memory_length):
     """(M, L) int64 window slots by episode step (trainer.py:88-90)."""
     if memory_length > max_episode_length:
@@ -886,28 +912,16 @@ class PPOTrainer:
         """Sort every minibatch of the epoch by episode (a minibatch is a set: the loss and its gradient do not depend on the
         order) and build its tile table {first (sample, head) row, rows, episode, 0}; one upload for the whole epoch."""
         H = self.model.transformer.num_heads
-        spt = 128 // H                                                   # samples per 128-row tile
         sorted_idx, tiles, n_tiles = [], [], []
         for mb in batches:
-            idx = mb.sample_index_cpu.numpy()
-            ep = grouping["episode_of_row"][idx]
-            order = np.argsort(ep, kind="stable")
-            idx, ep = idx[order], ep[order]
-            bounds = np.flatnonzero(np.diff(ep)) + 1
-            starts = np.concatenate(([0], bounds))
-            ends = np.concatenate((bounds, [len(ep)]))
-            rows = []
-            for s0, s1 in zip(starts.tolist(), ends.tolist()):
-                e = int(ep[s0])
-                for r in range(s0, s1, spt):
-                    rows.append((r * H, (min(s1, r + spt) - r) * H, e, 0))
+            idx, t = group_minibatch_by_episode(mb.sample_index_cpu.numpy(), grouping["episode_of_row"], H)
             sorted_idx.append(idx)
-            tiles.append(np.asarray(rows, dtype=np.int32).reshape(-1, 4))
-            n_tiles.append(len(rows))
+            tiles.append(t)
+            n_tiles.append(len(t))
         idx_dev = torch.from_numpy(np.concatenate(sorted_idx)).to(self.device)
         # every minibatch's tile table padded with empty entries (rows = 0: the CTA exits) to one length that is stable across
-        # minibatches and updates, so that a captured optimiser step can be replayed: tiles <= rows / 128 + episodes
-        max_tiles = max(len(b.sample_index_cpu) for b in batches) * H // 128 + 1 + (grouping["n_episodes"] + 63) // 64 * 64
+        # minibatches and updates, so that a captured optimiser step can be replayed
+        max_tiles = tile_table_length(max(len(b.sample_index_cpu) for b in batches), H, grouping["n_episodes"])
         padded = np.zeros((len(batches), max_tiles, 4), dtype=np.int32)
         for j, t in enumerate(tiles):
             padded[j, :len(t)] = t

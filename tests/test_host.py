@@ -347,3 +347,30 @@ def test_saved_model_loads_into_the_reference_model(tmp_path, obs_shape, ln, gtr
     np.testing.assert_allclose(new_mem.numpy(), g["new_mem"], atol=1e-5)
     lg = logits[0]
     np.testing.assert_allclose((lg - lg.logsumexp(-1, keepdim=True)).numpy(), g["logits"], atol=1e-5)
+
+
+@pytest.mark.parametrize("heads,n_rows,n_episodes", [(4, 2048, 70), (8, 500, 3), (1, 64, 64), (2, 129, 1)])
+def test_episode_grouping_tiles_cover_every_sample_once(heads, n_rows, n_episodes):
+    """Host side of the episode-grouped attention (trainer.group_minibatch_by_episode): the sorted minibatch is a permutation of
+    the input rows, every tile holds at most 128 (sample, head) rows of ONE episode, the tiles partition the rows in order, and
+    their number stays within the padded table length used for CUDA-graph replay."""
+    from trainer import group_minibatch_by_episode, tile_table_length
+    rng = np.random.default_rng(heads * 1000 + n_rows)
+    total = 5 * n_rows
+    episode_of_row = rng.integers(0, n_episodes, total).astype(np.int64)
+    sample_index = rng.permutation(total)[:n_rows].astype(np.int64)
+    idx, tiles = group_minibatch_by_episode(sample_index, episode_of_row, heads)
+    assert sorted(idx.tolist()) == sorted(sample_index.tolist())
+    ep_sorted = episode_of_row[idx]
+    assert np.all(np.diff(ep_sorted) >= 0)
+    assert tiles.dtype == np.int32 and tiles.shape[1] == 4
+    nxt = 0
+    for first, rows, ep, pad in tiles.tolist():
+        assert first == nxt and 0 < rows <= 128 and rows % heads == 0 and pad == 0
+        members = ep_sorted[first // heads:(first + rows) // heads]
+        assert np.all(members == ep)
+        nxt = first + rows
+    assert nxt == n_rows * heads
+    assert len(tiles) <= tile_table_length(n_rows, heads, n_episodes)
+    # the padded length only moves when the episode count crosses a multiple of 64
+    assert tile_table_length(n_rows, heads, 65) == tile_table_length(n_rows, heads, 128)
